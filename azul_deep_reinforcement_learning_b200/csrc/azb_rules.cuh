@@ -1,0 +1,687 @@
+// azb_rules.cuh -- the Azul rules on the bit-packed game state, one game per thread.
+//
+// Everything here is new code written for the packed layout below; the behaviour it must
+// reproduce is the reference's azulnet/azul.py (cited per function).  The functions are
+// __host__ __device__ so that tests/harness can compile the very same header with g++ and
+// compare it with the oracle on the CPU before any GPU time is spent; the product only ever
+// calls them from the kernels in azb_kernels.cu.
+//
+// Packed state, W(P) = 7 + 5*P uint32 words per game, stored structure-of-arrays in HBM
+// (word w of game g at state[w * stride + g], so a warp reads 32 consecutive words):
+//
+//   shared words
+//   0..2  PL0, PL1, PL2  bit-planes of the 30 (source, colour) tile counts: bit (d + 6c) of
+//                        plane k = bit k of count(source d, colour c); d = 0 is the centre,
+//                        d = 1..5 the factory displays.  Bit index == action index mod 30
+//                        (game_runner.py:102-103), so "source holds colour" for the legal mask
+//                        is PL0|PL1|PL2 and a display empties with three ANDs.
+//   3     MISC           [4:0] plane 3 of the centre counts (centre can hold 15 of a colour)
+//                        [5] first-player token in the centre (azul.py:71)
+//                        [8:6] current_player  [11:9] next_first_player  (1-based, azul.py:27,37-43)
+//                        [12] end_of_game  [15:13] sticky status (stuck, bag-empty, bad-import)
+//                        [27:16] turn_counter (azul.py:30)
+//   4     BOX            5 x 6-bit colour counts (azul.py:51; Lid pool only)
+//   5     LID            5 x 6-bit colour counts (azul.py:52)
+//   6     STEPS          env steps executed by this slot == position in the RNG schedule
+//   per player p (5 words at 7 + 5p)
+//   +0    PAT            pattern lines: row r at [6r+5:6r] = colour[2:0] | count[5:3]
+//                        (one colour per row is an invariant of legal play, azul.py:171-173)
+//   +1    WALL           bit (5*row + colour), the reference's colour-indexed wall (azul.py:23-24)
+//   +2    SCF            [15:0] score (azul.py:26)  [18:16] floor count 0..7 (azul.py:25)
+//   +3    STA            [11:0] first_player_stats  [27:12] -floor_penalty  [31:28] max_combo
+//   +4    STB            [7:0] completed rows  [15:8] completed colours  [23:16] completed columns
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AZB_HD __host__ __device__ __forceinline__
+#define AZB_M __host__ __device__ __forceinline__
+#else
+#define AZB_HD static inline
+#define AZB_M inline
+#endif
+
+namespace azb {
+
+enum : int { POOL_RANDOM = 0, POOL_LID = 1 };
+enum : uint32_t { ST_ILLEGAL = 1, ST_ENDED = 2, ST_STUCK = 4, ST_BAG_EMPTY = 8, ST_BAD_IMPORT = 16 };
+enum : uint32_t { PURPOSE_ACTION = 0, PURPOSE_REFILL = 1, PURPOSE_FIRST = 2, PURPOSE_RESET_REFILL = 3 };
+
+// ---- intrinsics that exist on both sides ---------------------------------------------------
+AZB_HD uint32_t mulhi(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+AZB_HD int popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+// count trailing zeros, 32 for x == 0
+AZB_HD int ctz(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)__brev(x));
+#else
+    return x ? __builtin_ctz(x) : 32;
+#endif
+}
+// count leading zeros, 32 for x == 0
+AZB_HD int clz(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+
+constexpr uint32_t M6 = 0x01041041u;     // bits 0,6,12,18,24: the five colour slots of one source
+constexpr uint32_t M5 = 0x00108421u;     // bits 0,5,10,15,20: one column of a 5x5 bit matrix
+constexpr uint32_t PLANE_MASK = 0x3FFFFFFFu;
+
+// 5 contiguous bits -> stride 6 (bit c -> bit 6c); the 25 partial products never collide
+AZB_HD uint32_t spread5to6(uint32_t x) { return (x * M5) & M6; }
+// stride 6 -> 5 contiguous bits (bit 6c -> bit c)
+AZB_HD uint32_t gather6to5(uint32_t x) { return (((x & M6) * M5) >> 20) & 31u; }
+
+// ---- Philox4x32-10 (Salmon et al. SC'11), the counter-based generator of the draw schedule ----
+struct Philox {
+    uint32_t k0, k1;
+    AZB_M void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const
+    {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0 = mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+// ---- the game in registers ----------------------------------------------------------------
+template <int P>
+struct Game {
+    uint32_t pl0, pl1, pl2, misc, box, lid, steps;
+    uint32_t pat[P], wall[P], scf[P], sta[P], stb[P];
+
+    static constexpr int WORDS = 7 + 5 * P;
+
+    AZB_M void load(const uint32_t* __restrict__ s, int64_t stride, int64_t g)
+    {
+        pl0 = s[0 * stride + g]; pl1 = s[1 * stride + g]; pl2 = s[2 * stride + g];
+        misc = s[3 * stride + g]; box = s[4 * stride + g]; lid = s[5 * stride + g];
+        steps = s[6 * stride + g];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            pat[p] = s[(7 + 5 * p) * stride + g];  wall[p] = s[(8 + 5 * p) * stride + g];
+            scf[p] = s[(9 + 5 * p) * stride + g];  sta[p] = s[(10 + 5 * p) * stride + g];
+            stb[p] = s[(11 + 5 * p) * stride + g];
+        }
+    }
+    AZB_M void store(uint32_t* __restrict__ s, int64_t stride, int64_t g) const
+    {
+        s[0 * stride + g] = pl0; s[1 * stride + g] = pl1; s[2 * stride + g] = pl2;
+        s[3 * stride + g] = misc; s[4 * stride + g] = box; s[5 * stride + g] = lid;
+        s[6 * stride + g] = steps;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            s[(7 + 5 * p) * stride + g] = pat[p];  s[(8 + 5 * p) * stride + g] = wall[p];
+            s[(9 + 5 * p) * stride + g] = scf[p];  s[(10 + 5 * p) * stride + g] = sta[p];
+            s[(11 + 5 * p) * stride + g] = stb[p];
+        }
+    }
+
+    AZB_M uint32_t current_player() const { return (misc >> 6) & 7u; }
+    AZB_M uint32_t next_first_player() const { return (misc >> 9) & 7u; }
+    AZB_M bool ended() const { return (misc >> 12) & 1u; }
+    AZB_M uint32_t status() const { return ((misc >> 13) & 7u) << 2; }
+    AZB_M uint32_t turn_counter() const { return (misc >> 16) & 0xFFFu; }
+    AZB_M void set_current_player(uint32_t v) { misc = (misc & ~(7u << 6)) | (v << 6); }
+    AZB_M void set_next_first_player(uint32_t v) { misc = (misc & ~(7u << 9)) | (v << 9); }
+    AZB_M void add_status(uint32_t bits) { misc |= ((bits >> 2) & 7u) << 13; }
+    // python indexing with current_player-1: seat 0 wraps to the last player (azul.py:27)
+    AZB_M int seat() const { uint32_t c = current_player(); return c ? (int)c - 1 : P - 1; }
+
+    AZB_M uint32_t sel(const uint32_t (&a)[P], int s) const
+    {
+        uint32_t v = a[0];
+#pragma unroll
+        for (int p = 1; p < P; p++) v = (s == p) ? a[p] : v;
+        return v;
+    }
+    AZB_M void put(uint32_t (&a)[P], int s, uint32_t v)
+    {
+#pragma unroll
+        for (int p = 0; p < P; p++) a[p] = (s == p) ? v : a[p];
+    }
+};
+
+// ---- legal mask: check_all_valid (game_runner.py:113-117) over is_legal_move (azul.py:162-176) ----
+// legal(d,c,p) = source d holds colour c  AND  (p == 0 OR (row p-1 of the mover holds no other
+// colour AND wall[p-1][c] is clear)).  A row already full of c stays legal (azul.py:171-175).
+template <int P>
+AZB_HD void legal_mask(const Game<P>& g, uint32_t m[6])
+{
+    const uint32_t src = (g.pl0 | g.pl1 | g.pl2 | spread5to6(g.misc & 31u)) & PLANE_MASK;
+    const int s = g.seat();
+    const uint32_t pat = g.sel(g.pat, s), wall = g.sel(g.wall, s);
+    m[0] = src;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, col = (pat >> (6 * r)) & 7u;
+        const uint32_t allowed = (cnt ? (1u << col) : 31u) & ~(wall >> (5 * r)) & 31u;
+        m[r + 1] = src & (spread5to6(allowed) * 63u);
+    }
+}
+
+// floors[] += n capped at 7 (azul.py:119-123)
+AZB_HD uint32_t floor_add(uint32_t scf, uint32_t n)
+{
+    uint32_t f = ((scf >> 16) & 7u) + n;
+    f = f < 7u ? f : 7u;
+    return (scf & ~(7u << 16)) | (f << 16);
+}
+
+// ---- move (azul.py:118-161); no legality check, like the reference ----
+template <int P, int POOL>
+AZB_HD void apply_move(Game<P>& g, uint32_t action)
+{
+    const uint32_t p = action / 30u, b = action - 30u * p, c = b / 6u, d = b - 6u * c;
+    const int s = g.seat();
+    uint32_t scf = g.sel(g.scf, s);
+    uint32_t n = ((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2);
+    const uint32_t cbit = 1u << (6u * c);
+    if (d != 0) {
+        // azul.py:125-133: chosen colour leaves, the rest of display d is added to the centre,
+        // as a bit-sliced 4-bit ripple add over all five colours at once
+        const uint32_t r0 = (g.pl0 >> d) & M6 & ~cbit, r1 = (g.pl1 >> d) & M6 & ~cbit, r2 = (g.pl2 >> d) & M6 & ~cbit;
+        const uint32_t c0 = g.pl0 & M6, c1 = g.pl1 & M6, c2 = g.pl2 & M6, c3 = spread5to6(g.misc & 31u);
+        const uint32_t s0 = c0 ^ r0, k0 = c0 & r0;
+        const uint32_t s1 = c1 ^ r1 ^ k0, k1 = (c1 & r1) | (k0 & (c1 ^ r1));
+        const uint32_t s2 = c2 ^ r2 ^ k1, k2 = (c2 & r2) | (k1 & (c2 ^ r2));
+        const uint32_t s3 = c3 ^ k2;
+        const uint32_t keep = ~((M6 << d) | M6);
+        g.pl0 = (g.pl0 & keep) | s0; g.pl1 = (g.pl1 & keep) | s1; g.pl2 = (g.pl2 & keep) | s2;
+        g.misc = (g.misc & ~31u) | gather6to5(s3);
+    } else {
+        // azul.py:134-143: take from the centre; the token goes to the floor first
+        n |= ((g.misc >> c) & 1u) << 3;
+        g.pl0 &= ~cbit; g.pl1 &= ~cbit; g.pl2 &= ~cbit;
+        g.misc &= ~(1u << c);
+        if (g.misc & 32u) {
+            g.misc &= ~32u;
+            g.set_next_first_player(g.current_player());
+            scf = floor_add(scf, 1u);
+        }
+    }
+    uint32_t to_floor = n;
+    if (p != 0) {
+        // azul.py:145-157: fill row p-1 up to its capacity p, the rest falls to the floor
+        uint32_t pat = g.sel(g.pat, s);
+        const uint32_t sh = 6u * (p - 1u);
+        const uint32_t cnt = (pat >> (sh + 3u)) & 7u;
+        const uint32_t room = p - cnt;                 // p >= cnt always
+        const uint32_t placed = n < room ? n : room;
+        to_floor = n - placed;
+        const uint32_t newcnt = cnt + placed;
+        pat = (pat & ~(63u << sh)) | ((newcnt ? (c | (newcnt << 3)) : 0u) << sh);
+        g.put(g.pat, s, pat);
+    }
+    scf = floor_add(scf, to_floor);
+    g.put(g.scf, s, scf);
+    if (POOL == POOL_LID) g.lid += to_floor << (6u * c);          // azul.py:156-157,160-161
+}
+
+// azul.py:177-181
+template <int P>
+AZB_HD void next_player(Game<P>& g)
+{
+    const uint32_t c = g.current_player();
+    g.set_current_player(c < (uint32_t)P ? c + 1u : 1u);
+}
+
+// azul.py:182-183 -- every display and all six centre slots (token included) are empty
+template <int P>
+AZB_HD bool is_end_of_round(const Game<P>& g)
+{
+    return ((g.pl0 | g.pl1 | g.pl2) & PLANE_MASK) == 0u && (g.misc & 63u) == 0u;
+}
+
+// azul.py:184-191 -- some wall row of some player holds all five colours
+template <int P>
+AZB_HD bool is_end_of_game(const Game<P>& g)
+{
+    uint32_t any = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const uint32_t w = g.wall[p];
+        uint32_t t = w & (w >> 1);
+        t &= t >> 2;
+        t &= w >> 4;
+        any |= t & M5;
+    }
+    return any != 0u;
+}
+
+// ---- count_score (azul.py:192-295) for one player ----
+// Adjacency runs on a column-space copy of the wall (column = (colour + row) mod 5,
+// azul.py:194-196) with ctz/clz run-length counts instead of the reference's four walks.
+template <int P, int POOL>
+AZB_HD void score_player(Game<P>& g, const int pl)
+{
+    uint32_t scf = g.scf[pl], pat = g.pat[pl], wall = g.wall[pl], sta = g.sta[pl], stb = g.stb[pl];
+    // count_floor, azul.py:200-210: 0,-1,-2,-4,-6,-8,-11,-14
+    const uint32_t f = (scf >> 16) & 7u;
+    const uint32_t pen = (0xEB864210u >> (4u * f)) & 15u;
+    int32_t gain = -(int32_t)pen;
+    sta += pen << 12;                                             // floor_penalty statistic (:208)
+    uint32_t wc = 0;                                              // wall in column space
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t row = (wall >> (5 * r)) & 31u;
+        wc |= (((row << r) | (row >> (5 - r))) & 31u) << (5 * r);
+    }
+    uint32_t combo = sta >> 28;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, c = (pat >> (6 * r)) & 7u;
+        if (cnt == (uint32_t)(r + 1)) {                           // :216 line is full
+            pat &= ~(63u << (6 * r));                             // :218
+            wall |= 1u << (5 * r + c);                            // :219
+            if (POOL == POOL_LID) g.lid += (uint32_t)r << (6u * c);   // :220-222
+            uint32_t k = c + (uint32_t)r;
+            k = k >= 5u ? k - 5u : k;                             // to_wall_position, :194-196
+            wc |= 1u << (5 * r + k);
+            const uint32_t rowbits = (wc >> (5 * r)) & 31u;
+            const int hr = ctz(~(rowbits >> (k + 1u)));           // :230-236 walk right
+            const int hl = clz(~((rowbits << (31u - k)) << 1));   // :237-242 walk left
+            const uint32_t colbits = (wc >> k) & M5;              // column k, bit 5j = row j
+            const int vd = (ctz(~(colbits >> (5 * (r + 1))) & M5) * 13) >> 6;      // :244-250 walk down
+            int vu = 0;                                           // :251-257 walk up
+            if (r > 0) vu = (clz(~(colbits << (31 - 5 * (r - 1))) & 0x84210800u) * 13) >> 6;
+            const int h = hr + hl, v = vd + vu;
+            const int pts = h + v + 1 + ((h > 0 && v > 0) ? 1 : 0);   // :258-263
+            combo = (uint32_t)pts > combo ? (uint32_t)pts : combo;    // :264
+            gain += pts;
+            if (rowbits == 31u) { gain += 2; stb += 1u; }                       // :266-272
+            if (((wall >> c) & M5) == M5) { gain += 10; stb += 1u << 8; }       // :274-280
+            if (colbits == M5) { gain += 7; stb += 1u << 16; }                  // :282-288
+        }
+    }
+    int32_t score = (int32_t)(scf & 0xFFFFu) + gain;              // :292
+    score = score < 0 ? 0 : score;                                // :294-295
+    g.scf[pl] = (uint32_t)score;                                  // floor cleared (:209)
+    g.pat[pl] = pat; g.wall[pl] = wall;
+    g.sta[pl] = (sta & 0x0FFFFFFFu) | (combo << 28);
+    g.stb[pl] = stb;
+}
+
+template <int P, int POOL>
+AZB_HD void count_score(Game<P>& g)
+{
+#pragma unroll
+    for (int p = 0; p < P; p++) score_player<P, POOL>(g, p);
+}
+
+// one more tile of colour c on source position b = d + 6c: bit-sliced increment
+AZB_HD void plane_inc(uint32_t& pl0, uint32_t& pl1, uint32_t& pl2, uint32_t b)
+{
+    const uint32_t t = 1u << b;
+    const uint32_t k0 = pl0 & t; pl0 ^= t;
+    const uint32_t k1 = pl1 & k0; pl1 ^= k0;
+    pl2 ^= k1;
+}
+
+// azul.py:64-73: everything new_round does before the 20 draws
+template <int P>
+AZB_HD void new_round_header(Game<P>& g)
+{
+    const uint32_t nf = g.next_first_player();
+    g.set_current_player(nf);                                     // :66
+    const int s = nf ? (int)nf - 1 : P - 1;
+#pragma unroll
+    for (int p = 0; p < P; p++) g.sta[p] += (s == p) ? 1u : 0u;   // :67 first_player_stats
+    g.misc = (g.misc & ~(0xFFFu << 16)) | (((g.turn_counter() + 1u) & 0xFFFu) << 16);   // :68
+    g.set_next_first_player(0u);                                  // :69
+    g.misc = (g.misc & ~31u) | 32u;                               // :71 centre empty + token
+    g.pl0 = g.pl1 = g.pl2 = 0u;                                   // :73
+}
+
+// Lid pool, one draw (azul.py:79-89): pour the lid into an empty box, pick colour c when the
+// point r in [0,total) falls in its cumulative count.  Returns colour or -1 when no tile is left.
+template <int P>
+AZB_HD int lid_draw(Game<P>& g, uint32_t& x)
+{
+    uint32_t b0 = g.box & 63u, b1 = (g.box >> 6) & 63u, b2 = (g.box >> 12) & 63u, b3 = (g.box >> 18) & 63u,
+             b4 = (g.box >> 24) & 63u;
+    uint32_t total = b0 + b1 + b2 + b3 + b4;
+    if (total == 0u) {                                            // :81-83
+        g.box = g.lid; g.lid = 0u;
+        b0 = g.box & 63u; b1 = (g.box >> 6) & 63u; b2 = (g.box >> 12) & 63u; b3 = (g.box >> 18) & 63u;
+        b4 = (g.box >> 24) & 63u;
+        total = b0 + b1 + b2 + b3 + b4;
+        if (total == 0u) { g.add_status(ST_BAG_EMPTY); return -1; }   // :86 TODO in the reference
+    }
+    const uint32_t r = mulhi(x, total);
+    x *= total;
+    const uint32_t e1 = b0 + b1, e2 = e1 + b2, e3 = e2 + b3;
+    const int c = (int)(r >= b0) + (int)(r >= e1) + (int)(r >= e2) + (int)(r >= e3);
+    g.box -= 1u << (6 * c);                                       // :89
+    return c;
+}
+
+// azul.py:64-89 with the Philox draw schedule (DESIGN.md "RNG schedule")
+template <int P, int POOL>
+AZB_HD void new_round_philox(Game<P>& g, const Philox& rng, uint32_t gid, uint32_t purpose)
+{
+    new_round_header(g);
+    uint32_t R[12];
+    rng(gid, g.steps, purpose, 0u, R);
+    rng(gid, g.steps, purpose, 1u, R + 4);
+    if (POOL == POOL_LID) rng(gid, g.steps, purpose, 2u, R + 8);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        if (POOL == POOL_RANDOM) {
+            uint32_t x = R[i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t c = mulhi(x, 5u);                  // :78 randrange(0,5)
+                x *= 5u;
+                plane_inc(g.pl0, g.pl1, g.pl2, (uint32_t)(i + 1) + 6u * c);
+            }
+        } else {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if ((j & 1) == 0) x = R[2 * i + (j >> 1)];
+                const int c = lid_draw(g, x);
+                if (c >= 0) plane_inc(g.pl0, g.pl1, g.pl2, (uint32_t)(i + 1) + 6u * (uint32_t)c);
+            }
+        }
+    }
+}
+
+// azul.py:64-89 with the 20 colours injected (replay of recorded draws; -1 leaves a slot empty)
+template <int P, int POOL, typename DrawFn>
+AZB_HD void new_round_injected(Game<P>& g, DrawFn draw)
+{
+    new_round_header(g);
+#pragma unroll 1
+    for (int k = 0; k < 20; k++) {
+        const int c = draw(k);
+        if (c < 0 || c > 4) continue;
+        if (POOL == POOL_LID) {
+            const uint32_t tot = (g.box & 63u) + ((g.box >> 6) & 63u) + ((g.box >> 12) & 63u) +
+                                 ((g.box >> 18) & 63u) + ((g.box >> 24) & 63u);
+            if (tot == 0u) { g.box = g.lid; g.lid = 0u; }         // :81-83
+            if (((g.box >> (6 * c)) & 63u) == 0u) { g.add_status(ST_BAG_EMPTY); continue; }
+            g.box -= 1u << (6 * c);                               // :89
+        }
+        plane_inc(g.pl0, g.pl1, g.pl2, (uint32_t)(k / 4 + 1) + 6u * (uint32_t)c);
+    }
+}
+
+// Azul.__init__ (azul.py:18-61): an empty game that still needs new_round()
+template <int P, int POOL>
+AZB_HD void init_game(Game<P>& g, uint32_t first_player)
+{
+    g.pl0 = g.pl1 = g.pl2 = 0u;
+    g.misc = first_player << 9;
+    g.box = (POOL == POOL_LID) ? (20u | 20u << 6 | 20u << 12 | 20u << 18 | 20u << 24) : 0u;
+    g.lid = 0u;
+#pragma unroll
+    for (int p = 0; p < P; p++) { g.pat[p] = g.wall[p] = g.scf[p] = g.sta[p] = g.stb[p] = 0u; }
+}
+
+// fresh game in this slot: Azul(rules) + new_round() (game_runner.py:79-80)
+template <int P, int POOL>
+AZB_HD void reset_game(Game<P>& g, const Philox& rng, uint32_t gid, int first_rule)
+{
+    uint32_t first = (uint32_t)first_rule;
+    if (first_rule == 0) {                                        // azul.py:36-37 random.choice
+        uint32_t w[4];
+        rng(gid, g.steps, PURPOSE_FIRST, 0u, w);
+        first = 1u + mulhi(w[0], (uint32_t)P);
+    }
+    init_game<P, POOL>(g, first);
+    new_round_philox<P, POOL>(g, rng, gid, PURPOSE_RESET_REFILL);
+}
+
+// ---- step (azul.py:296-313) after the legality / ended checks; returns true when the game ended ----
+template <int P, int POOL, typename RefillFn>
+AZB_HD bool advance(Game<P>& g, uint32_t action, RefillFn refill)
+{
+    apply_move<P, POOL>(g, action);                               // :304
+    g.steps += 1u;
+    if (is_end_of_round(g)) {                                     // :306
+        count_score<P, POOL>(g);                                  // :307
+        if (is_end_of_game(g)) { g.misc |= 1u << 12; return true; }   // :308-309
+        refill(g);                                                // :311
+    } else {
+        next_player(g);                                           // :313
+    }
+    return false;
+}
+
+AZB_HD bool action_is_legal(const uint32_t m[6], uint32_t action)
+{
+    if (action >= 180u) return false;
+    const uint32_t p = action / 30u, b = action - 30u * p;
+    uint32_t w = m[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++) w = (p == (uint32_t)i) ? m[i] : w;
+    return (w >> b) & 1u;
+}
+
+// position of the k-th (0-based) set bit of a 30-bit word; k < popc(m)
+AZB_HD uint32_t select_bit(uint32_t m, uint32_t k)
+{
+    uint32_t pos = 0, c;
+    c = (uint32_t)popc(m & 0xFFFFu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
+    c = (uint32_t)popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
+    c = (uint32_t)popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
+    c = (uint32_t)popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
+    c = m & 1u;                      if (k >= c) { pos += 1; }
+    return pos;
+}
+
+// The integer random agent (game_runner.py:87-97): legal floor actions (p = 0) weigh 1, every
+// other legal action 100; the point r = mulhi(word, total) walks words 1..5 first, then word 0.
+// Returns 180 when no action is legal.
+AZB_HD uint32_t random_action(const uint32_t m[6], uint32_t word)
+{
+    const uint32_t n1 = (uint32_t)popc(m[1]), n2 = (uint32_t)popc(m[2]), n3 = (uint32_t)popc(m[3]),
+                   n4 = (uint32_t)popc(m[4]), n5 = (uint32_t)popc(m[5]), n0 = (uint32_t)popc(m[0]);
+    const uint32_t n_hi = n1 + n2 + n3 + n4 + n5;
+    const uint32_t total = 100u * n_hi + n0;
+    if (total == 0u) return 180u;
+    const uint32_t r = mulhi(word, total);
+    if (r >= 100u * n_hi) return select_bit(m[0], r - 100u * n_hi);
+    uint32_t k = r / 100u;
+    uint32_t w = m[1], base = 30u;
+    if (k >= n1) { k -= n1; w = m[2]; base = 60u;
+        if (k >= n2) { k -= n2; w = m[3]; base = 90u;
+            if (k >= n3) { k -= n3; w = m[4]; base = 120u;
+                if (k >= n4) { k -= n4; w = m[5]; base = 150u; } } } }
+    return base + select_bit(w, k);
+}
+
+// ---- unpacked record <-> packed game (kernel K7; record layout in layout.py) -----------------
+// Returns false (and flags ST_BAD_IMPORT) when the record cannot be represented: a pattern row
+// holding two colours, or a count outside its field.
+template <int P, typename Rd>
+AZB_HD bool import_record(Game<P>& g, Rd rd)
+{
+    bool ok = true;
+    g.pl0 = g.pl1 = g.pl2 = 0u; g.misc = 0u; g.box = g.lid = 0u;
+    for (int i = 0; i < 5; i++)
+        for (int c = 0; c < 5; c++) {
+            const int32_t n = rd(i * 5 + c);
+            ok &= (n >= 0 && n <= 7);
+            const uint32_t b = (uint32_t)(i + 1 + 6 * c), v = (uint32_t)n;
+            g.pl0 |= (v & 1u) << b; g.pl1 |= ((v >> 1) & 1u) << b; g.pl2 |= ((v >> 2) & 1u) << b;
+        }
+    for (int c = 0; c < 5; c++) {
+        const int32_t n = rd(25 + c);
+        ok &= (n >= 0 && n <= 15);
+        const uint32_t b = (uint32_t)(6 * c), v = (uint32_t)n;
+        g.pl0 |= (v & 1u) << b; g.pl1 |= ((v >> 1) & 1u) << b; g.pl2 |= ((v >> 2) & 1u) << b;
+        g.misc |= ((v >> 3) & 1u) << c;
+    }
+    { const int32_t t = rd(30); ok &= (t == 0 || t == 1); g.misc |= (uint32_t)(t & 1) << 5; }
+    const int o_pat = 31, o_wall = 31 + 25 * P, o_fl = 31 + 50 * P, o_sc = 31 + 51 * P, o_s = 31 + 52 * P;
+    for (int p = 0; p < P; p++) {
+        uint32_t pat = 0, wall = 0;
+        for (int r = 0; r < 5; r++) {
+            int colours = 0;
+            for (int c = 0; c < 5; c++) {
+                const int32_t n = rd(o_pat + 25 * p + 5 * r + c);
+                ok &= (n >= 0 && n <= 7);
+                if (n != 0) { colours++; pat |= ((uint32_t)c | ((uint32_t)n << 3)) << (6 * r); }
+                if (rd(o_wall + 25 * p + 5 * r + c) != 0) wall |= 1u << (5 * r + c);
+            }
+            if (colours > 1) { ok = false; pat &= ~(63u << (6 * r)); }
+        }
+        const int32_t fl = rd(o_fl + p), sc = rd(o_sc + p);
+        ok &= (fl >= 0 && fl <= 7 && sc >= 0 && sc <= 0xFFFF);
+        g.pat[p] = pat; g.wall[p] = wall;
+        g.scf[p] = ((uint32_t)sc & 0xFFFFu) | (((uint32_t)fl & 7u) << 16);
+        const int32_t fps = rd(o_s + 15 + p), fpen = -rd(o_s + 15 + P + p), mc = rd(o_s + 15 + 2 * P + p);
+        ok &= (fps >= 0 && fps <= 0xFFF && fpen >= 0 && fpen <= 0xFFFF && mc >= 0 && mc <= 15);
+        g.sta[p] = ((uint32_t)fps & 0xFFFu) | (((uint32_t)fpen & 0xFFFFu) << 12) | (((uint32_t)mc & 15u) << 28);
+        const int32_t cr = rd(o_s + 15 + 3 * P + 3 * p), cc = rd(o_s + 15 + 3 * P + 3 * p + 1),
+                      ck = rd(o_s + 15 + 3 * P + 3 * p + 2);
+        ok &= (cr >= 0 && cr <= 255 && cc >= 0 && cc <= 255 && ck >= 0 && ck <= 255);
+        g.stb[p] = ((uint32_t)cr & 255u) | (((uint32_t)cc & 255u) << 8) | (((uint32_t)ck & 255u) << 16);
+    }
+    const int32_t cur = rd(o_s + 0), nf = rd(o_s + 1), eog = rd(o_s + 3), turn = rd(o_s + 4);
+    ok &= (cur >= 0 && cur <= P && nf >= 0 && nf <= P && turn >= 0 && turn <= 0xFFF && rd(o_s + 2) == P);
+    g.misc |= ((uint32_t)cur & 7u) << 6 | ((uint32_t)nf & 7u) << 9 | (eog ? 1u << 12 : 0u) | ((uint32_t)turn & 0xFFFu) << 16;
+    for (int c = 0; c < 5; c++) {
+        const int32_t b = rd(o_s + 5 + c), l = rd(o_s + 10 + c);
+        ok &= (b >= 0 && b <= 63 && l >= 0 && l <= 63);
+        g.box |= ((uint32_t)b & 63u) << (6 * c); g.lid |= ((uint32_t)l & 63u) << (6 * c);
+    }
+    g.steps = (uint32_t)rd(o_s + 15 + 6 * P);
+    g.add_status((uint32_t)rd(o_s + 16 + 6 * P) & (ST_STUCK | ST_BAG_EMPTY | ST_BAD_IMPORT));
+    if (!ok) g.add_status(ST_BAD_IMPORT);
+    return ok;
+}
+
+template <int P, typename Wr>
+AZB_HD void export_record(const Game<P>& g, Wr wr)
+{
+    for (int i = 0; i < 5; i++)
+        for (int c = 0; c < 5; c++) {
+            const uint32_t b = (uint32_t)(i + 1 + 6 * c);
+            wr(i * 5 + c, (int32_t)(((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2)));
+        }
+    for (int c = 0; c < 5; c++) {
+        const uint32_t b = (uint32_t)(6 * c);
+        wr(25 + c, (int32_t)(((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2) |
+                             (((g.misc >> c) & 1u) << 3)));
+    }
+    wr(30, (int32_t)((g.misc >> 5) & 1u));
+    const int o_pat = 31, o_wall = 31 + 25 * P, o_fl = 31 + 50 * P, o_sc = 31 + 51 * P, o_s = 31 + 52 * P;
+    for (int p = 0; p < P; p++) {
+        for (int r = 0; r < 5; r++) {
+            const uint32_t cnt = (g.pat[p] >> (6 * r + 3)) & 7u, col = (g.pat[p] >> (6 * r)) & 7u;
+            for (int c = 0; c < 5; c++) {
+                wr(o_pat + 25 * p + 5 * r + c, (int32_t)((cnt && col == (uint32_t)c) ? cnt : 0u));
+                wr(o_wall + 25 * p + 5 * r + c, (int32_t)((g.wall[p] >> (5 * r + c)) & 1u));
+            }
+        }
+        wr(o_fl + p, (int32_t)((g.scf[p] >> 16) & 7u));
+        wr(o_sc + p, (int32_t)(g.scf[p] & 0xFFFFu));
+        wr(o_s + 15 + p, (int32_t)(g.sta[p] & 0xFFFu));
+        wr(o_s + 15 + P + p, -(int32_t)((g.sta[p] >> 12) & 0xFFFFu));
+        wr(o_s + 15 + 2 * P + p, (int32_t)(g.sta[p] >> 28));
+        wr(o_s + 15 + 3 * P + 3 * p + 0, (int32_t)(g.stb[p] & 255u));
+        wr(o_s + 15 + 3 * P + 3 * p + 1, (int32_t)((g.stb[p] >> 8) & 255u));
+        wr(o_s + 15 + 3 * P + 3 * p + 2, (int32_t)((g.stb[p] >> 16) & 255u));
+    }
+    wr(o_s + 0, (int32_t)g.current_player());
+    wr(o_s + 1, (int32_t)g.next_first_player());
+    wr(o_s + 2, P);
+    wr(o_s + 3, (int32_t)g.ended());
+    wr(o_s + 4, (int32_t)g.turn_counter());
+    for (int c = 0; c < 5; c++) {
+        wr(o_s + 5 + c, (int32_t)((g.box >> (6 * c)) & 63u));
+        wr(o_s + 10 + c, (int32_t)((g.lid >> (6 * c)) & 63u));
+    }
+    wr(o_s + 15 + 6 * P, (int32_t)g.steps);
+    wr(o_s + 16 + 6 * P, (int32_t)g.status());
+}
+
+// ---- K-step random-agent rollout of one slot (kernel K1+K2+K3+K6 body) ---------------------
+// counters (DESIGN.md "rollout counters"): 0 steps, 1 games finished, 2 rounds started,
+// 3 sum score seat 0, 4 sum score seat 1, 5 games seat 0 won, 6 stuck aborts, 7 games that ran the
+// bag empty, 8 sum turn_counter, 9 sum -floor_penalty seat 0, 10 sum max_combo seat 0, 11 completed
+// rows, 12 completed columns, 13 completed colours (seat 0), 14 sum first_player_stats seat 0,
+// 15 sum of all seats' scores.  Sink::add(index, value) receives the increments.
+template <int P, typename Sink>
+AZB_HD void tally_finished(const Game<P>& g, Sink& sink)
+{
+    sink.add(1, 1);
+    sink.add(3, g.scf[0] & 0xFFFFu);
+    sink.add(4, g.scf[1] & 0xFFFFu);
+    sink.add(5, (g.scf[0] & 0xFFFFu) > (g.scf[1] & 0xFFFFu) ? 1u : 0u);
+    sink.add(8, g.turn_counter());
+    sink.add(9, (g.sta[0] >> 12) & 0xFFFFu);
+    sink.add(10, g.sta[0] >> 28);
+    sink.add(11, g.stb[0] & 255u);
+    sink.add(12, (g.stb[0] >> 16) & 255u);
+    sink.add(13, (g.stb[0] >> 8) & 255u);
+    sink.add(14, g.sta[0] & 0xFFFu);
+    uint32_t all = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) all += g.scf[p] & 0xFFFFu;
+    sink.add(15, all);
+}
+
+template <int P, int POOL, typename Sink>
+AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first_rule, int k_steps, Sink& sink)
+{
+    uint32_t aw[4] = {0u, 0u, 0u, 0u};
+    bool have_words = false;
+    uint32_t rounds = 0;
+    for (int i = 0; i < k_steps; i++) {
+        uint32_t m[6];
+        if (g.ended()) { reset_game<P, POOL>(g, rng, gid, first_rule); rounds++; }
+        legal_mask(g, m);
+        if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u) {    // stuck round: abort + fresh game
+            sink.add(6, 1);
+            reset_game<P, POOL>(g, rng, gid, first_rule); rounds++;
+            legal_mask(g, m);
+        }
+        if (!have_words || (g.steps & 3u) == 0u) { rng(gid, g.steps >> 2, PURPOSE_ACTION, 0u, aw); have_words = true; }
+        const uint32_t idx = g.steps & 3u;
+        const uint32_t word = idx == 0u ? aw[0] : idx == 1u ? aw[1] : idx == 2u ? aw[2] : aw[3];
+        const uint32_t action = random_action(m, word);
+        const uint32_t turn_before = g.turn_counter(), bag_before = g.status() & ST_BAG_EMPTY;
+        const bool over = advance<P, POOL>(g, action, [&](Game<P>& gg) {
+            new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL);
+        });
+        if (g.turn_counter() != turn_before) rounds++;
+        if (!bag_before && (g.status() & ST_BAG_EMPTY)) sink.add(7, 1);
+        if (over) {
+            tally_finished(g, sink);
+            reset_game<P, POOL>(g, rng, gid, first_rule); rounds++;
+        }
+    }
+    sink.add(0, (uint32_t)k_steps);
+    sink.add(2, rounds);
+}
+
+}  // namespace azb

@@ -1,0 +1,87 @@
+// rules_host.cpp -- TEST HARNESS ONLY (never loaded by the product package).
+// Compiles azb_rules.cuh -- the exact header the CUDA kernels include -- with g++ so the packed
+// bit-plane rules can be compared with the oracle on the CPU (tests/test_rules_host.py) before a
+// GPU is involved.  Works on unpacked records: import -> operation on the packed game -> export.
+#include <cstdint>
+#include <cstring>
+#include "../../azul_deep_reinforcement_learning_b200/csrc/azb_rules.cuh"
+
+using namespace azb;
+
+struct HostSink {
+    int64_t* c;
+    void add(int i, uint32_t v) { c[i] += v; }
+};
+
+template <int P, int POOL>
+static int run_op(int32_t* rec, int op, int a, const int8_t* draws, uint64_t seed, uint32_t gid, int first_rule,
+                  uint32_t* mask6, int32_t* preview)
+{
+    Game<P> g;
+    bool ok = import_record<P>(g, [&](int i) { return rec[i]; });
+    if (!ok) return -16;
+    Philox rng{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    int rc = 0;
+    switch (op) {
+    case 0: apply_move<P, POOL>(g, (uint32_t)a); break;
+    case 1: {   // step with legality/ended checks (azul.py:296-302)
+        uint32_t m[6];
+        if (g.ended()) { rc = -2; break; }
+        legal_mask(g, m);
+        if (!action_is_legal(m, (uint32_t)a)) { rc = -1; break; }
+        if (draws) advance<P, POOL>(g, (uint32_t)a, [&](Game<P>& gg) { new_round_injected<P, POOL>(gg, [&](int k) { return (int)draws[k]; }); });
+        else advance<P, POOL>(g, (uint32_t)a, [&](Game<P>& gg) { new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL); });
+        break;
+    }
+    case 2: next_player(g); break;
+    case 3: count_score<P, POOL>(g); break;
+    case 5: new_round_injected<P, POOL>(g, [&](int k) { return (int)draws[k]; }); break;
+    case 6: reset_game<P, POOL>(g, rng, gid, first_rule); break;
+    case 7: { Game<P> h = g; count_score<P, POOL>(h); for (int p = 0; p < P; p++) preview[p] = (int32_t)(h.scf[p] & 0xFFFFu); break; }
+    case 8: rc = is_end_of_round(g); break;
+    case 9: rc = is_end_of_game(g); break;
+    case 100: break;   // round trip
+    default: return -100;
+    }
+    if (mask6) legal_mask(g, mask6);
+    if (rc >= 0 || op == 8 || op == 9) export_record<P>(g, [&](int i, int32_t v) { rec[i] = v; });
+    return rc;
+}
+
+template <int P, int POOL>
+static void run_rollout(int32_t* recs, int64_t n, int first_rule, uint64_t seed, uint32_t gid0, int k, int64_t* counters)
+{
+    const int U = 48 + 58 * P;
+    Philox rng{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    HostSink sink{counters};
+    for (int64_t i = 0; i < n; i++) {
+        int32_t* rec = recs + i * U;
+        Game<P> g;
+        import_record<P>(g, [&](int j) { return rec[j]; });
+        rollout_steps<P, POOL>(g, rng, gid0 + (uint32_t)i, first_rule, k, sink);
+        export_record<P>(g, [&](int j, int32_t v) { rec[j] = v; });
+    }
+}
+
+#define DISPATCH(P, POOL, CALL)                                                         \
+    if (P == 2 && POOL == 0) { return CALL<2, 0>; } if (P == 2 && POOL == 1) { return CALL<2, 1>; } \
+    if (P == 3 && POOL == 0) { return CALL<3, 0>; } if (P == 3 && POOL == 1) { return CALL<3, 1>; } \
+    if (P == 4 && POOL == 0) { return CALL<4, 0>; } if (P == 4 && POOL == 1) { return CALL<4, 1>; }
+
+extern "C" int hh_op(int32_t* rec, int players, int pool, int op, int a, const int8_t* draws, uint64_t seed,
+                     uint32_t gid, int first_rule, uint32_t* mask6, int32_t* preview)
+{
+#define CALL_OP(P, POOL) if (players == P && pool == POOL) return run_op<P, POOL>(rec, op, a, draws, seed, gid, first_rule, mask6, preview);
+    CALL_OP(2, 0) CALL_OP(2, 1) CALL_OP(3, 0) CALL_OP(3, 1) CALL_OP(4, 0) CALL_OP(4, 1)
+    return -101;
+}
+
+extern "C" int hh_rollout(int32_t* recs, int64_t n, int players, int pool, int first_rule, uint64_t seed,
+                          uint32_t gid0, int k, int64_t* counters)
+{
+#define CALL_RO(P, POOL) if (players == P && pool == POOL) { run_rollout<P, POOL>(recs, n, first_rule, seed, gid0, k, counters); return 0; }
+    CALL_RO(2, 0) CALL_RO(2, 1) CALL_RO(3, 0) CALL_RO(3, 1) CALL_RO(4, 0) CALL_RO(4, 1)
+    return -101;
+}
+
+extern "C" int hh_random_action(const uint32_t* mask6, uint32_t word) { return (int)random_action(mask6, word); }
