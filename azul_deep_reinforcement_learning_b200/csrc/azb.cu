@@ -1,0 +1,540 @@
+// azb.cu -- sm_100a kernels and the C ABI (include/azb.h) of the batched Azul engine.
+//
+// One game per thread: the whole packed state (17 / 22 / 27 words for 2 / 3 / 4 players) lives in
+// registers, loads and stores of the structure-of-arrays state are fully coalesced (a warp touches
+// 32 consecutive words per state word), and all rule arithmetic is SWAR on bit-planes
+// (azb_rules.cuh).  The path is integer work bounded by HBM traffic for the single-step entry
+// points and by the issue rate for the fused K-step rollout; there is nothing GEMM-shaped here.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/azb.h"
+#include "azb_rules.cuh"
+
+using namespace azb;
+
+// ------------------------------------------------------------------------------------------
+// handle + error plumbing
+// ------------------------------------------------------------------------------------------
+struct azb_handle {
+    int device;
+    int64_t n_games;
+    int players;
+    int tile_pool;
+    int first_player;
+    uint64_t seed;
+    uint64_t game_id_base;
+    int block_threads;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+#define AZB_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) return fail(AZB_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+struct Launch {
+    const uint32_t* __restrict__ state_in;
+    uint32_t* __restrict__ state;
+    int64_t n;
+    uint32_t k0, k1;       // Philox key
+    uint32_t gid0;         // global id of game 0
+    int first_rule;
+};
+
+__device__ __forceinline__ void store_mask(uint32_t* __restrict__ mask6, int64_t n, int64_t g, const uint32_t m[6])
+{
+#pragma unroll
+    for (int p = 0; p < 6; p++) mask6[p * n + g] = m[p];
+}
+
+// K6: fresh game in the selected slots
+template <int P, int POOL>
+__global__ void k_reset(Launch L, const uint8_t* __restrict__ which)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= L.n) return;
+    if (which && which[g] == 0) return;
+    Game<P> gm;
+    gm.steps = L.state[6 * L.n + g];
+    const Philox rng{L.k0, L.k1};
+    reset_game<P, POOL>(gm, rng, L.gid0 + (uint32_t)g, L.first_rule);
+    gm.store(L.state, L.n, g);
+}
+
+// K2: legal mask only -- reads the 4 shared words and the mover's pattern + wall words
+template <int P>
+__global__ void k_legal_mask(const uint32_t* __restrict__ s, int64_t n, uint32_t* __restrict__ mask6)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    Game<P> gm;
+    gm.pl0 = s[g]; gm.pl1 = s[n + g]; gm.pl2 = s[2 * n + g]; gm.misc = s[3 * n + g];
+    const int seat = gm.seat();
+#pragma unroll
+    for (int p = 0; p < P; p++) { gm.pat[p] = 0; gm.wall[p] = 0; }
+    const uint32_t pat = s[(7 + 5 * seat) * n + g], wall = s[(8 + 5 * seat) * n + g];
+    gm.put(gm.pat, seat, pat);
+    gm.put(gm.wall, seat, wall);
+    uint32_t m[6];
+    legal_mask(gm, m);
+    store_mask(mask6, n, g, m);
+}
+
+// K1 (+K2, K5): one Azul.step per game
+template <int P, int POOL>
+__global__ void k_step(Launch L, const uint8_t* __restrict__ action, const int8_t* __restrict__ draws,
+                       uint32_t* __restrict__ mask6_out, int16_t* __restrict__ preview_out,
+                       uint8_t* __restrict__ done_out, uint8_t* __restrict__ status_out)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= L.n) return;
+    Game<P> gm;
+    gm.load(L.state, L.n, g);
+    const uint32_t a = action[g];
+    uint32_t status = 0;
+    uint32_t m[6];
+    if (a != AZB_ACTION_SKIP) {
+        if (gm.ended()) {
+            status = ST_ENDED;                                        // azul.py:298-299
+        } else {
+            legal_mask(gm, m);
+            if (!action_is_legal(m, a)) {
+                status = ST_ILLEGAL;                                  // azul.py:301-302
+            } else {
+                const Philox rng{L.k0, L.k1};
+                const uint32_t gid = L.gid0 + (uint32_t)g;
+                if (draws) {
+                    const int8_t* d = draws + 20 * g;
+                    advance<P, POOL>(gm, a, [&](Game<P>& gg) {
+                        new_round_injected<P, POOL>(gg, [&](int k) { return (int)d[k]; });
+                    });
+                } else {
+                    advance<P, POOL>(gm, a, [&](Game<P>& gg) {
+                        new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL);
+                    });
+                }
+                gm.store(L.state, L.n, g);
+            }
+        }
+    }
+    if (mask6_out || status_out) {
+        legal_mask(gm, m);
+        if (!gm.ended() && (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u && gm.current_player() != 0u)
+            status |= ST_STUCK;
+        if (mask6_out) store_mask(mask6_out, L.n, g, m);
+    }
+    if (preview_out) {
+        Game<P> cp = gm;
+        count_score<P, POOL>(cp);
+#pragma unroll
+        for (int p = 0; p < P; p++) preview_out[p * L.n + g] = (int16_t)(cp.scf[p] & 0xFFFFu);
+    }
+    if (done_out) done_out[g] = gm.ended() ? 1 : 0;
+    if (status_out) status_out[g] = (uint8_t)(status | gm.status());
+}
+
+// K1+K2+K3+K6 fused: k_steps random-agent env steps per game in one launch
+struct BlockSink {
+    unsigned long long* c;
+    __device__ __forceinline__ void add(int i, uint32_t v)
+    {
+        if (v) atomicAdd(&c[i], (unsigned long long)v);
+    }
+};
+
+template <int P, int POOL>
+__global__ void k_rollout_random(Launch L, int k_steps, uint32_t* __restrict__ mask6_out,
+                                 unsigned long long* __restrict__ counters)
+{
+    __shared__ unsigned long long cnt[AZB_N_COUNTERS];
+    if (threadIdx.x < AZB_N_COUNTERS) cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < L.n) {
+        Game<P> gm;
+        gm.load(L.state, L.n, g);
+        const Philox rng{L.k0, L.k1};
+        BlockSink sink{cnt};
+        rollout_steps<P, POOL>(gm, rng, L.gid0 + (uint32_t)g, L.first_rule, k_steps, sink);
+        gm.store(L.state, L.n, g);
+        if (mask6_out) {
+            uint32_t m[6];
+            legal_mask(gm, m);
+            store_mask(mask6_out, L.n, g, m);
+        }
+    }
+    __syncthreads();
+    if (counters && threadIdx.x < AZB_N_COUNTERS && cnt[threadIdx.x]) atomicAdd(&counters[threadIdx.x], cnt[threadIdx.x]);
+}
+
+// K5: score preview on a copy
+template <int P, int POOL>
+__global__ void k_score_preview(const uint32_t* __restrict__ s, int64_t n, int16_t* __restrict__ out)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    Game<P> gm;
+    gm.load(s, n, g);
+    count_score<P, POOL>(gm);
+#pragma unroll
+    for (int p = 0; p < P; p++) out[p * n + g] = (int16_t)(gm.scf[p] & 0xFFFFu);
+}
+
+// K7: unpacked records <-> packed state
+template <int P>
+__global__ void k_import(const int32_t* __restrict__ rec, uint32_t* __restrict__ s, int64_t n, uint8_t* __restrict__ ok_out)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int32_t* r = rec + g * (48 + 58 * P);
+    Game<P> gm;
+    const bool ok = import_record<P>(gm, [&](int i) { return r[i]; });
+    gm.store(s, n, g);
+    if (ok_out) ok_out[g] = ok ? 1 : 0;
+}
+
+template <int P>
+__global__ void k_export(const uint32_t* __restrict__ s, int32_t* __restrict__ rec, int64_t n)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    int32_t* r = rec + g * (48 + 58 * P);
+    Game<P> gm;
+    gm.load(s, n, g);
+    export_record<P>(gm, [&](int i, int32_t v) { r[i] = v; });
+}
+
+// GameRunner.get_state (game_runner.py:56-72)
+template <int P>
+__global__ void k_observe(const uint32_t* __restrict__ s, int64_t n, int perspective, float* __restrict__ obs)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    constexpr int D = 32 + 52 * P;
+    Game<P> gm;
+    gm.load(s, n, g);
+    float* o = obs + g * D;
+    const int persp = perspective >= 0 ? perspective : gm.seat();
+    for (int i = 0; i < 5; i++)
+        for (int c = 0; c < 5; c++) {
+            const uint32_t b = (uint32_t)(i + 1 + 6 * c);
+            o[i * 5 + c] = (float)(((gm.pl0 >> b) & 1u) | (((gm.pl1 >> b) & 1u) << 1) | (((gm.pl2 >> b) & 1u) << 2));
+        }
+    for (int c = 0; c < 5; c++) {
+        const uint32_t b = (uint32_t)(6 * c);
+        o[25 + c] = (float)(((gm.pl0 >> b) & 1u) | (((gm.pl1 >> b) & 1u) << 1) | (((gm.pl2 >> b) & 1u) << 2) |
+                            (((gm.misc >> c) & 1u) << 3));
+    }
+    o[30] = (float)((gm.misc >> 5) & 1u);
+    // order = [perspective] + ascending others (game_runner.py:57)
+#pragma unroll
+    for (int slot = 0; slot < P; slot++) {
+        const int p = slot == 0 ? persp : (slot - 1 < persp ? slot - 1 : slot);
+        const uint32_t pat = gm.sel(gm.pat, p), wall = gm.sel(gm.wall, p), scf = gm.sel(gm.scf, p);
+        for (int r = 0; r < 5; r++) {
+            const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, col = (pat >> (6 * r)) & 7u;
+            for (int c = 0; c < 5; c++) {
+                o[31 + 25 * slot + 5 * r + c] = (float)((cnt && col == (uint32_t)c) ? cnt : 0u);
+                o[31 + 25 * P + 25 * slot + 5 * r + c] = (float)((wall >> (5 * r + c)) & 1u);
+            }
+        }
+        o[31 + 50 * P + slot] = (float)((scf >> 16) & 7u);
+        o[31 + 51 * P + slot] = (float)(scf & 0xFFFFu);
+    }
+    const int nf = (int)gm.next_first_player();
+    o[31 + 52 * P] = nf > 0 ? (float)(((nf - 1 - persp) % P + P) % P + 1) : 0.0f;     // game_runner.py:58-61
+}
+
+// Azul.get_statistics raw integers (azul.py:314-315)
+template <int P>
+__global__ void k_stats(const uint32_t* __restrict__ s, int64_t n, int32_t* __restrict__ out)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    Game<P> gm;
+    gm.load(s, n, g);
+    int32_t* o = out + g * 10;
+    uint32_t fps = 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) fps += gm.sta[p] & 0xFFFu;
+    o[0] = (int32_t)(gm.scf[0] & 0xFFFFu);
+    o[1] = (int32_t)(gm.scf[1] & 0xFFFFu);
+    o[2] = (int32_t)gm.turn_counter();
+    o[3] = (int32_t)(gm.sta[0] & 0xFFFu);
+    o[4] = (int32_t)fps;
+    o[5] = (int32_t)((gm.sta[0] >> 12) & 0xFFFFu);
+    o[6] = (int32_t)(gm.sta[0] >> 28);
+    o[7] = (int32_t)(gm.stb[0] & 255u);
+    o[8] = (int32_t)((gm.stb[0] >> 16) & 255u);
+    o[9] = (int32_t)((gm.stb[0] >> 8) & 255u);
+}
+
+// the reference's per-function entry points (façade): 0 move, 1 next_player, 2 count_score, 3 new_round
+template <int P, int POOL, int OP>
+__global__ void k_op(Launch L, const uint8_t* __restrict__ action, const int8_t* __restrict__ draws)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= L.n) return;
+    Game<P> gm;
+    gm.load(L.state, L.n, g);
+    if (OP == 0) {
+        const uint32_t a = action[g];
+        if (a >= 180u) return;
+        apply_move<P, POOL>(gm, a);
+    } else if (OP == 1) {
+        next_player(gm);
+    } else if (OP == 2) {
+        count_score<P, POOL>(gm);
+    } else {
+        if (draws) {
+            const int8_t* d = draws + 20 * g;
+            new_round_injected<P, POOL>(gm, [&](int k) { return (int)d[k]; });
+        } else {
+            const Philox rng{L.k0, L.k1};
+            new_round_philox<P, POOL>(gm, rng, L.gid0 + (uint32_t)g, PURPOSE_REFILL);
+        }
+    }
+    gm.store(L.state, L.n, g);
+}
+
+template <int P>
+__global__ void k_round_flags(const uint32_t* __restrict__ s, int64_t n, uint8_t* __restrict__ flags)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    Game<P> gm;
+    gm.load(s, n, g);
+    flags[g] = (uint8_t)((is_end_of_round(gm) ? 1 : 0) | (is_end_of_game(gm) ? 2 : 0));
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+#define DISPATCH_P(h, EXPR)                         \
+    switch ((h)->players) {                         \
+    case 2: { constexpr int P = 2; EXPR; } break;   \
+    case 3: { constexpr int P = 3; EXPR; } break;   \
+    default: { constexpr int P = 4; EXPR; } break;  \
+    }
+
+#define DISPATCH_PP(h, EXPR)                                                   \
+    if ((h)->tile_pool == AZB_POOL_LID) { constexpr int POOL = 1; DISPATCH_P(h, EXPR) } \
+    else { constexpr int POOL = 0; DISPATCH_P(h, EXPR) }
+
+static Launch make_launch(const azb_t* h, uint32_t* state)
+{
+    Launch L;
+    L.state_in = state; L.state = state; L.n = h->n_games;
+    L.k0 = (uint32_t)h->seed; L.k1 = (uint32_t)(h->seed >> 32);
+    L.gid0 = (uint32_t)h->game_id_base;
+    L.first_rule = h->first_player;
+    return L;
+}
+
+static inline dim3 grid_of(const azb_t* h) { return dim3((unsigned)((h->n_games + h->block_threads - 1) / h->block_threads)); }
+
+#define CHECK_HANDLE(h)                                       \
+    if (!(h)) return fail(AZB_E_INVALID, "null handle%s");    \
+    AZB_CUDA(cudaSetDevice((h)->device));
+
+#define CHECK_LAUNCH() AZB_CUDA(cudaGetLastError())
+
+extern "C" {
+
+int azb_abi_version(void) { return AZB_ABI_VERSION; }
+int azb_state_words(int players) { return (players >= 2 && players <= 4) ? 7 + 5 * players : AZB_E_INVALID; }
+int azb_record_size(int players) { return (players >= 2 && players <= 4) ? 48 + 58 * players : AZB_E_INVALID; }
+int azb_obs_size(int players) { return (players >= 2 && players <= 4) ? 32 + 52 * players : AZB_E_INVALID; }
+const char* azb_last_error(void) { return g_err; }
+
+int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_pool, int first_player,
+               uint64_t seed, uint64_t game_id_base)
+{
+    if (!out) return fail(AZB_E_INVALID, "out is null%s");
+    *out = nullptr;
+    if (players < 2 || players > 4) return fail(AZB_E_INVALID, "players must be 2..4%s");
+    if (tile_pool != AZB_POOL_RANDOM && tile_pool != AZB_POOL_LID) return fail(AZB_E_INVALID, "tile_pool must be 0 (Random) or 1 (Lid)%s");
+    if (first_player < 0 || first_player > players) return fail(AZB_E_INVALID, "first_player must be 0 (Random) or 1..players%s");   // IllegalRule, azul.py:40-41
+    if (n_games < 1 || n_games > (int64_t)1 << 31) return fail(AZB_E_INVALID, "n_games out of range%s");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(AZB_E_NODEVICE, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(AZB_E_INVALID, "device index out of range%s");
+    AZB_CUDA(cudaSetDevice(device));
+    azb_t* h = new azb_handle();
+    h->device = device; h->n_games = n_games; h->players = players; h->tile_pool = tile_pool;
+    h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128;
+    *out = h;
+    return 0;
+}
+
+int azb_destroy(azb_t* h)
+{
+    delete h;
+    return 0;
+}
+
+int azb_set_block_threads(azb_t* h, int threads)
+{
+    if (!h) return fail(AZB_E_INVALID, "null handle%s");
+    if (threads == 0) threads = 128;
+    if (threads < 32 || threads > 1024 || threads % 32) return fail(AZB_E_INVALID, "block threads must be a multiple of 32 in 32..1024%s");
+    h->block_threads = threads;
+    return 0;
+}
+
+int azb_reset(azb_t* h, uint32_t* state, const uint8_t* which, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_reset<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, which)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_legal_mask(azb_t* h, const uint32_t* state, uint32_t* mask6, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !mask6) return fail(AZB_E_INVALID, "null buffer%s");
+    DISPATCH_P(h, (k_legal_mask<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, mask6)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_step(azb_t* h, uint32_t* state, const uint8_t* action, const int8_t* draws20, uint32_t* mask6_out,
+             int16_t* preview_out, uint8_t* done_out, uint8_t* status_out, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !action) return fail(AZB_E_INVALID, "null buffer%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_step<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
+                       L, action, draws20, mask6_out, preview_out, done_out, status_out)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_out, unsigned long long* counters,
+                       void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    if (k_steps < 0) return fail(AZB_E_INVALID, "k_steps < 0%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_rollout_random<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
+                       L, k_steps, mask6_out, counters)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_score_preview(azb_t* h, const uint32_t* state, int16_t* score_out, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !score_out) return fail(AZB_E_INVALID, "null buffer%s");
+    DISPATCH_PP(h, (k_score_preview<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, score_out)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_import_state(azb_t* h, const int32_t* records, uint32_t* state, uint8_t* ok_out, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !records) return fail(AZB_E_INVALID, "null buffer%s");
+    DISPATCH_P(h, (k_import<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(records, state, h->n_games, ok_out)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_export_state(azb_t* h, const uint32_t* state, int32_t* records, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !records) return fail(AZB_E_INVALID, "null buffer%s");
+    DISPATCH_P(h, (k_export<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, records, h->n_games)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_observe(azb_t* h, const uint32_t* state, int perspective, float* obs, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !obs) return fail(AZB_E_INVALID, "null buffer%s");
+    if (perspective < -1 || perspective >= h->players) return fail(AZB_E_INVALID, "perspective out of range%s");
+    DISPATCH_P(h, (k_observe<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, perspective, obs)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_stats(azb_t* h, const uint32_t* state, int32_t* stats10, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !stats10) return fail(AZB_E_INVALID, "null buffer%s");
+    DISPATCH_P(h, (k_stats<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, stats10)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_move(azb_t* h, uint32_t* state, const uint8_t* action, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !action) return fail(AZB_E_INVALID, "null buffer%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_op<P, POOL, 0><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, action, nullptr)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_next_player(azb_t* h, uint32_t* state, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_op<P, POOL, 1><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, nullptr, nullptr)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_count_score(azb_t* h, uint32_t* state, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_op<P, POOL, 2><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, nullptr, nullptr)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_op<P, POOL, 3><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, nullptr, draws20)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_round_flags(azb_t* h, const uint32_t* state, uint8_t* flags, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !flags) return fail(AZB_E_INVALID, "null buffer%s");
+    DISPATCH_P(h, (k_round_flags<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, flags)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+"""Host side of the batched engine: a thin owner of device buffers around the C ABI.
+
+PyTorch is used for device memory and streams only; every operation on the game state is a
+hand-written sm_100a kernel reached through ``include/azb.h``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .layout import (FIRST_PLAYER_RANDOM, MASK_WORDS, N_ACTIONS, TILE_POOL_LID, TILE_POOL_RANDOM, state_words,
+                     unpacked_size)
+
+N_COUNTERS = 16
+COUNTER_NAMES = [
+    "steps", "games", "rounds", "score_seat0", "score_seat1", "wins_seat0", "stuck", "bag_empty", "turns",
+    "floor_penalty_seat0", "max_combo_seat0", "rows_seat0", "columns_seat0", "colours_seat0",
+    "first_player_seat0", "score_all",
+]
+ACTION_SKIP = 255
+
+
+def rules_to_ints(players, rules):
+    """Reference ``rules`` dict (azul.py:35-56) -> (tile_pool, first_player) integers."""
+    from .azulnet.azul import IllegalRule
+    first = 1
+    if "first_player" in rules:
+        fp = rules["first_player"]
+        if fp == "Random":
+            first = FIRST_PLAYER_RANDOM
+        elif type(fp) == int and 1 <= fp <= players:
+            first = fp
+        else:
+            raise IllegalRule
+    pool = TILE_POOL_RANDOM
+    if "tile_pool" in rules:
+        tp = rules["tile_pool"]
+        if tp == "Random":
+            pool = TILE_POOL_RANDOM
+        elif tp == "Lid":
+            pool = TILE_POOL_LID
+        else:
+            raise IllegalRule
+    return pool, first
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedAzul:
+    """``n_games`` independent Azul games on one GPU.
+
+    Reference counterpart: ``n_games`` ``azulnet.Azul`` objects (azul.py:17) plus the mask / random
+    agent / reward helpers of ``azulnet.game_runner``.  State lives in ``self.state``
+    (uint32 ``[W, n_games]`` as an int32 tensor, packed structure-of-arrays).
+    """
+
+    def __init__(self, n_games, players=2, tile_pool=TILE_POOL_RANDOM, first_player=1, seed=0, device=0,
+                 game_id_base=0, reset=True):
+        if not torch.cuda.is_available():
+            raise _lib.AzbError("no CUDA device: the engine has no CPU path")
+        self.lib = _lib.load()
+        self.n_games, self.players, self.tile_pool, self.first_player = int(n_games), players, tile_pool, first_player
+        self.seed, self.game_id_base = int(seed), int(game_id_base)
+        self.device = torch.device("cuda", device)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.azb_create(ctypes.byref(h), device, self.n_games, players, tile_pool, first_player,
+                                      self.seed & (2 ** 64 - 1), self.game_id_base))
+        self._h = h
+        self.W = state_words(players)
+        self.U = unpacked_size(players)
+        self.state = torch.zeros((self.W, self.n_games), dtype=torch.int32, device=self.device)
+        self.counters = torch.zeros(N_COUNTERS, dtype=torch.int64, device=self.device)
+        if reset:
+            self.reset()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.lib.azb_destroy(h)
+            self._h = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _new(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def set_block_threads(self, threads):
+        _lib.check(self.lib.azb_set_block_threads(self._h, threads))
+
+    # -- K6 ----------------------------------------------------------------------------------
+    def reset(self, which=None):
+        """Fresh game (``Azul(rules)`` + ``new_round()``) in all slots or where ``which`` is non-zero."""
+        if which is not None:
+            which = which.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.azb_reset(self._h, _ptr(self.state), _ptr(which), self._stream()))
+
+    # -- K2 ----------------------------------------------------------------------------------
+    def legal_mask(self, out=None):
+        """uint32 ``[6, n_games]`` (int32 tensor); word p bit (d + 6c) <=> action d + 6c + 30p."""
+        out = self._new((MASK_WORDS, self.n_games), torch.int32) if out is None else out
+        _lib.check(self.lib.azb_legal_mask(self._h, _ptr(self.state), _ptr(out), self._stream()))
+        return out
+
+    # -- K1 ----------------------------------------------------------------------------------
+    def step(self, action, draws=None, want_mask=True, want_preview=False):
+        """One ``Azul.step`` per game.  Returns dict(done, status[, mask][, preview])."""
+        action = action.to(device=self.device, dtype=torch.uint8).contiguous()
+        assert action.numel() == self.n_games
+        if draws is not None:
+            draws = draws.to(device=self.device, dtype=torch.int8).contiguous()
+            assert draws.numel() == 20 * self.n_games
+        mask = self._new((MASK_WORDS, self.n_games), torch.int32) if want_mask else None
+        preview = self._new((self.players, self.n_games), torch.int16) if want_preview else None
+        done = self._new((self.n_games,), torch.uint8)
+        status = self._new((self.n_games,), torch.uint8)
+        _lib.check(self.lib.azb_step(self._h, _ptr(self.state), _ptr(action), _ptr(draws), _ptr(mask), _ptr(preview),
+                                    _ptr(done), _ptr(status), self._stream()))
+        out = {"done": done, "status": status}
+        if want_mask:
+            out["mask"] = mask
+        if want_preview:
+            out["preview"] = preview
+        return out
+
+    # -- K1+K2+K3+K6 fused -------------------------------------------------------------------
+    def rollout_random(self, k_steps, mask_out=None):
+        """``k_steps`` random-agent env steps per game with auto-reset; counters accumulate on device."""
+        _lib.check(self.lib.azb_rollout_random(self._h, _ptr(self.state), int(k_steps), _ptr(mask_out),
+                                              _ptr(self.counters), self._stream()))
+
+    def read_counters(self):
+        c = self.counters.cpu().numpy()
+        return dict(zip(COUNTER_NAMES, (int(x) for x in c)))
+
+    # -- K5 ----------------------------------------------------------------------------------
+    def score_preview(self):
+        out = self._new((self.players, self.n_games), torch.int16)
+        _lib.check(self.lib.azb_score_preview(self._h, _ptr(self.state), _ptr(out), self._stream()))
+        return out
+
+    # -- K7 ----------------------------------------------------------------------------------
+    def import_records(self, records):
+        """int32 ``[n_games, U]`` unpacked records -> packed state; returns the per-game ok flags."""
+        rec = torch.as_tensor(np.ascontiguousarray(records, dtype=np.int32)).to(self.device)
+        assert rec.shape == (self.n_games, self.U), rec.shape
+        ok = self._new((self.n_games,), torch.uint8)
+        _lib.check(self.lib.azb_import_state(self._h, _ptr(rec), _ptr(self.state), _ptr(ok), self._stream()))
+        return ok
+
+    def export_records(self):
+        rec = self._new((self.n_games, self.U), torch.int32)
+        _lib.check(self.lib.azb_export_state(self._h, _ptr(self.state), _ptr(rec), self._stream()))
+        return rec
+
+    def observe(self, perspective=-1):
+        """``GameRunner.get_state`` for every game: float32 ``[n_games, 32 + 52P]``."""
+        obs = self._new((self.n_games, 32 + 52 * self.players), torch.float32)
+        _lib.check(self.lib.azb_observe(self._h, _ptr(self.state), int(perspective), _ptr(obs), self._stream()))
+        return obs
+
+    def stats(self):
+        out = self._new((self.n_games, 10), torch.int32)
+        _lib.check(self.lib.azb_stats(self._h, _ptr(self.state), _ptr(out), self._stream()))
+        return out
+
+    # -- per-function entry points of the reference (façade) ------------------------------
+    def move(self, action):
+        action = action.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.azb_move(self._h, _ptr(self.state), _ptr(action), self._stream()))
+
+    def next_player(self):
+        _lib.check(self.lib.azb_next_player(self._h, _ptr(self.state), self._stream()))
+
+    def count_score(self):
+        _lib.check(self.lib.azb_count_score(self._h, _ptr(self.state), self._stream()))
+
+    def new_round(self, draws=None):
+        if draws is not None:
+            draws = draws.to(device=self.device, dtype=torch.int8).contiguous()
+            assert draws.numel() == 20 * self.n_games
+        _lib.check(self.lib.azb_new_round(self._h, _ptr(self.state), _ptr(draws), self._stream()))
+
+    def round_flags(self):
+        out = self._new((self.n_games,), torch.uint8)
+        _lib.check(self.lib.azb_round_flags(self._h, _ptr(self.state), _ptr(out), self._stream()))
+        return out
+
+
+def mask_to_bool(mask6):
+    """uint32 ``[6, G]`` mask words -> bool ``[G, 180]`` in the reference's action order."""
+    m = mask6.to(torch.int64) & 0xFFFFFFFF
+    bits = (m.unsqueeze(-1) >> torch.arange(30, device=m.device)) & 1      # [6, G, 30]
+    return bits.permute(1, 0, 2).reshape(m.shape[1], N_ACTIONS).bool()

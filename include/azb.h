@@ -1,0 +1,135 @@
+/*
+ * azb.h -- C ABI of the B200-native batched Azul engine (libazb.so).
+ *
+ * The reference (patello/azul_deep_reinforcement_learning) has NO native / FFI interface: its
+ * boundary for this path is the Python surface re-exported by azulnet/__init__.py:1-5.  The entry
+ * points below are what a binding for that surface needs; each one names the reference
+ * function(s) it replaces for a whole batch of independent games.  The Python package
+ * azul_deep_reinforcement_learning_b200 binds them with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative AZB_E_* code; nothing throws across the
+ *     ABI; azb_last_error() returns a thread-local message for the last failure.
+ *   - the CALLER owns every device buffer (plain device pointers, e.g. torch tensor data_ptr());
+ *     the handle owns only configuration.  All launches are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*, NULL = default stream); no hidden synchronisation.
+ *   - one handle per (device, batch shape); thread-compatible, not thread-safe.
+ *   - per-game status bits replace the reference's exceptions:
+ *       AZB_ST_ILLEGAL  IllegalMove (azul.py:301-302), state untouched
+ *       AZB_ST_ENDED    GameEnded   (azul.py:298-299), state untouched
+ *       AZB_ST_STUCK    no legal action although the round is not over (reference crashes)
+ *       AZB_ST_BAG_EMPTY  Lid pool ran out of tiles during a refill (azul.py:86 TODO)
+ *       AZB_ST_BAD_IMPORT record not representable in the packed state
+ *
+ * Buffers (G = n_games, P = players, W = azb_state_words(P), U = azb_record_size(P)):
+ *   state    uint32 [W][G]   packed structure-of-arrays game state (DESIGN.md "HBM layout")
+ *   mask6    uint32 [6][G]   legal mask; word p bit (d + 6c) <=> action d + 6c + 30p legal
+ *                            (action codec of game_runner.py:102-111)
+ *   action   uint8  [G]      0..179; AZB_ACTION_SKIP leaves that game untouched (status 0)
+ *   draws20  int8   [G][20]  tile colours for the next new_round in (display, slot) order
+ *                            (azul.py:74-75); NULL = counter-based Philox4x32-10 schedule
+ *   records  int32  [G][U]   unpacked interchange records mirroring the reference Azul object
+ */
+#ifndef AZB_H
+#define AZB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZB_ABI_VERSION 1
+
+#define AZB_POOL_RANDOM 0          /* rules["tile_pool"] == "Random", azul.py:45-47 */
+#define AZB_POOL_LID 1             /* rules["tile_pool"] == "Lid",    azul.py:48-52 */
+#define AZB_FIRST_PLAYER_RANDOM 0  /* rules["first_player"] == "Random", azul.py:36-37; 1..P fixed */
+
+#define AZB_ST_ILLEGAL 1
+#define AZB_ST_ENDED 2
+#define AZB_ST_STUCK 4
+#define AZB_ST_BAG_EMPTY 8
+#define AZB_ST_BAD_IMPORT 16
+
+#define AZB_ACTION_SKIP 255
+#define AZB_N_ACTIONS 180
+#define AZB_N_COUNTERS 16
+
+#define AZB_E_INVALID (-1)         /* bad argument */
+#define AZB_E_CUDA (-2)            /* CUDA runtime error (message in azb_last_error) */
+#define AZB_E_NODEVICE (-3)        /* no usable CUDA device: there is no CPU fallback */
+
+typedef struct azb_handle azb_t;
+
+int azb_abi_version(void);
+int azb_state_words(int players);           /* 7 + 5P */
+int azb_record_size(int players);           /* 48 + 58P */
+int azb_obs_size(int players);              /* 32 + 52P (136 for P = 2, agent.py:29) */
+const char* azb_last_error(void);
+
+/* Azul.__init__ configuration for a batch (azul.py:18-61): players 2..4, rules as integers,
+ * Philox key `seed`; game g of this handle has global id game_id_base + g (multi-GPU sharding:
+ * results do not depend on how the id range is split over devices). */
+int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_pool, int first_player,
+               uint64_t seed, uint64_t game_id_base);
+int azb_destroy(azb_t* h);
+/* threads per block for the kernels of this handle (multiple of 32, <= 1024); 0 = default */
+int azb_set_block_threads(azb_t* h, int threads);
+
+/* GameRunner.reset / Azul(rules) + new_round() (game_runner.py:76-80, azul.py:18-89): fresh
+ * game in every slot with which[g] != 0 (which == NULL: all slots).  total_steps is preserved. */
+int azb_reset(azb_t* h, uint32_t* state, const uint8_t* which, void* stream);
+
+/* check_all_valid (game_runner.py:113-117) over Azul.is_legal_move (azul.py:162-176) */
+int azb_legal_mask(azb_t* h, const uint32_t* state, uint32_t* mask6, void* stream);
+
+/* Azul.step (azul.py:296-313) for every game.  Outputs are optional (NULL to skip):
+ *   mask6_out   legal mask of the resulting state
+ *   preview_out int16 [P][G] score after a non-mutating count_score (game_runner.py:48-50)
+ *   done_out    uint8 [G] end_of_game after the step
+ *   status_out  uint8 [G] AZB_ST_* bits of this call plus the sticky ones */
+int azb_step(azb_t* h, uint32_t* state, const uint8_t* action, const int8_t* draws20, uint32_t* mask6_out,
+             int16_t* preview_out, uint8_t* done_out, uint8_t* status_out, void* stream);
+
+/* k_steps env steps per game with the random agent on every seat (RandomAgent, game_runner.py:87-97:
+ * weight 0.01 for straight-to-floor actions, 1.0 otherwise), Philox draws and auto-reset, fused in
+ * one launch; counters: device uint64[AZB_N_COUNTERS], accumulated. */
+int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_out,
+                       unsigned long long* counters, void* stream);
+
+/* score after count_score on a copy (game_runner.py:48-50): int16 [P][G]; state untouched */
+int azb_score_preview(azb_t* h, const uint32_t* state, int16_t* score_out, void* stream);
+
+/* Azul.import_JSON / export_JSON / __eq__ field set (azul.py:63,90-117) plus box/lid, end_of_game
+ * and the statistics arrays, as unpacked int32 records.  ok_out (uint8 [G], optional) is 0 for
+ * records that cannot be packed (those slots also carry AZB_ST_BAD_IMPORT). */
+int azb_import_state(azb_t* h, const int32_t* records, uint32_t* state, uint8_t* ok_out, void* stream);
+int azb_export_state(azb_t* h, const uint32_t* state, int32_t* records, void* stream);
+
+/* GameRunner.get_state (game_runner.py:56-72): float32 [G][32 + 52P]; perspective 0..P-1, or -1
+ * for the seat to move in each game (opponent_move, game_runner.py:38). */
+int azb_observe(azb_t* h, const uint32_t* state, int perspective, float* obs, void* stream);
+
+/* Azul.get_statistics (azul.py:314-315) as int32 [G][10]: player_score, opponent_score, rounds,
+ * first_player_stats[0], sum(first_player_stats), -floor_penalty[0], max_combo[0], completed rows,
+ * completed columns, completed colours (seat 0). */
+int azb_stats(azb_t* h, const uint32_t* state, int32_t* stats10, void* stream);
+
+/* The reference's public per-function entry points, batched (used by the azulnet façade):
+ *   azb_move         Azul.move            azul.py:118-161 (no legality check, like the reference)
+ *   azb_next_player  Azul.next_player     azul.py:177-181
+ *   azb_count_score  Azul.count_score     azul.py:192-295
+ *   azb_new_round    Azul.new_round       azul.py:64-89 (draws20 NULL = Philox schedule)
+ *   azb_round_flags  uint8 [G]: bit 0 Azul.is_end_of_round (azul.py:182-183),
+ *                                bit 1 Azul.is_end_of_game (azul.py:184-191, recomputed from walls) */
+int azb_move(azb_t* h, uint32_t* state, const uint8_t* action, void* stream);
+int azb_next_player(azb_t* h, uint32_t* state, void* stream);
+int azb_count_score(azb_t* h, uint32_t* state, void* stream);
+int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream);
+int azb_round_flags(azb_t* h, const uint32_t* state, uint8_t* flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZB_H */

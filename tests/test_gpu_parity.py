@@ -1,0 +1,303 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden traces recorded from the
+unmodified reference, the reference's own known-answer scenarios, and seeded rollouts against the
+C oracle.  Needs a B200: run with ``-m gpu``.  Everything is integer work: the bar is bit-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from azul_deep_reinforcement_learning_b200.layout import UnpackedLayout  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests.helpers import TRACE_CONFIGS, TraceGame, load_kat, load_trace, stream_digest  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def engine(*a, **k):
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul
+    return BatchedAzul(*a, **k)
+
+
+def empty_records(n, players, pool, first):
+    L = UnpackedLayout(players)
+    rec = np.zeros((n, L.size), np.int32)
+    rec[:, L.n_players] = players
+    rec[:, L.next_first_player] = first
+    if pool:
+        rec[:, L.box:L.box + 5] = 20
+    return rec
+
+
+@pytest.mark.parametrize("players,rules", TRACE_CONFIGS)
+def test_replay_golden_traces(players, rules):
+    """All 64 recorded games of a configuration advance in lock-step in one batch."""
+    tr = load_trace(players, rules)
+    pool = int(tr["tile_pool"])
+    n = len(tr["first_player"])
+    L = UnpackedLayout(players)
+    games = [TraceGame(tr, i) for i in range(n)]
+    eng = engine(n, players, pool, 1, reset=False)
+    ok = eng.import_records(empty_records(n, players, pool, tr["first_player"].astype(np.int32)))
+    assert bool(ok.all())
+    eng.new_round(torch.from_numpy(np.stack([g.draws[0] for g in games])))
+    rec = eng.export_records().cpu().numpy()
+    assert np.array_equal(rec, tr["initial_states"].astype(np.int32))
+    T = max(len(g.actions) for g in games)
+    rnd = np.ones(n, np.int64)
+    masks = [[] for _ in range(n)]
+    states = [[] for _ in range(n)]
+    for t in range(T):
+        act = np.full(n, 255, np.uint8)
+        draws = np.full((n, 20), -1, np.int8)
+        for i, g in enumerate(games):
+            if t < len(g.actions):
+                act[i] = g.actions[t]
+                if rnd[i] < len(g.draws):
+                    draws[i] = g.draws[rnd[i]]
+        pre_mask = eng.legal_mask().cpu().numpy().astype(np.uint32)
+        turn_before = rec[:, L.turn_counter].copy()
+        out = eng.step(torch.from_numpy(act), torch.from_numpy(draws))
+        rec = eng.export_records().cpu().numpy()
+        status = out["status"].cpu().numpy()
+        done = out["done"].cpu().numpy()
+        post_mask = out["mask"].cpu().numpy().astype(np.uint32)
+        rnd += rec[:, L.turn_counter] != turn_before
+        for i, g in enumerate(games):
+            if t < len(g.actions):
+                assert status[i] == 0, (i, t, status[i])
+                masks[i].append(pre_mask[:, i].copy()); states[i].append(rec[i].copy())
+                if g.full:
+                    assert np.array_equal(pre_mask[:, i], g.masks[t]), (i, t)
+                    assert np.array_equal(rec[i], g.states[t + 1]), (i, t)
+                    if t + 1 < len(g.actions):
+                        assert np.array_equal(post_mask[:, i], g.masks[t + 1]), (i, t)
+                assert done[i] == (t + 1 == len(g.actions))
+    for i, g in enumerate(games):
+        assert np.array_equal(rec[i], g.final), i
+        assert stream_digest(masks[i], states[i]) == g.sha, i
+        assert rnd[i] == len(g.draws)
+    # GameEnded (azul.py:298-299): state untouched, status bit set
+    out = eng.step(torch.zeros(n, dtype=torch.uint8), None)
+    assert bool((out["status"].cpu() & 2).all())
+    assert np.array_equal(eng.export_records().cpu().numpy(), rec)
+
+
+def test_known_answer_scenarios():
+    """tests/test_azul.py:123-331 op sequences: all scenarios run side by side in one batch."""
+    kat = load_kat()
+    L = UnpackedLayout(2)
+    for pool in (0, 1):
+        idx = [s for s in range(len(kat["kat_names"])) if int(kat["kat_pool"][s]) == pool]
+        n = len(idx)
+        rec0 = np.stack([kat["fixture_records"][int(kat["kat_fixture"][s])].astype(np.int32) for s in idx])
+        if pool:
+            rec0[:, L.box:L.box + 5] = 20
+        eng = engine(n, 2, pool, 1, reset=False)
+        assert bool(eng.import_records(rec0).all())
+        nops = max(int(kat["kat_op_offsets"][s + 1] - kat["kat_op_offsets"][s]) for s in idx)
+        for j in range(nops):
+            # one op per scenario per round; different op kinds go through different entry points
+            sel = {c: np.full(n, 255, np.uint8) for c in (0, 1)}
+            which = {c: [] for c in (0, 1, 2, 3, 4)}
+            draws = np.full((n, 20), -1, np.int8)
+            for i, s in enumerate(idx):
+                k = int(kat["kat_op_offsets"][s]) + j
+                if k >= int(kat["kat_op_offsets"][s + 1]):
+                    continue
+                code, a, b, c = [int(x) for x in kat["kat_ops"][k]]
+                which[code].append((i, k, a + 6 * b + 30 * c))
+                if code in (0, 1):
+                    sel[code][i] = a + 6 * b + 30 * c
+                    if code == 1 and kat["kat_draws"][k][0] >= 0:
+                        draws[i] = kat["kat_draws"][k]
+            before = eng.state.clone()
+            if which[4]:
+                m = eng.legal_mask().cpu().numpy().astype(np.uint32)
+                for i, k, a in which[4]:
+                    assert int(m[a // 30, i] >> (a % 30) & 1) == int(kat["kat_returns"][k]), (kat["kat_names"][idx[i]], k)
+            if which[0]:
+                eng.move(torch.from_numpy(sel[0]))
+            if which[1]:
+                out = eng.step(torch.from_numpy(sel[1]), torch.from_numpy(draws))
+                st = out["status"].cpu().numpy()
+                for i, k, a in which[1]:
+                    want = int(kat["kat_returns"][k])
+                    assert (st[i] & 3) == {0: 0, -1: 1, -2: 2}[want], (kat["kat_names"][idx[i]], k)
+            for code, fn in ((2, eng.next_player), (3, eng.count_score)):
+                if which[code]:
+                    # these entry points act on the whole batch: apply, then restore the others
+                    keep = torch.ones(n, dtype=torch.bool, device=eng.device)
+                    keep[[i for i, _, _ in which[code]]] = False
+                    snap = eng.state.clone()
+                    fn()
+                    eng.state[:, keep] = snap[:, keep]
+            rec = eng.export_records().cpu().numpy()
+            for code in which:
+                for i, k, a in which[code]:
+                    assert np.array_equal(rec[i], kat["kat_records"][k].astype(np.int32)), (kat["kat_names"][idx[i]], k)
+            del before
+
+
+def test_fixture_masks_roundtrip_preview_flags():
+    kat = load_kat()
+    recs = kat["fixture_records"].astype(np.int32)
+    n = len(recs)
+    eng = engine(n, 2, 0, 1, reset=False)
+    assert bool(eng.import_records(recs).all())
+    assert np.array_equal(eng.export_records().cpu().numpy(), recs)
+    m = eng.legal_mask().cpu().numpy().astype(np.uint32)
+    assert np.array_equal(m.T, kat["fixture_masks"])
+    prev = eng.score_preview().cpu().numpy()
+    flags = eng.round_flags().cpu().numpy()
+    for i in range(n):
+        g = O.Game(2, 0, record=recs[i].copy())
+        assert np.array_equal(prev[:, i], g.score_preview()), kat["fixture_names"][i]
+        assert flags[i] == int(g.is_end_of_round()) + 2 * int(g.is_end_of_game())
+    assert np.array_equal(eng.export_records().cpu().numpy(), recs)     # preview did not mutate
+
+
+def test_import_flags_unrepresentable_records():
+    L = UnpackedLayout(2)
+    rec = empty_records(4, 2, 0, 1)
+    rec[1, L.pattern_lines + 10] = 1
+    rec[1, L.pattern_lines + 13] = 1            # two colours in one row
+    rec[2, L.center + 1] = 16                   # more than a centre field can hold
+    eng = engine(4, 2, 0, 1, reset=False)
+    ok = eng.import_records(rec).cpu().numpy()
+    assert list(ok) == [1, 0, 0, 1]
+    out = eng.export_records().cpu().numpy()
+    assert out[1, L.status] & 16 and out[2, L.status] & 16 and out[0, L.status] == 0
+
+
+@pytest.mark.parametrize("players", [2, 3, 4])
+@pytest.mark.parametrize("pool", [0, 1])
+@pytest.mark.parametrize("first_rule", [0, 1])
+def test_rollout_matches_oracle(players, pool, first_rule):
+    """Seeded Philox rollouts with auto-reset: records and counters identical to the C oracle."""
+    seed, gid0, n, k = 0xABCDEF0123 + players, 777, 2048, 160
+    eng = engine(n, players, pool, first_rule, seed=seed, game_id_base=gid0)
+    a = O.fresh_records(n, players, pool, first_rule, seed, gid0)
+    assert np.array_equal(eng.export_records().cpu().numpy(), a)          # K6 reset parity
+    ca = O.rollout_random(a, players, pool, first_rule, seed, gid0, k, threads=8)
+    mask = torch.empty((6, n), dtype=torch.int32, device=eng.device)
+    eng.rollout_random(k, mask)
+    b = eng.export_records().cpu().numpy()
+    assert np.array_equal(a, b), np.nonzero((a != b).any(axis=1))[0][:10]
+    cb = eng.counters.cpu().numpy()
+    assert np.array_equal(ca, cb), (ca, cb)
+    # the mask written by the fused kernel is the mask of the final state
+    assert torch.equal(mask, eng.legal_mask())
+    want = np.stack([O.Game(players, pool, record=a[i]).legal_mask() for i in range(64)])
+    assert np.array_equal(mask[:, :64].cpu().numpy().astype(np.uint32).T, want)
+
+
+def test_step_philox_matches_oracle_and_illegal_leaves_state():
+    """azb_step with the Philox schedule (draws20 = NULL) against ao_step; illegal actions are flagged."""
+    players, pool, seed, n = 2, 1, 99, 512
+    eng = engine(n, players, pool, 0, seed=seed)
+    recs = eng.export_records().cpu().numpy()
+    rng = np.random.default_rng(5)
+    for t in range(80):
+        masks = eng.legal_mask().cpu().numpy().astype(np.uint32)
+        act = np.zeros(n, np.uint8)
+        expect = np.zeros(n, np.int64)
+        for i in range(n):
+            g = O.Game(players, pool, record=recs[i])
+            if rng.random() < 0.15:
+                a = int(rng.integers(0, 200))          # sometimes illegal / out of range
+            else:
+                a = O.random_action(masks[:, i], int(rng.integers(0, 2 ** 32)))
+                a = 0 if a < 0 else a
+            act[i] = a
+            expect[i] = g.step(a, None, seed, i)
+            recs[i] = g.rec
+        out = eng.step(torch.from_numpy(act), None)
+        got = eng.export_records().cpu().numpy()
+        st = out["status"].cpu().numpy()
+        assert np.array_equal(got, recs), t
+        assert np.array_equal(st & 3, np.where(expect == 0, 0, np.where(expect == -1, 1, 2))), t
+
+
+def test_observe_matches_reference_layout():
+    """GameRunner.get_state (game_runner.py:56-72) rebuilt with numpy from exported records."""
+    for players in (2, 3, 4):
+        n = 256
+        eng = engine(n, players, 1, 0, seed=3)
+        eng.rollout_random(37)
+        rec = eng.export_records().cpu().numpy()
+        L = UnpackedLayout(players)
+        for persp in list(range(players)) + [-1]:
+            obs = eng.observe(persp).cpu().numpy()
+            assert obs.shape == (n, 32 + 52 * players)
+            for i in range(0, n, 17):
+                r = rec[i]
+                p0 = persp if persp >= 0 else (int(r[L.current_player]) - 1) % players
+                order = [p0] + [q for q in range(players) if q != p0]
+                pat = r[L.pattern_lines:L.pattern_lines + 25 * players].reshape(players, 25)
+                wal = r[L.walls:L.walls + 25 * players].reshape(players, 25)
+                nf = int(r[L.next_first_player])
+                pn = ((nf - 1 - p0) % players) + 1 if nf > 0 else 0
+                want = np.concatenate([r[0:25], r[25:31], pat[order].ravel(), wal[order].ravel(),
+                                       r[L.floors:L.floors + players][order], r[L.score:L.score + players][order], [pn]])
+                assert np.array_equal(obs[i], want.astype(np.float32)), (players, persp, i)
+    # tests/test_game_runner.py:71-75: a fresh 2-player game observes 136 values summing to 21
+    eng = engine(8, 2, 1, 0, seed=1)
+    obs = eng.observe(0)
+    assert obs.shape[1] == 136 and bool((obs.sum(dim=1) == 21).all())
+
+
+def test_stats_match_records():
+    eng = engine(512, 2, 0, 1, seed=11)
+    eng.rollout_random(45)
+    rec = eng.export_records().cpu().numpy()
+    st = eng.stats().cpu().numpy()
+    L = UnpackedLayout(2)
+    assert np.array_equal(st[:, 0], rec[:, L.score]) and np.array_equal(st[:, 1], rec[:, L.score + 1])
+    assert np.array_equal(st[:, 2], rec[:, L.turn_counter])
+    assert np.array_equal(st[:, 3], rec[:, L.first_player_stats])
+    assert np.array_equal(st[:, 4], rec[:, L.first_player_stats:L.first_player_stats + 2].sum(axis=1))
+    assert np.array_equal(st[:, 5], -rec[:, L.floor_penalty])
+    assert np.array_equal(st[:, 6], rec[:, L.max_combo])
+    assert np.array_equal(st[:, 7], rec[:, L.completed_lines + 0])
+    assert np.array_equal(st[:, 8], rec[:, L.completed_lines + 2])
+    assert np.array_equal(st[:, 9], rec[:, L.completed_lines + 1])
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (65,536 games): size-independent properties of the rollout."""
+    n, k = 65536, 512
+    for pool in (0, 1):
+        eng = engine(n, 2, pool, 0, seed=0x5EED)
+        eng.rollout_random(k)
+        one = eng.state.clone()
+        c1 = eng.counters.clone()
+        # determinism + restartability: two half-length launches == one launch
+        eng2 = engine(n, 2, pool, 0, seed=0x5EED)
+        eng2.rollout_random(200); eng2.rollout_random(k - 200)
+        assert torch.equal(one, eng2.state) and torch.equal(c1, eng2.counters)
+        # sharding independence: the same id range split over two handles (multi-GPU layout)
+        h = n // 2
+        lo = engine(h, 2, pool, 0, seed=0x5EED, game_id_base=0)
+        hi = engine(h, 2, pool, 0, seed=0x5EED, game_id_base=h)
+        lo.rollout_random(k); hi.rollout_random(k)
+        assert torch.equal(one[:, :h], lo.state) and torch.equal(one[:, h:], hi.state)
+        assert torch.equal(c1, lo.counters + hi.counters)
+        cnt = eng.read_counters()
+        assert cnt["steps"] == n * k and cnt["games"] > 0 and cnt["stuck"] == 0
+        assert 45 < cnt["steps"] / cnt["games"] < 75          # ~57 steps per 2-player game
+        rec = eng.export_records().cpu().numpy()
+        L = UnpackedLayout(2)
+        assert (rec[:, L.status] == 0).all() and (rec[:, L.end_of_game] == 0).all()
+        tiles_on_table = rec[:, 0:30].sum(axis=1)
+        assert (tiles_on_table > 0).all()                     # auto-reset leaves every slot playable
+        assert (rec[:, L.floors:L.floors + 2] <= 7).all() and (rec[:, L.score:L.score + 2] >= 0).all()
+        if pool == 1:
+            # tile conservation: box + lid + table + pattern lines + walls == 100
+            total = (rec[:, L.box:L.box + 10].sum(axis=1) + tiles_on_table +
+                     rec[:, L.pattern_lines:L.pattern_lines + 50].sum(axis=1) + rec[:, L.walls:L.walls + 50].sum(axis=1))
+            # floor tiles are already in the lid (azul.py:155-161)
+            assert (total == 100).all()
+        # every legal-mask bit implies its source holds that colour
+        m = eng.legal_mask().cpu().numpy().astype(np.uint32)
+        src = m[0]
+        assert ((m[1:] & ~src) == 0).all() and (src != 0).all()
