@@ -9,7 +9,7 @@ _lib = None
 ABI_VERSION = 1
 SYMBOLS = [
     "azb_abi_version", "azb_state_words", "azb_record_size", "azb_obs_size", "azb_last_error",
-    "azb_create", "azb_destroy", "azb_set_block_threads", "azb_reset", "azb_legal_mask", "azb_step",
+    "azb_create", "azb_destroy", "azb_set_block_threads", "azb_set_rollout_defer", "azb_reset", "azb_legal_mask", "azb_step",
     "azb_rollout_random", "azb_score_preview", "azb_import_state", "azb_export_state", "azb_observe",
     "azb_stats", "azb_move", "azb_next_player", "azb_count_score", "azb_new_round", "azb_round_flags",
 ]
@@ -37,6 +37,7 @@ def load():
     L.azb_create.argtypes = [ctypes.POINTER(vp), i32, i64, i32, i32, i32, u64, u64]
     L.azb_destroy.argtypes = [vp]
     L.azb_set_block_threads.argtypes = [vp, i32]
+    L.azb_set_rollout_defer.argtypes = [vp, i32]
     L.azb_reset.argtypes = [vp, vp, vp, vp]
     L.azb_legal_mask.argtypes = [vp, vp, vp, vp]
     L.azb_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -27,6 +27,7 @@ struct azb_handle {
     uint64_t seed;
     uint64_t game_id_base;
     int block_threads;
+    int defer;             // rollout: games of a warp that must be waiting before the end-of-round pass runs
 };
 
 static thread_local char g_err[512] = "";
@@ -157,19 +158,21 @@ struct BlockSink {
 };
 
 template <int P, int POOL>
-__global__ void k_rollout_random(Launch L, int k_steps, uint32_t* __restrict__ mask6_out,
+__global__ void k_rollout_random(Launch L, int k_steps, int defer, uint32_t* __restrict__ mask6_out,
                                  unsigned long long* __restrict__ counters)
 {
     __shared__ unsigned long long cnt[AZB_N_COUNTERS];
     if (threadIdx.x < AZB_N_COUNTERS) cnt[threadIdx.x] = 0ull;
     __syncthreads();
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g < L.n) {
-        Game<P> gm;
-        gm.load(L.state, L.n, g);
-        const Philox rng{L.k0, L.k1};
-        BlockSink sink{cnt};
-        rollout_steps<P, POOL>(gm, rng, L.gid0 + (uint32_t)g, L.first_rule, k_steps, sink);
+    const bool valid = g < L.n;
+    const int64_t gl = valid ? g : L.n - 1;            // whole warps stay in the loop: they vote together
+    Game<P> gm;
+    gm.load(L.state, L.n, gl);
+    const Philox rng{L.k0, L.k1};
+    BlockSink sink{cnt};
+    rollout_steps<P, POOL>(gm, rng, L.gid0 + (uint32_t)gl, L.first_rule, k_steps, sink, WarpLanes{}, valid, defer);
+    if (valid) {
         gm.store(L.state, L.n, g);
         if (mask6_out) {
             uint32_t m[6];
@@ -378,7 +381,7 @@ int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_p
     AZB_CUDA(cudaSetDevice(device));
     azb_t* h = new azb_handle();
     h->device = device; h->n_games = n_games; h->players = players; h->tile_pool = tile_pool;
-    h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128;
+    h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->defer = 16;
     *out = h;
     return 0;
 }
@@ -395,6 +398,15 @@ int azb_set_block_threads(azb_t* h, int threads)
     if (threads == 0) threads = 128;
     if (threads < 32 || threads > 1024 || threads % 32) return fail(AZB_E_INVALID, "block threads must be a multiple of 32 in 32..1024%s");
     h->block_threads = threads;
+    return 0;
+}
+
+int azb_set_rollout_defer(azb_t* h, int games)
+{
+    if (!h) return fail(AZB_E_INVALID, "null handle%s");
+    if (games == 0) games = 16;
+    if (games < 1 || games > 32) return fail(AZB_E_INVALID, "defer must be 1..32%s");
+    h->defer = games;
     return 0;
 }
 
@@ -437,7 +449,7 @@ int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_o
     if (k_steps < 0) return fail(AZB_E_INVALID, "k_steps < 0%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_rollout_random<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
-                       L, k_steps, mask6_out, counters)));
+                       L, k_steps, h->defer, mask6_out, counters)));
     CHECK_LAUNCH();
     return 0;
 }

@@ -650,38 +650,73 @@ AZB_HD void tally_finished(const Game<P>& g, Sink& sink)
     sink.add(15, all);
 }
 
-template <int P, int POOL, typename Sink>
-AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first_rule, int k_steps, Sink& sink)
+// Warp-vote policies for rollout_steps: the kernels vote across the 32 games of a warp, the host
+// harness (one game at a time) votes with itself.
+struct SingleLane {
+    AZB_M int count(bool p) const { return p ? 1 : 0; }
+};
+#if defined(__CUDACC__)
+struct WarpLanes {
+    __device__ __forceinline__ int count(bool p) const { return __popc(__ballot_sync(0xFFFFFFFFu, p)); }
+};
+#endif
+
+// Each slot executes exactly k_steps env steps.  A step is split in two phases so that a warp
+// does not pay for the rare, long end-of-round work on every iteration:
+//   light  legal mask -> random action -> move (azul.py:304) -> next_player, every iteration;
+//   heavy  count_score -> end_of_game ? tally + fresh game : new_round (azul.py:306-311), run by the
+//          warp only once `defer` of its games are waiting for it (or nothing else can move).
+// A game that finished its round simply waits for the next heavy pass; its trajectory, and so every
+// result, is independent of `defer` and of which games share its warp.
+template <int P, int POOL, typename Sink, typename Vote>
+AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first_rule, int k_steps, Sink& sink,
+                          const Vote vote, bool valid, int defer)
 {
     uint32_t aw[4] = {0u, 0u, 0u, 0u};
-    bool have_words = false;
+    bool have_words = false, pending = false;
     uint32_t rounds = 0;
-    for (int i = 0; i < k_steps; i++) {
-        uint32_t m[6];
-        if (g.ended()) { reset_game<P, POOL>(g, rng, gid, first_rule); rounds++; }
-        legal_mask(g, m);
-        if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u) {    // stuck round: abort + fresh game
-            sink.add(6, 1);
-            reset_game<P, POOL>(g, rng, gid, first_rule); rounds++;
+    int remaining = valid ? k_steps : 0;
+    if (remaining > 0 && g.ended()) { reset_game<P, POOL>(g, rng, gid, first_rule); rounds++; }
+    for (;;) {
+        if (remaining > 0 && !pending) {
+            uint32_t m[6];
             legal_mask(g, m);
+            if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u) {    // stuck round: abort + fresh game
+                sink.add(6, 1);
+                reset_game<P, POOL>(g, rng, gid, first_rule); rounds++;
+                legal_mask(g, m);
+            }
+            if (!have_words || (g.steps & 3u) == 0u) { rng(gid, g.steps >> 2, PURPOSE_ACTION, 0u, aw); have_words = true; }
+            const uint32_t idx = g.steps & 3u;
+            const uint32_t word = idx == 0u ? aw[0] : idx == 1u ? aw[1] : idx == 2u ? aw[2] : aw[3];
+            apply_move<P, POOL>(g, random_action(m, word));           // azul.py:304
+            g.steps += 1u;
+            remaining--;
+            if (is_end_of_round(g)) pending = true;                   // azul.py:306
+            else next_player(g);                                      // azul.py:313
         }
-        if (!have_words || (g.steps & 3u) == 0u) { rng(gid, g.steps >> 2, PURPOSE_ACTION, 0u, aw); have_words = true; }
-        const uint32_t idx = g.steps & 3u;
-        const uint32_t word = idx == 0u ? aw[0] : idx == 1u ? aw[1] : idx == 2u ? aw[2] : aw[3];
-        const uint32_t action = random_action(m, word);
-        const uint32_t turn_before = g.turn_counter(), bag_before = g.status() & ST_BAG_EMPTY;
-        const bool over = advance<P, POOL>(g, action, [&](Game<P>& gg) {
-            new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL);
-        });
-        if (g.turn_counter() != turn_before) rounds++;
-        if (!bag_before && (g.status() & ST_BAG_EMPTY)) sink.add(7, 1);
-        if (over) {
-            tally_finished(g, sink);
-            reset_game<P, POOL>(g, rng, gid, first_rule); rounds++;
+        const int n_pending = vote.count(pending);
+        const int n_movable = vote.count(remaining > 0 && !pending);
+        if (n_pending > 0 && (n_pending >= defer || n_movable == 0)) {
+            if (pending) {
+                pending = false;
+                count_score<P, POOL>(g);                              // azul.py:307
+                rounds++;
+                if (is_end_of_game(g)) {                              // azul.py:308-309
+                    g.misc |= 1u << 12;
+                    tally_finished(g, sink);
+                    reset_game<P, POOL>(g, rng, gid, first_rule);
+                } else {
+                    const uint32_t bag_before = g.status() & ST_BAG_EMPTY;
+                    new_round_philox<P, POOL>(g, rng, gid, PURPOSE_REFILL);   // azul.py:311
+                    if (!bag_before && (g.status() & ST_BAG_EMPTY)) sink.add(7, 1);
+                }
+            }
+        } else if (n_movable == 0) {
+            break;
         }
     }
-    sink.add(0, (uint32_t)k_steps);
-    sink.add(2, rounds);
+    if (valid) { sink.add(0, (uint32_t)k_steps); sink.add(2, rounds); }
 }
 
 }  // namespace azb

@@ -92,6 +92,9 @@ class BatchedAzul:
     def set_block_threads(self, threads):
         _lib.check(self.lib.azb_set_block_threads(self._h, threads))
 
+    def set_rollout_defer(self, games):
+        _lib.check(self.lib.azb_set_rollout_defer(self._h, games))
+
     # -- K6 ----------------------------------------------------------------------------------
     def reset(self, which=None):
         """Fresh game (``Azul(rules)`` + ``new_round()``) in all slots or where ``which`` is non-zero."""
@@ -132,6 +135,27 @@ class BatchedAzul:
         """``k_steps`` random-agent env steps per game with auto-reset; counters accumulate on device."""
         _lib.check(self.lib.azb_rollout_random(self._h, _ptr(self.state), int(k_steps), _ptr(mask_out),
                                               _ptr(self.counters), self._stream()))
+
+    def rollout_random_host(self, host_state, k_steps, host_mask=None, host_counters=None):
+        """End-to-end form of :meth:`rollout_random` on HOST buffers (pinned for async copies).
+
+        ``host_state`` (int32 ``[W, n_games]``) is copied to the device, rolled out for ``k_steps`` and
+        copied back in place; the final legal mask and the accumulated counters are copied to
+        ``host_mask`` / ``host_counters`` when given.  Returns after the results are on the host.
+        """
+        self.state.copy_(host_state, non_blocking=True)
+        mask = None
+        if host_mask is not None:
+            if getattr(self, "_mask_buf", None) is None:
+                self._mask_buf = self._new((MASK_WORDS, self.n_games), torch.int32)
+            mask = self._mask_buf
+        self.rollout_random(k_steps, mask)
+        host_state.copy_(self.state, non_blocking=True)
+        if host_mask is not None:
+            host_mask.copy_(mask, non_blocking=True)
+        if host_counters is not None:
+            host_counters.copy_(self.counters, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
 
     def read_counters(self):
         c = self.counters.cpu().numpy()

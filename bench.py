@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- Azul env steps/s of the batched random-agent rollout (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One bench "step" = one pass of the hot path over the batch: ONE launch of the fused rollout kernel
+(azb_rollout_random: legal mask + random agent + Azul.step + scoring + refill + auto-reset) that
+advances every one of the G games by --k-steps env steps.  N = 1 runs BASELINE.json configs[1]
+(65,536 parallel 2-player random-agent games); N > 1 (torchrun, one rank per GPU) shards the global
+game-id range over the ranks with no data-path collective (weak scaling, G games per GPU) and uses
+NCCL only for the max-over-ranks timing and the rollout-counter reduction.
+
+The JSON line carries
+  value      env steps/s, state resident in HBM, timed with CUDA events on the launching stream
+  e2e        the same metric through the public host API with HOST buffers: per step the packed state
+             is copied from pinned host memory to the device, rolled out, and state + legal mask +
+             counters are copied back
+  roofline   algorithmic bytes (2*S(P)+25 per env step) / kernel time vs measured HBM peak
+  cpu_baseline  the C oracle port timed on this host's cores on a bounded sample (N = 1, rank 0)
+--impl reference times the reference arm for this tier: the oracle port (the reference is pure Python
+and cannot travel to the GPU box) on all host threads, same config / metric / unit.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "azul_env_steps_per_sec"
+UNIT = "env_steps/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=65536, help="games per GPU (BASELINE configs[1])")
+    ap.add_argument("--players", type=int, default=2)
+    ap.add_argument("--pool", default="lid", choices=["lid", "random"],
+                    help="tile pool; 'lid' + random first player = GameRunner's default rules (game_runner.py:23)")
+    ap.add_argument("--k-steps", type=int, default=256, help="env steps per game per launch")
+    ap.add_argument("--block", type=int, default=0, help="threads per block (0 = library default)")
+    ap.add_argument("--defer", type=int, default=0, help="rollout end-of-round batching threshold (0 = library default)")
+    ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "%d parallel %d-player random-agent Azul games per GPU, env step + legal mask, auto-reset "
+                    "(BASELINE.json configs[1])" % (args.games, args.players),
+        "games_per_gpu": args.games, "players": args.players,
+        "rules": {"tile_pool": "Lid" if args.pool == "lid" else "Random", "first_player": "Random"},
+        "env_steps_per_game_per_launch": args.k_steps,
+        "rng": "Philox4x32-10, seed 0x%X, keyed by global game id" % args.seed,
+        "l2": "flushed between timed launches (256 MiB device fill outside the CUDA-event brackets)",
+        "parallelism": "games sharded by global id over %d GPU(s); no data-path collective" % n_gpus,
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (oracle port): cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------
+def cpu_rollout_rate(args, seconds, threads):
+    """Time the C oracle's rollout (same Philox schedule, same rules) on `threads` host threads."""
+    from oracle import oracle as O
+    pool = 1 if args.pool == "lid" else 0
+    probe_n, probe_k = 256 * threads, 64
+    recs = O.fresh_records(probe_n, args.players, pool, 0, args.seed, 0)
+    t0 = time.perf_counter()
+    O.rollout_random(recs, args.players, pool, 0, args.seed, 0, probe_k, threads=threads)
+    rate = probe_n * probe_k / max(time.perf_counter() - t0, 1e-6)
+    k = args.k_steps
+    n = int(max(threads, min(args.games, rate * seconds / k)))
+    recs = O.fresh_records(n, args.players, pool, 0, args.seed, 0)
+    t0 = time.perf_counter()
+    cnt = O.rollout_random(recs, args.players, pool, 0, args.seed, 0, k, threads=threads)
+    dt = time.perf_counter() - t0
+    assert cnt[0] == n * k
+    return n * k / dt, n, k, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                   # rank 0 alone runs the CPU arm
+    threads = os.cpu_count() or 1
+    pool = 1 if args.pool == "lid" else 0
+    from oracle import oracle as O
+    # bounded sample per step so the whole run ends within minutes: ~1.5 s of CPU work per step
+    rate, _, _, _ = cpu_rollout_rate(args, 1.0, threads)
+    n = int(max(threads, min(args.games, rate * 1.5 / args.k_steps)))
+    recs = O.fresh_records(n, args.players, pool, 0, args.seed, 0)
+    for _ in range(args.warmup):
+        O.rollout_random(recs, args.players, pool, 0, args.seed, 0, args.k_steps, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.rollout_random(recs, args.players, pool, 0, args.seed, 0, args.k_steps, threads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.k_steps * args.steps / dt
+    sample = "%d of %d games x %d env steps per step, C oracle port (oracle/azul_oracle.c), %d threads" % (
+        n, args.games, args.k_steps, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is pure Python and cannot travel to the GPU box; this arm is the C restatement "
+                "pinned bit-exactly to it (tests/test_oracle_golden.py). Python reference measured in the build "
+                "container: ~3.4e3 env steps/s/core (BASELINE.md §2).",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def hbm_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic(args):
+    """dram bytes per launch from the committed ncu capture of this configuration, if any."""
+    p = os.path.join(REPO, "profiles", "rollout_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        key = "p%d_%s_g%d_k%d" % (args.players, args.pool, args.games, args.k_steps)
+        return d.get(key)
+    except Exception:
+        return None
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul
+    from azul_deep_reinforcement_learning_b200.layout import algorithmic_bytes_per_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pool = 1 if args.pool == "lid" else 0
+    G, K = args.games, args.k_steps
+
+    eng = BatchedAzul(G, args.players, pool, 0, seed=args.seed, device=local, game_id_base=rank * G)
+    if args.block:
+        eng.set_block_threads(args.block)
+    if args.defer:
+        eng.set_rollout_defer(args.defer)
+    mask = torch.empty((6, G), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.rollout_random(K, mask)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)                    # L2 flush, outside the event bracket
+        ev[s][0].record()
+        eng.rollout_random(K, mask)
+        ev[s][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(kernel_ms)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+
+    # ---- end to end through the host API ------------------------------------------------
+    host_state = torch.empty(eng.state.shape, dtype=torch.int32).pin_memory()
+    host_state.copy_(eng.state)
+    host_mask = torch.empty((6, G), dtype=torch.int32).pin_memory()
+    host_cnt = torch.empty(16, dtype=torch.int64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        eng.rollout_random_host(host_state, K, host_mask, host_cnt)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.rollout_random_host(host_state, K, host_mask, host_cnt)
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    h2d = host_state.numel() * 4
+    d2h = host_state.numel() * 4 + host_mask.numel() * 4 + host_cnt.numel() * 8
+
+    # ---- rollout statistics (C2: one small allreduce) -----------------------------------
+    cnt = eng.counters.clone()
+    if world > 1:
+        dist.all_reduce(cnt)
+    cnt = cnt.cpu().tolist()
+
+    if rank == 0:
+        steps_total = world * G * K * args.steps
+        value = steps_total / (dev_ms_max * 1e-3)
+        b_alg = algorithmic_bytes_per_step(args.players)
+        avg_launch_s = (dev_ms / args.steps) * 1e-3
+        achieved = b_alg * G * K / avg_launch_s / 1e9
+        peak, peak_src = hbm_peak()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": world * G * K * e2e_steps / float(e2e_t.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": profiled_traffic(args), "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": b_alg, "env_steps_per_launch": G * K,
+                         "kernel": "k_rollout_random<%d,%d>" % (args.players, pool),
+                         "kernel_ms_avg": dev_ms / args.steps, "kernel_ms_min": min(kernel_ms)},
+            "clocks": clocks,
+            "wall_s": wall,
+            "games_per_sec": (cnt[1] / max(cnt[0], 1)) * value,
+            "rollout_counters": {"steps": cnt[0], "games": cnt[1], "rounds": cnt[2], "stuck": cnt[6]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, n, k, dt = cpu_rollout_rate(args, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "%d of %d games x %d env steps, C oracle port on %d threads, %.1f s" % (n, G, k, threads, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -301,3 +301,18 @@ def test_full_size_properties():
         m = eng.legal_mask().cpu().numpy().astype(np.uint32)
         src = m[0]
         assert ((m[1:] & ~src) == 0).all() and (src != 0).all()
+
+
+def test_rollout_independent_of_launch_shape():
+    """Ragged batch (not a multiple of the warp size), every block size and end-of-round batching
+    threshold give the oracle's result: the warp-level scheduling never changes a game."""
+    players, pool, seed, n, k = 3, 1, 4242, 1000, 120
+    ref = O.fresh_records(n, players, pool, 0, seed, 5)
+    cref = O.rollout_random(ref, players, pool, 0, seed, 5, k, threads=8)
+    for block, defer in ((128, 1), (32, 7), (64, 16), (256, 32), (96, 24)):
+        eng = engine(n, players, pool, 0, seed=seed, game_id_base=5)
+        eng.set_block_threads(block)
+        eng.set_rollout_defer(defer)
+        eng.rollout_random(k)
+        assert np.array_equal(eng.export_records().cpu().numpy(), ref), (block, defer)
+        assert np.array_equal(eng.counters.cpu().numpy(), cref), (block, defer)
