@@ -381,7 +381,7 @@ int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_p
     AZB_CUDA(cudaSetDevice(device));
     azb_t* h = new azb_handle();
     h->device = device; h->n_games = n_games; h->players = players; h->tile_pool = tile_pool;
-    h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->defer = 16;
+    h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->defer = 32;
     *out = h;
     return 0;
 }
@@ -404,7 +404,7 @@ int azb_set_block_threads(azb_t* h, int threads)
 int azb_set_rollout_defer(azb_t* h, int games)
 {
     if (!h) return fail(AZB_E_INVALID, "null handle%s");
-    if (games == 0) games = 16;
+    if (games == 0) games = 32;
     if (games < 1 || games > 32) return fail(AZB_E_INVALID, "defer must be 1..32%s");
     h->defer = games;
     return 0;

@@ -36,7 +36,9 @@
 #if defined(__CUDACC__)
 #define AZB_HD __host__ __device__ __forceinline__
 #define AZB_M __host__ __device__ __forceinline__
+#define AZB_ROLLED _Pragma("unroll 1")   // keep rare, long paths small: the rollout kernel must fit the I-cache
 #else
+#define AZB_ROLLED
 #define AZB_HD static inline
 #define AZB_M inline
 #endif
@@ -293,23 +295,23 @@ AZB_HD void score_player(Game<P>& g, const int pl)
         wc |= (((row << r) | (row >> (5 - r))) & 31u) << (5 * r);
     }
     uint32_t combo = sta >> 28;
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, c = (pat >> (6 * r)) & 7u;
-        if (cnt == (uint32_t)(r + 1)) {                           // :216 line is full
-            pat &= ~(63u << (6 * r));                             // :218
-            wall |= 1u << (5 * r + c);                            // :219
-            if (POOL == POOL_LID) g.lid += (uint32_t)r << (6u * c);   // :220-222
-            uint32_t k = c + (uint32_t)r;
+    AZB_ROLLED
+    for (uint32_t r = 0; r < 5u; r++) {
+        const uint32_t sh6 = 6u * r, sh5 = 5u * r;
+        const uint32_t cnt = (pat >> (sh6 + 3u)) & 7u, c = (pat >> sh6) & 7u;
+        if (cnt == r + 1u) {                                      // :216 line is full
+            pat &= ~(63u << sh6);                                 // :218
+            wall |= 1u << (sh5 + c);                              // :219
+            if (POOL == POOL_LID) g.lid += r << (6u * c);         // :220-222
+            uint32_t k = c + r;
             k = k >= 5u ? k - 5u : k;                             // to_wall_position, :194-196
-            wc |= 1u << (5 * r + k);
-            const uint32_t rowbits = (wc >> (5 * r)) & 31u;
+            wc |= 1u << (sh5 + k);
+            const uint32_t rowbits = (wc >> sh5) & 31u;
             const int hr = ctz(~(rowbits >> (k + 1u)));           // :230-236 walk right
             const int hl = clz(~((rowbits << (31u - k)) << 1));   // :237-242 walk left
             const uint32_t colbits = (wc >> k) & M5;              // column k, bit 5j = row j
-            const int vd = (ctz(~(colbits >> (5 * (r + 1))) & M5) * 13) >> 6;      // :244-250 walk down
-            int vu = 0;                                           // :251-257 walk up
-            if (r > 0) vu = (clz(~(colbits << (31 - 5 * (r - 1))) & 0x84210800u) * 13) >> 6;
+            const int vd = (ctz(~(colbits >> (sh5 + 5u)) & M5) * 13) >> 6;                 // :244-250 walk down
+            const int vu = (clz(~((colbits << (31u - sh5)) << 5) & 0x84210800u) * 13) >> 6;  // :251-257 walk up
             const int h = hr + hl, v = vd + vu;
             const int pts = h + v + 1 + ((h > 0 && v > 0) ? 1 : 0);   // :258-263
             combo = (uint32_t)pts > combo ? (uint32_t)pts : combo;    // :264
@@ -381,32 +383,43 @@ AZB_HD int lid_draw(Game<P>& g, uint32_t& x)
     return c;
 }
 
-// azul.py:64-89 with the Philox draw schedule (DESIGN.md "RNG schedule")
+// azul.py:64-89 with the Philox draw schedule (DESIGN.md "RNG schedule"): call j of
+// Philox(gid, steps, purpose, j) yields words R[4j..4j+3]; Random pool: display i draws its four
+// colours from R[i] (c = mulhi(x,5), x *= 5); Lid pool: display i draws two colours from each of
+// R[2i], R[2i+1] (r = mulhi(x,total), x *= total).
 template <int P, int POOL>
 AZB_HD void new_round_philox(Game<P>& g, const Philox& rng, uint32_t gid, uint32_t purpose)
 {
     new_round_header(g);
-    uint32_t R[12];
-    rng(gid, g.steps, purpose, 0u, R);
-    rng(gid, g.steps, purpose, 1u, R + 4);
-    if (POOL == POOL_LID) rng(gid, g.steps, purpose, 2u, R + 8);
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
+    constexpr uint32_t CALLS = POOL == POOL_LID ? 3u : 2u;
+    AZB_ROLLED
+    for (uint32_t j = 0; j < CALLS; j++) {
+        uint32_t w[4];
+        rng(gid, g.steps, purpose, j, w);
         if (POOL == POOL_RANDOM) {
-            uint32_t x = R[i];
+            const uint32_t nq = j == 0u ? 4u : 1u;                // displays 0..3 from call 0, display 4 from call 1
+            AZB_ROLLED
+            for (uint32_t q = 0; q < nq; q++) {
+                uint32_t x = q == 0u ? w[0] : q == 1u ? w[1] : q == 2u ? w[2] : w[3];
+                const uint32_t d = 4u * j + q + 1u;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t c = mulhi(x, 5u);                  // :78 randrange(0,5)
-                x *= 5u;
-                plane_inc(g.pl0, g.pl1, g.pl2, (uint32_t)(i + 1) + 6u * c);
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t c = mulhi(x, 5u);              // :78 randrange(0,5)
+                    x *= 5u;
+                    plane_inc(g.pl0, g.pl1, g.pl2, d + 6u * c);
+                }
             }
         } else {
-            uint32_t x = 0;
+            const uint32_t nh = j == 2u ? 2u : 4u;                // half-displays: words 2i, 2i+1 of display i
+            AZB_ROLLED
+            for (uint32_t q = 0; q < nh; q++) {
+                uint32_t x = q == 0u ? w[0] : q == 1u ? w[1] : q == 2u ? w[2] : w[3];
+                const uint32_t d = 2u * j + (q >> 1) + 1u;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if ((j & 1) == 0) x = R[2 * i + (j >> 1)];
-                const int c = lid_draw(g, x);
-                if (c >= 0) plane_inc(g.pl0, g.pl1, g.pl2, (uint32_t)(i + 1) + 6u * (uint32_t)c);
+                for (int t = 0; t < 2; t++) {
+                    const int c = lid_draw(g, x);
+                    if (c >= 0) plane_inc(g.pl0, g.pl1, g.pl2, d + 6u * (uint32_t)c);
+                }
             }
         }
     }
@@ -673,44 +686,58 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                           const Vote vote, bool valid, int defer)
 {
     uint32_t aw[4] = {0u, 0u, 0u, 0u};
-    bool have_words = false, pending = false;
+    bool have_words = false;
     uint32_t rounds = 0;
     int remaining = valid ? k_steps : 0;
-    if (remaining > 0 && g.ended()) { reset_game<P, POOL>(g, rng, gid, first_rule); rounds++; }
+    // 0 playing, 1 round over: waits for score + refill, 2 waits for a fresh game (stuck / ended on entry)
+    int phase = (remaining > 0 && g.ended()) ? 2 : 0;
     for (;;) {
-        if (remaining > 0 && !pending) {
+        if (remaining > 0 && phase == 0) {
             uint32_t m[6];
             legal_mask(g, m);
-            if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u) {    // stuck round: abort + fresh game
-                sink.add(6, 1);
-                reset_game<P, POOL>(g, rng, gid, first_rule); rounds++;
-                legal_mask(g, m);
+            if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u) {
+                sink.add(6, 1);                                       // stuck round: abort the game
+                phase = 2;
+            } else {
+                if (!have_words || (g.steps & 3u) == 0u) { rng(gid, g.steps >> 2, PURPOSE_ACTION, 0u, aw); have_words = true; }
+                const uint32_t idx = g.steps & 3u;
+                const uint32_t word = idx == 0u ? aw[0] : idx == 1u ? aw[1] : idx == 2u ? aw[2] : aw[3];
+                apply_move<P, POOL>(g, random_action(m, word));       // azul.py:304
+                g.steps += 1u;
+                remaining--;
+                if (is_end_of_round(g)) phase = 1;                    // azul.py:306
+                else next_player(g);                                  // azul.py:313
             }
-            if (!have_words || (g.steps & 3u) == 0u) { rng(gid, g.steps >> 2, PURPOSE_ACTION, 0u, aw); have_words = true; }
-            const uint32_t idx = g.steps & 3u;
-            const uint32_t word = idx == 0u ? aw[0] : idx == 1u ? aw[1] : idx == 2u ? aw[2] : aw[3];
-            apply_move<P, POOL>(g, random_action(m, word));           // azul.py:304
-            g.steps += 1u;
-            remaining--;
-            if (is_end_of_round(g)) pending = true;                   // azul.py:306
-            else next_player(g);                                      // azul.py:313
         }
-        const int n_pending = vote.count(pending);
-        const int n_movable = vote.count(remaining > 0 && !pending);
-        if (n_pending > 0 && (n_pending >= defer || n_movable == 0)) {
-            if (pending) {
-                pending = false;
-                count_score<P, POOL>(g);                              // azul.py:307
+        const int n_waiting = vote.count(phase != 0);
+        const int n_movable = vote.count(remaining > 0 && phase == 0);
+        if (n_waiting > 0 && (n_waiting >= defer || n_movable == 0)) {
+            if (phase != 0) {
+                bool fresh = phase == 2;
+                phase = 0;
                 rounds++;
-                if (is_end_of_game(g)) {                              // azul.py:308-309
-                    g.misc |= 1u << 12;
-                    tally_finished(g, sink);
-                    reset_game<P, POOL>(g, rng, gid, first_rule);
-                } else {
-                    const uint32_t bag_before = g.status() & ST_BAG_EMPTY;
-                    new_round_philox<P, POOL>(g, rng, gid, PURPOSE_REFILL);   // azul.py:311
-                    if (!bag_before && (g.status() & ST_BAG_EMPTY)) sink.add(7, 1);
+                if (!fresh) {
+                    count_score<P, POOL>(g);                          // azul.py:307
+                    if (is_end_of_game(g)) {                          // azul.py:308-309
+                        g.misc |= 1u << 12;
+                        tally_finished(g, sink);
+                        fresh = true;
+                    }
                 }
+                uint32_t purpose = PURPOSE_REFILL;
+                if (fresh) {                                          // Azul(rules), game_runner.py:79
+                    uint32_t first = (uint32_t)first_rule;
+                    if (first_rule == 0) {                            // azul.py:36-37 random.choice
+                        uint32_t w[4];
+                        rng(gid, g.steps, PURPOSE_FIRST, 0u, w);
+                        first = 1u + mulhi(w[0], (uint32_t)P);
+                    }
+                    init_game<P, POOL>(g, first);
+                    purpose = PURPOSE_RESET_REFILL;
+                }
+                const uint32_t bag_before = g.status() & ST_BAG_EMPTY;
+                new_round_philox<P, POOL>(g, rng, gid, purpose);      // azul.py:311 / game_runner.py:80
+                if (!bag_before && (g.status() & ST_BAG_EMPTY)) sink.add(7, 1);
             }
         } else if (n_movable == 0) {
             break;

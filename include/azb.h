@@ -77,7 +77,7 @@ int azb_destroy(azb_t* h);
 /* threads per block for the kernels of this handle (multiple of 32, <= 1024); 0 = default */
 int azb_set_block_threads(azb_t* h, int threads);
 /* azb_rollout_random tuning: how many of a warp's 32 games must have reached the end of their round
- * before the warp runs the scoring / refill pass for them (1..32, 0 = default 16).  Results do not
+ * before the warp runs the scoring / refill pass for them (1..32, 0 = default 32).  Results do not
  * depend on it. */
 int azb_set_rollout_defer(azb_t* h, int games);
 
