@@ -40,14 +40,15 @@ FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallba
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=65536, help="games per GPU (BASELINE configs[1])")
     ap.add_argument("--players", type=int, default=2)
     ap.add_argument("--pool", default="lid", choices=["lid", "random"],
                     help="tile pool; 'lid' + random first player = GameRunner's default rules (game_runner.py:23)")
-    ap.add_argument("--k-steps", type=int, default=256, help="env steps per game per launch")
+    ap.add_argument("--k-steps", type=int, default=4096,
+                    help="env steps per game per launch (SURVEY §8d config 2: K = 4,096 with auto-reset)")
     ap.add_argument("--block", type=int, default=0, help="threads per block (0 = library default)")
     ap.add_argument("--defer", type=int, default=0, help="rollout end-of-round batching threshold (0 = library default)")
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED)
@@ -129,24 +130,67 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled every 10 ms through NVML (nvidia_ml_py) while the timed region
+    runs; falls back to an `nvidia-smi -lms` subprocess (the profiling recipe's clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index):
-        self.gpu_index, self.proc = gpu_index, None
+    def __init__(self, torch_device_index):
+        import threading
+        self.idx, self.proc, self.thread, self.stop_flag = torch_device_index, None, None, threading.Event()
+        self.sm, self.bits, self.max_mhz, self.power = [], 0, None, []
+        self.nvml = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join()
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.bits & bit)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                    "reasons": reasons, "source": "nvml, 10 ms period, timed region only"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"]}
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -167,7 +211,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------
