@@ -246,19 +246,17 @@ def run_b200(args):
     from azul_deep_reinforcement_learning_b200.engine import BatchedAzul
     from azul_deep_reinforcement_learning_b200.layout import algorithmic_bytes_per_step
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from azul_deep_reinforcement_learning_b200 import parallel
+    rank, world, local = parallel.world()
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        parallel.init("nccl", local)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     pool = 1 if args.pool == "lid" else 0
     G, K = args.games, args.k_steps
 
-    eng = BatchedAzul(G, args.players, pool, 0, seed=args.seed, device=local, game_id_base=rank * G)
+    eng = BatchedAzul(G, args.players, pool, 0, seed=args.seed, device=local, game_id_base=parallel.shard(rank, G))
     if args.block:
         eng.set_block_threads(args.block)
     if args.defer:
@@ -291,10 +289,7 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = sum(kernel_ms)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
+    dev_ms_max = parallel.max_over_ranks(dev_ms, dev)
 
     # ---- end to end through the host API ------------------------------------------------
     host_state = torch.empty(eng.state.shape, dtype=torch.int32).pin_memory()
@@ -309,17 +304,12 @@ def run_b200(args):
     for _ in range(e2e_steps):
         eng.rollout_random_host(host_state, K, host_mask, host_cnt)
     barrier()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
     h2d = host_state.numel() * 4
     d2h = host_state.numel() * 4 + host_mask.numel() * 4 + host_cnt.numel() * 8
 
     # ---- rollout statistics (C2: one small allreduce) -----------------------------------
-    cnt = eng.counters.clone()
-    if world > 1:
-        dist.all_reduce(cnt)
-    cnt = cnt.cpu().tolist()
+    cnt = parallel.reduce_counters(eng.counters.clone()).cpu().tolist()
 
     if rank == 0:
         steps_total = world * G * K * args.steps
@@ -333,7 +323,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config(args, world),
-            "e2e": {"value": world * G * K * e2e_steps / float(e2e_t.item()), "unit": UNIT,
+            "e2e": {"value": world * G * K * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
