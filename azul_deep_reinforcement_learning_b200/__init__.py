@@ -6,7 +6,7 @@ from .layout import (  # noqa: F401
 
 def __getattr__(name):
     # torch / CUDA are only needed once the engine is touched
-    if name in ("BatchedAzul", "mask_to_bool", "COUNTER_NAMES"):
+    if name in ("BatchedAzul", "mask_to_bool", "COUNTER_NAMES", "PackedPolicy", "policy_step"):
         from . import engine
         return getattr(engine, name)
     raise AttributeError(name)

@@ -10,52 +10,25 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "../../include/azb.h"
+#include "azb_internal.h"
 #include "azb_rules.cuh"
 
 using namespace azb;
 
 // ------------------------------------------------------------------------------------------
-// handle + error plumbing
+// error plumbing
 // ------------------------------------------------------------------------------------------
-struct azb_handle {
-    int device;
-    int64_t n_games;
-    int players;
-    int tile_pool;
-    int first_player;
-    uint64_t seed;
-    uint64_t game_id_base;
-    int block_threads;
-    int defer;             // rollout: games of a warp that must be waiting before the end-of-round pass runs
-};
-
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, const char* detail = "")
+int azb_fail(int code, const char* fmt, const char* detail)
 {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
 }
 
-#define AZB_CUDA(call)                                                                     \
-    do {                                                                                   \
-        cudaError_t e_ = (call);                                                           \
-        if (e_ != cudaSuccess) return fail(AZB_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
-    } while (0)
-
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-struct Launch {
-    const uint32_t* __restrict__ state_in;
-    uint32_t* __restrict__ state;
-    int64_t n;
-    uint32_t k0, k1;       // Philox key
-    uint32_t gid0;         // global id of game 0
-    int first_rule;
-};
-
 __device__ __forceinline__ void store_mask(uint32_t* __restrict__ mask6, int64_t n, int64_t g, const uint32_t m[6])
 {
 #pragma unroll
@@ -338,23 +311,7 @@ __global__ void k_round_flags(const uint32_t* __restrict__ s, int64_t n, uint8_t
     if ((h)->tile_pool == AZB_POOL_LID) { constexpr int POOL = 1; DISPATCH_P(h, EXPR) } \
     else { constexpr int POOL = 0; DISPATCH_P(h, EXPR) }
 
-static Launch make_launch(const azb_t* h, uint32_t* state)
-{
-    Launch L;
-    L.state_in = state; L.state = state; L.n = h->n_games;
-    L.k0 = (uint32_t)h->seed; L.k1 = (uint32_t)(h->seed >> 32);
-    L.gid0 = (uint32_t)h->game_id_base;
-    L.first_rule = h->first_player;
-    return L;
-}
-
 static inline dim3 grid_of(const azb_t* h) { return dim3((unsigned)((h->n_games + h->block_threads - 1) / h->block_threads)); }
-
-#define CHECK_HANDLE(h)                                       \
-    if (!(h)) return fail(AZB_E_INVALID, "null handle%s");    \
-    AZB_CUDA(cudaSetDevice((h)->device));
-
-#define CHECK_LAUNCH() AZB_CUDA(cudaGetLastError())
 
 extern "C" {
 
@@ -367,21 +324,22 @@ const char* azb_last_error(void) { return g_err; }
 int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_pool, int first_player,
                uint64_t seed, uint64_t game_id_base)
 {
-    if (!out) return fail(AZB_E_INVALID, "out is null%s");
+    if (!out) return azb_fail(AZB_E_INVALID, "out is null%s");
     *out = nullptr;
-    if (players < 2 || players > 4) return fail(AZB_E_INVALID, "players must be 2..4%s");
-    if (tile_pool != AZB_POOL_RANDOM && tile_pool != AZB_POOL_LID) return fail(AZB_E_INVALID, "tile_pool must be 0 (Random) or 1 (Lid)%s");
-    if (first_player < 0 || first_player > players) return fail(AZB_E_INVALID, "first_player must be 0 (Random) or 1..players%s");   // IllegalRule, azul.py:40-41
-    if (n_games < 1 || n_games > (int64_t)1 << 31) return fail(AZB_E_INVALID, "n_games out of range%s");
+    if (players < 2 || players > 4) return azb_fail(AZB_E_INVALID, "players must be 2..4%s");
+    if (tile_pool != AZB_POOL_RANDOM && tile_pool != AZB_POOL_LID) return azb_fail(AZB_E_INVALID, "tile_pool must be 0 (Random) or 1 (Lid)%s");
+    if (first_player < 0 || first_player > players) return azb_fail(AZB_E_INVALID, "first_player must be 0 (Random) or 1..players%s");   // IllegalRule, azul.py:40-41
+    if (n_games < 1 || n_games > (int64_t)1 << 31) return azb_fail(AZB_E_INVALID, "n_games out of range%s");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
-        return fail(AZB_E_NODEVICE, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
-    if (device < 0 || device >= count) return fail(AZB_E_INVALID, "device index out of range%s");
+        return azb_fail(AZB_E_NODEVICE, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return azb_fail(AZB_E_INVALID, "device index out of range%s");
     AZB_CUDA(cudaSetDevice(device));
     azb_t* h = new azb_handle();
     h->device = device; h->n_games = n_games; h->players = players; h->tile_pool = tile_pool;
     h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->defer = 32;
+    AZB_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     *out = h;
     return 0;
 }
@@ -394,18 +352,18 @@ int azb_destroy(azb_t* h)
 
 int azb_set_block_threads(azb_t* h, int threads)
 {
-    if (!h) return fail(AZB_E_INVALID, "null handle%s");
+    if (!h) return azb_fail(AZB_E_INVALID, "null handle%s");
     if (threads == 0) threads = 128;
-    if (threads < 32 || threads > 1024 || threads % 32) return fail(AZB_E_INVALID, "block threads must be a multiple of 32 in 32..1024%s");
+    if (threads < 32 || threads > 1024 || threads % 32) return azb_fail(AZB_E_INVALID, "block threads must be a multiple of 32 in 32..1024%s");
     h->block_threads = threads;
     return 0;
 }
 
 int azb_set_rollout_defer(azb_t* h, int games)
 {
-    if (!h) return fail(AZB_E_INVALID, "null handle%s");
+    if (!h) return azb_fail(AZB_E_INVALID, "null handle%s");
     if (games == 0) games = 32;
-    if (games < 1 || games > 32) return fail(AZB_E_INVALID, "defer must be 1..32%s");
+    if (games < 1 || games > 32) return azb_fail(AZB_E_INVALID, "defer must be 1..32%s");
     h->defer = games;
     return 0;
 }
@@ -413,7 +371,7 @@ int azb_set_rollout_defer(azb_t* h, int games)
 int azb_reset(azb_t* h, uint32_t* state, const uint8_t* which, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_reset<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, which)));
     CHECK_LAUNCH();
@@ -423,7 +381,7 @@ int azb_reset(azb_t* h, uint32_t* state, const uint8_t* which, void* stream)
 int azb_legal_mask(azb_t* h, const uint32_t* state, uint32_t* mask6, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !mask6) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !mask6) return azb_fail(AZB_E_INVALID, "null buffer%s");
     DISPATCH_P(h, (k_legal_mask<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, mask6)));
     CHECK_LAUNCH();
     return 0;
@@ -433,7 +391,7 @@ int azb_step(azb_t* h, uint32_t* state, const uint8_t* action, const int8_t* dra
              int16_t* preview_out, uint8_t* done_out, uint8_t* status_out, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !action) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !action) return azb_fail(AZB_E_INVALID, "null buffer%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_step<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
                        L, action, draws20, mask6_out, preview_out, done_out, status_out)));
@@ -445,8 +403,8 @@ int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_o
                        void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state) return fail(AZB_E_INVALID, "state is null%s");
-    if (k_steps < 0) return fail(AZB_E_INVALID, "k_steps < 0%s");
+    if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
+    if (k_steps < 0) return azb_fail(AZB_E_INVALID, "k_steps < 0%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_rollout_random<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
                        L, k_steps, h->defer, mask6_out, counters)));
@@ -457,7 +415,7 @@ int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_o
 int azb_score_preview(azb_t* h, const uint32_t* state, int16_t* score_out, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !score_out) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !score_out) return azb_fail(AZB_E_INVALID, "null buffer%s");
     DISPATCH_PP(h, (k_score_preview<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, score_out)));
     CHECK_LAUNCH();
     return 0;
@@ -466,7 +424,7 @@ int azb_score_preview(azb_t* h, const uint32_t* state, int16_t* score_out, void*
 int azb_import_state(azb_t* h, const int32_t* records, uint32_t* state, uint8_t* ok_out, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !records) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !records) return azb_fail(AZB_E_INVALID, "null buffer%s");
     DISPATCH_P(h, (k_import<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(records, state, h->n_games, ok_out)));
     CHECK_LAUNCH();
     return 0;
@@ -475,7 +433,7 @@ int azb_import_state(azb_t* h, const int32_t* records, uint32_t* state, uint8_t*
 int azb_export_state(azb_t* h, const uint32_t* state, int32_t* records, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !records) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !records) return azb_fail(AZB_E_INVALID, "null buffer%s");
     DISPATCH_P(h, (k_export<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, records, h->n_games)));
     CHECK_LAUNCH();
     return 0;
@@ -484,8 +442,8 @@ int azb_export_state(azb_t* h, const uint32_t* state, int32_t* records, void* st
 int azb_observe(azb_t* h, const uint32_t* state, int perspective, float* obs, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !obs) return fail(AZB_E_INVALID, "null buffer%s");
-    if (perspective < -1 || perspective >= h->players) return fail(AZB_E_INVALID, "perspective out of range%s");
+    if (!state || !obs) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    if (perspective < -1 || perspective >= h->players) return azb_fail(AZB_E_INVALID, "perspective out of range%s");
     DISPATCH_P(h, (k_observe<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, perspective, obs)));
     CHECK_LAUNCH();
     return 0;
@@ -494,7 +452,7 @@ int azb_observe(azb_t* h, const uint32_t* state, int perspective, float* obs, vo
 int azb_stats(azb_t* h, const uint32_t* state, int32_t* stats10, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !stats10) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !stats10) return azb_fail(AZB_E_INVALID, "null buffer%s");
     DISPATCH_P(h, (k_stats<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, stats10)));
     CHECK_LAUNCH();
     return 0;
@@ -503,7 +461,7 @@ int azb_stats(azb_t* h, const uint32_t* state, int32_t* stats10, void* stream)
 int azb_move(azb_t* h, uint32_t* state, const uint8_t* action, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !action) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !action) return azb_fail(AZB_E_INVALID, "null buffer%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_op<P, POOL, 0><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, action, nullptr)));
     CHECK_LAUNCH();
@@ -513,7 +471,7 @@ int azb_move(azb_t* h, uint32_t* state, const uint8_t* action, void* stream)
 int azb_next_player(azb_t* h, uint32_t* state, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_op<P, POOL, 1><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, nullptr, nullptr)));
     CHECK_LAUNCH();
@@ -523,7 +481,7 @@ int azb_next_player(azb_t* h, uint32_t* state, void* stream)
 int azb_count_score(azb_t* h, uint32_t* state, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_op<P, POOL, 2><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, nullptr, nullptr)));
     CHECK_LAUNCH();
@@ -533,7 +491,7 @@ int azb_count_score(azb_t* h, uint32_t* state, void* stream)
 int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state) return fail(AZB_E_INVALID, "state is null%s");
+    if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_op<P, POOL, 3><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, nullptr, draws20)));
     CHECK_LAUNCH();
@@ -543,7 +501,7 @@ int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream
 int azb_round_flags(azb_t* h, const uint32_t* state, uint8_t* flags, void* stream)
 {
     CHECK_HANDLE(h);
-    if (!state || !flags) return fail(AZB_E_INVALID, "null buffer%s");
+    if (!state || !flags) return azb_fail(AZB_E_INVALID, "null buffer%s");
     DISPATCH_P(h, (k_round_flags<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, flags)));
     CHECK_LAUNCH();
     return 0;

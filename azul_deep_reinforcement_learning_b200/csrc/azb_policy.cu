@@ -1,0 +1,537 @@
+// azb_policy.cu -- K4: the ActorCritic MLP (reference azulnet/model.py:12-41) fused with the
+// observation builder (game_runner.py:56-72), masked softmax / log-softmax (model.py:37-40),
+// action sampling (agent.py:64-81), the entropy term of nn_runner.py:36-40 and, optionally, the
+// env step, for a batch of 2-player games.
+//
+// Shape of the work: 128 games per tile (one game per thread, one tile per pass of a persistent CTA).
+//   layer 1   [128 x 144] x [144 x 368]   obs (136, zero-padded to 144) times [W1_actor ; W1_critic]^T
+//             (180 + 180 hidden units, padded to 192 + 176)                    -> TMEM columns [0,368)
+//   layer 2   [128 x 192] x [192 x 192]   relu(hidden_actor) times W2_actor^T   -> TMEM columns [0,192)
+//   critic    value = w2c . relu(hidden_critic) + b2c on CUDA cores straight from the TMEM row
+// Both dense layers run on the 5th-generation tensor cores: tcgen05.mma (kind::f16, bf16 inputs, fp32
+// accumulate in TMEM), issued by one thread, operands in shared memory in the canonical K-major
+// no-swizzle core-matrix layout, accumulators read back with tcgen05.ld 32x32b (thread t <- TMEM lane t,
+// i.e. every thread receives exactly the row of its own game, so softmax and sampling need no
+// cross-thread traffic).  The bf16 weights (180 KB) stay resident in shared memory for the lifetime of
+// the CTA; the observation tile is generated in-kernel from the packed state and never touches HBM.
+#include <cuda_bf16.h>
+
+#include "azb_internal.h"
+#include "azb_rules.cuh"
+
+using namespace azb;
+
+namespace pol {
+
+constexpr int TILE_M = 128;                 // games per tile == threads per CTA
+constexpr int K1 = 144, K1_CHUNKS = K1 / 8; // obs 136 -> 144 (multiple of the MMA K = 16)
+constexpr int N1A = 192, N1C = 176;         // hidden units per head, padded to a multiple of 16
+constexpr int N1 = N1A + N1C, N1_GROUPS = N1 / 8;
+constexpr int K2 = 192, K2_CHUNKS = K2 / 8;
+constexpr int N2 = 192, N2_GROUPS = N2 / 8;
+constexpr int M_GROUPS = TILE_M / 8;
+constexpr int HID = 180, ACT = 180, OBS = 136;
+
+// shared-memory image (bytes).  A core matrix is 8 rows x 16 bytes = 128 contiguous bytes; a tile is
+// stored [k-chunk][row-group][8 rows][8 bf16], so SBO (next row group) = 128 B and LBO (next k-chunk)
+// = groups * 128 B.
+constexpr int W1_BYTES = K1_CHUNKS * N1_GROUPS * 128;        // 105,984
+constexpr int W2_BYTES = K2_CHUNKS * N2_GROUPS * 128;        //  73,728
+constexpr int A_BYTES = K2_CHUNKS * M_GROUPS * 128;          //  49,152 (layer-2 A; layer-1 A aliases its start)
+constexpr int OFF_W1 = 0;
+constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
+constexpr int OFF_VEC = OFF_W2 + W2_BYTES;                    // fp32 vectors: b1a[192] b1c[176] w2c[176] b2a[192] b2c[1] pad[3]
+constexpr int VEC_FLOATS = N1A + N1C + N1C + N2 + 4;
+constexpr int PACKED_BYTES = OFF_VEC + VEC_FLOATS * 4;        // what azb_policy_pack_weights produces
+constexpr int OFF_A = (PACKED_BYTES + 127) / 128 * 128;
+constexpr int OFF_BAR = OFF_A + A_BYTES;                      // 2 mbarriers + tmem base
+constexpr int SMEM_BYTES = OFF_BAR + 32;
+static_assert(SMEM_BYTES <= 232448, "policy kernel exceeds the 227 KB shared memory of an SM");
+
+constexpr int V_B1A = 0, V_B1C = N1A, V_W2C = N1A + N1C, V_B2A = N1A + 2 * N1C, V_B2C = N1A + 2 * N1C + N2;
+
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// [13:0] start >> 4, [29:16] leading byte offset >> 4 (next k-chunk), [45:32] stride byte offset >> 4 (next
+// 8-row group), [47:46] version = 1, [63:61] layout type 0
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (InstrDescriptor): fp32 accumulate, bf16 x bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t instr_desc(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+// exact float of a small non-negative integer without the conversion pipe
+__device__ __forceinline__ float small_int_to_float(uint32_t n) { return __uint_as_float(0x4B000000u | n) - 8388608.0f; }
+
+// ---- observation (game_runner.py:56-72), perspective = the seat to move -----------------------
+template <int IDX>
+__device__ __forceinline__ float obs_value(const Game<2>& g, uint32_t pat_me, uint32_t pat_ot, uint32_t wall_me,
+                                           uint32_t wall_ot, uint32_t scf_me, uint32_t scf_ot, int persp)
+{
+    if constexpr (IDX < 25) {                         // displays[i][c]
+        constexpr int i = IDX / 5, c = IDX % 5, b = i + 1 + 6 * c;
+        return small_int_to_float(((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2));
+    } else if constexpr (IDX < 30) {                  // centre colour counts
+        constexpr int c = IDX - 25, b = 6 * c;
+        return small_int_to_float(((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2) |
+                                  (((g.misc >> c) & 1u) << 3));
+    } else if constexpr (IDX == 30) {                 // first-player token
+        return (g.misc & 32u) ? 1.0f : 0.0f;
+    } else if constexpr (IDX < 81) {                  // pattern lines, mine then the opponent's
+        constexpr int q = IDX - 31, r = (q % 25) / 5, c = q % 5;
+        const uint32_t pat = q < 25 ? pat_me : pat_ot;
+        const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, col = (pat >> (6 * r)) & 7u;
+        return (col == (uint32_t)c) ? small_int_to_float(cnt) : 0.0f;
+    } else if constexpr (IDX < 131) {                 // walls (colour-indexed, game_runner.py:69)
+        constexpr int q = IDX - 81, bit = q % 25;
+        const uint32_t w = q < 25 ? wall_me : wall_ot;
+        return ((w >> bit) & 1u) ? 1.0f : 0.0f;
+    } else if constexpr (IDX == 131) { return small_int_to_float((scf_me >> 16) & 7u);
+    } else if constexpr (IDX == 132) { return small_int_to_float((scf_ot >> 16) & 7u);
+    } else if constexpr (IDX == 133) { return small_int_to_float(scf_me & 0xFFFFu);
+    } else if constexpr (IDX == 134) { return small_int_to_float(scf_ot & 0xFFFFu);
+    } else if constexpr (IDX == 135) {                // next first player seen from this seat (game_runner.py:58-61)
+        const int nf = (int)g.next_first_player();
+        return nf > 0 ? small_int_to_float((uint32_t)(((nf - 1 - persp) & 1) + 1)) : 0.0f;
+    } else {
+        return 0.0f;
+    }
+}
+
+template <int CH>
+__device__ __forceinline__ void obs_chunks(const Game<2>& g, uint32_t pat_me, uint32_t pat_ot, uint32_t wall_me,
+                                           uint32_t wall_ot, uint32_t scf_me, uint32_t scf_ot, int persp,
+                                           unsigned char* a_tile, int row)
+{
+    if constexpr (CH < K1_CHUNKS) {
+#define OV(i) obs_value<8 * CH + (i)>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp)
+        uint4 v;
+        v.x = pack_bf16(OV(0), OV(1)); v.y = pack_bf16(OV(2), OV(3));
+        v.z = pack_bf16(OV(4), OV(5)); v.w = pack_bf16(OV(6), OV(7));
+#undef OV
+        *reinterpret_cast<uint4*>(a_tile + (CH * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = v;
+        obs_chunks<CH + 1>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row);
+    }
+}
+
+__device__ __forceinline__ void build_obs_tile(const Game<2>& g, unsigned char* a_tile, int row)
+{
+    const int persp = g.seat();
+    const uint32_t pat_me = g.sel(g.pat, persp), pat_ot = g.sel(g.pat, 1 - persp);
+    const uint32_t wall_me = g.sel(g.wall, persp), wall_ot = g.sel(g.wall, 1 - persp);
+    const uint32_t scf_me = g.sel(g.scf, persp), scf_ot = g.sel(g.scf, 1 - persp);
+    obs_chunks<0>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row);
+}
+
+// 6 x 30-bit mask words (word p = destination p) -> 180 contiguous bits, bit a = action a
+__device__ __forceinline__ void linear_mask(const uint32_t m[6], uint32_t lin[6])
+{
+    lin[0] = m[0] | (m[1] << 30);
+    lin[1] = (m[1] >> 2) | (m[2] << 28);
+    lin[2] = (m[2] >> 4) | (m[3] << 26);
+    lin[3] = (m[3] >> 6) | (m[4] << 24);
+    lin[4] = (m[4] >> 8) | (m[5] << 22);
+    lin[5] = m[5] >> 10;
+}
+
+__device__ __forceinline__ uint32_t pick6(const uint32_t (&a)[6], int i)
+{
+    return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : i == 3 ? a[3] : i == 4 ? a[4] : a[5];
+}
+
+struct PolicyArgs {
+    const uint32_t* __restrict__ state_in;   // packed state (read)
+    uint32_t* __restrict__ state;            // packed state (written when apply_step)
+    int64_t n;
+    const unsigned char* __restrict__ packed;
+    uint32_t k0, k1, gid0;
+    int mode;            // 0 sample from the masked policy, 1 argmax (agent.py action_selection)
+    int apply_step;      // also execute Azul.step with the chosen action (Philox refill)
+    float* __restrict__ logits_out;          // [n][180] raw logits (debug / parity), may be null
+    float* __restrict__ value_out;           // [n]
+    uint8_t* __restrict__ action_out;        // [n]
+    float* __restrict__ logp_out;            // [n] log pi(action)
+    float* __restrict__ entropy_out;         // [n] -mean(log pi over legal actions) (nn_runner.py:36-40)
+    uint8_t* __restrict__ done_out;          // [n]
+    uint8_t* __restrict__ status_out;        // [n]
+    uint32_t* __restrict__ mask6_out;        // [6][n] legal mask used for the decision
+};
+
+constexpr uint32_t PURPOSE_POLICY = 4;
+
+template <int POOL>
+__global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned char* a_tile = smem + OFF_A;
+    const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
+    const uint32_t bar1 = smem_u32(smem + OFF_BAR), bar2 = bar1 + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+
+    // one-time: weights image -> shared memory, barriers, tensor memory
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(A.packed);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < PACKED_BYTES / 16; i += TILE_M) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        mbar_init(bar1, 1);
+        mbar_init(bar2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+
+    const uint32_t w1_addr = smem_u32(smem + OFF_W1), w2_addr = smem_u32(smem + OFF_W2), a_addr = smem_u32(a_tile);
+    const Philox rng{A.k0, A.k1};
+    uint32_t phase = 0;
+    const int64_t tiles = (A.n + TILE_M - 1) / TILE_M;
+
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t g = tile * TILE_M + tid;
+        const bool valid = g < A.n;
+        const int64_t gl = valid ? g : A.n - 1;
+        Game<2> gm;
+        gm.load(A.state_in, A.n, gl);
+
+        // ---- observation tile -> shared memory (layer-1 A operand) ----
+        build_obs_tile(gm, a_tile, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- layer 1 on the tensor cores ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int s = 0; s < K1 / 16; s++) {
+                const uint64_t ad = smem_desc(a_addr + s * 2 * (M_GROUPS * 128), M_GROUPS * 128, 128);
+                const uint64_t bd_a = smem_desc(w1_addr + s * 2 * (N1_GROUPS * 128), N1_GROUPS * 128, 128);
+                const uint64_t bd_c = smem_desc(w1_addr + (N1A / 8) * 128 + s * 2 * (N1_GROUPS * 128), N1_GROUPS * 128, 128);
+                umma(tmem_base, ad, bd_a, instr_desc(N1A), s > 0);
+                umma(tmem_base + N1A, ad, bd_c, instr_desc(N1C), s > 0);
+            }
+            umma_commit(bar1);
+        }
+        mbar_wait(bar1, phase);
+        tc_fence_after();
+
+        // ---- epilogue 1: actor hidden -> relu -> bf16 -> shared memory (layer-2 A operand, aliases the obs tile) ----
+#pragma unroll 1
+        for (int c0 = 0; c0 < N1A; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_row + c0, v);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 o;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int j = c0 + 8 * q + 2 * e;
+                    ow[e] = pack_bf16(fmaxf(v[8 * q + 2 * e] + vec[V_B1A + j], 0.0f), fmaxf(v[8 * q + 2 * e + 1] + vec[V_B1A + j + 1], 0.0f));
+                }
+                *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (tid >> 3)) * 128 + (tid & 7) * 16) = o;
+            }
+        }
+        // ---- critic head on CUDA cores straight from TMEM: value = w2c . relu(h_c + b1c) + b2c ----
+        float value = vec[V_B2C];
+#pragma unroll 1
+        for (int c0 = 0; c0 < 160; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_row + N1A + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) value = fmaf(fmaxf(v[i] + vec[V_B1C + c0 + i], 0.0f), vec[V_W2C + c0 + i], value);
+        }
+        {
+            float v[16];
+            tmem_ld16(tmem_row + N1A + 160, v);
+#pragma unroll
+            for (int i = 0; i < 16; i++) value = fmaf(fmaxf(v[i] + vec[V_B1C + 160 + i], 0.0f), vec[V_W2C + 160 + i], value);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- layer 2 on the tensor cores ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int s = 0; s < K2 / 16; s++) {
+                const uint64_t ad = smem_desc(a_addr + s * 2 * (M_GROUPS * 128), M_GROUPS * 128, 128);
+                const uint64_t bd = smem_desc(w2_addr + s * 2 * (N2_GROUPS * 128), N2_GROUPS * 128, 128);
+                umma(tmem_base, ad, bd, instr_desc(N2), s > 0);
+            }
+            umma_commit(bar2);
+        }
+        mbar_wait(bar2, phase);
+        tc_fence_after();
+        phase ^= 1;
+
+        // ---- epilogue 2: masked softmax / log-softmax, sampling, entropy term ----
+        uint32_t m[6], lin[6];
+        legal_mask(gm, m);
+        linear_mask(m, lin);
+        const int n_valid = __popc(lin[0]) + __popc(lin[1]) + __popc(lin[2]) + __popc(lin[3]) + __popc(lin[4]) + __popc(lin[5]);
+        // pass 1: running max and sum of exp over the legal logits (online softmax), sum of legal logits, argmax
+        float mx = -INFINITY, se = 0.0f, sl = 0.0f;
+        int amax = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 192; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_row + c0, v);
+            const uint32_t bits = pick6(lin, c0 >> 5);
+            if (A.logits_out && valid) {
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if (c0 + i < ACT) A.logits_out[g * ACT + c0 + i] = v[i] + vec[V_B2A + c0 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                if ((bits >> i) & 1u) {
+                    const float l = v[i] + vec[V_B2A + c0 + i];
+                    sl += l;
+                    if (l > mx) { se = se * __expf(mx - l) + 1.0f; mx = l; amax = c0 + i; }
+                    else se += __expf(l - mx);
+                }
+            }
+        }
+        const float lse = mx + __logf(se);              // log sum exp over the legal actions
+        uint32_t action = (uint32_t)amax;
+        if (A.mode == 0 && n_valid > 0) {
+            // pass 2: inverse-CDF sampling with one Philox word (agent.py:69 np.random.choice(p = policy))
+            uint32_t w[4];
+            rng(A.gid0 + (uint32_t)gl, gm.steps >> 2, PURPOSE_POLICY, 0u, w);
+            const uint32_t idx = gm.steps & 3u;
+            const uint32_t word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
+            const float target = (float)(word >> 8) * (1.0f / 16777216.0f) * se;
+            float cum = 0.0f;
+            bool found = false;
+            int last = amax;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 192; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_row + c0, v);
+                const uint32_t bits = pick6(lin, c0 >> 5);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    if (((bits >> i) & 1u) && !found) {
+                        cum += __expf(v[i] + vec[V_B2A + c0 + i] - mx);
+                        last = c0 + i;
+                        if (cum > target) { found = true; }
+                    }
+                }
+            }
+            action = (uint32_t)last;
+        }
+        // log pi(action) needs that one logit again: one more 32-column read of the right block
+        float logp = 0.0f;
+        if (n_valid > 0) {
+            float la = 0.0f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 192; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_row + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if ((uint32_t)(c0 + i) == action) la = v[i] + vec[V_B2A + c0 + i];
+            }
+            logp = la - lse;
+        }
+        const float entropy = n_valid > 0 ? -(sl / (float)n_valid - lse) : 0.0f;
+
+        uint32_t status = n_valid > 0 ? 0u : (gm.ended() ? (uint32_t)ST_ENDED : (uint32_t)ST_STUCK);
+        if (valid) {
+            if (A.mask6_out) {
+#pragma unroll
+                for (int p = 0; p < 6; p++) A.mask6_out[p * A.n + g] = m[p];
+            }
+            if (A.value_out) A.value_out[g] = value;
+            if (A.action_out) A.action_out[g] = n_valid > 0 ? (uint8_t)action : (uint8_t)AZB_ACTION_SKIP;
+            if (A.logp_out) A.logp_out[g] = logp;
+            if (A.entropy_out) A.entropy_out[g] = entropy;
+        }
+        if (A.apply_step && n_valid > 0 && !gm.ended()) {
+            const uint32_t gid = A.gid0 + (uint32_t)gl;
+            advance<2, POOL>(gm, action, [&](Game<2>& gg) { new_round_philox<2, POOL>(gg, rng, gid, PURPOSE_REFILL); });
+            if (valid) gm.store(A.state, A.n, g);
+        }
+        if (valid) {
+            if (A.done_out) A.done_out[g] = gm.ended() ? 1 : 0;
+            if (A.status_out) A.status_out[g] = (uint8_t)(status | gm.status());
+        }
+        // every thread's TMEM reads are complete before the next tile's layer 1 overwrites the accumulators
+        tc_fence_before();
+        __syncthreads();
+    }
+
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// fp32 torch-layout weights -> the bf16 shared-memory image
+__global__ void k_pack_weights(const float* __restrict__ w1a, const float* __restrict__ b1a, const float* __restrict__ w2a,
+                               const float* __restrict__ b2a, const float* __restrict__ w1c, const float* __restrict__ b1c,
+                               const float* __restrict__ w2c, const float* __restrict__ b2c, unsigned char* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per bf16 element of W1 / W2, then the fp32 vectors
+    if (i < N1 * K1) {
+        const int n = i / K1, k = i % K1;
+        float v = 0.0f;
+        if (k < OBS) {
+            if (n < HID) v = w1a[n * OBS + k];
+            else if (n >= N1A && n - N1A < HID) v = w1c[(n - N1A) * OBS + k];
+        }
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        *reinterpret_cast<__nv_bfloat16*>(out + OFF_W1 + ((k >> 3) * N1_GROUPS + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2) = b;
+    } else if (i < N1 * K1 + N2 * K2) {
+        const int j = i - N1 * K1, n = j / K2, k = j % K2;
+        const float v = (n < ACT && k < HID) ? w2a[n * HID + k] : 0.0f;
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        *reinterpret_cast<__nv_bfloat16*>(out + OFF_W2 + ((k >> 3) * N2_GROUPS + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2) = b;
+    } else if (i < N1 * K1 + N2 * K2 + VEC_FLOATS) {
+        const int j = i - N1 * K1 - N2 * K2;
+        float v = 0.0f;
+        if (j < V_B1C) { if (j < HID) v = b1a[j]; }
+        else if (j < V_W2C) { if (j - V_B1C < HID) v = b1c[j - V_B1C]; }
+        else if (j < V_B2A) { if (j - V_W2C < HID) v = w2c[j - V_W2C]; }
+        else if (j < V_B2C) { if (j - V_B2A < ACT) v = b2a[j - V_B2A]; }
+        else if (j == V_B2C) v = b2c[0];
+        reinterpret_cast<float*>(out + OFF_VEC)[j] = v;
+    }
+}
+
+}  // namespace pol
+
+extern "C" {
+
+int azb_policy_packed_bytes(void) { return pol::PACKED_BYTES; }
+
+int azb_policy_pack_weights(azb_t* h, const float* w1a, const float* b1a, const float* w2a, const float* b2a,
+                            const float* w1c, const float* b1c, const float* w2c, const float* b2c, void* packed,
+                            void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !packed) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    const int total = pol::N1 * pol::K1 + pol::N2 * pol::K2 + pol::VEC_FLOATS;
+    pol::k_pack_weights<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w1a, b1a, w2a, b2a, w1c, b1c, w2c, b2c,
+                                                                              (unsigned char*)packed);
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int apply_step, uint8_t* action_out,
+                    float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
+                    uint8_t* status_out, float* logits_out, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !packed) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    if (h->players != 2) return azb_fail(AZB_E_INVALID, "the policy network is defined for 2 players (136 inputs, agent.py:29)%s");
+    if (mode != 0 && mode != 1) return azb_fail(AZB_E_INVALID, "mode must be 0 (sample) or 1 (argmax)%s");
+    pol::PolicyArgs A;
+    A.state_in = state; A.state = state; A.n = h->n_games; A.packed = (const unsigned char*)packed;
+    A.k0 = (uint32_t)h->seed; A.k1 = (uint32_t)(h->seed >> 32); A.gid0 = (uint32_t)h->game_id_base;
+    A.mode = mode; A.apply_step = apply_step;
+    A.logits_out = logits_out; A.value_out = value_out; A.action_out = action_out; A.logp_out = logp_out;
+    A.entropy_out = entropy_out; A.done_out = done_out; A.status_out = status_out; A.mask6_out = mask6_out;
+    const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;
+    const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+    if (h->tile_pool == AZB_POOL_LID) {
+        AZB_CUDA(cudaFuncSetAttribute(pol::k_policy<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
+        pol::k_policy<1><<<grid, pol::TILE_M, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    } else {
+        AZB_CUDA(cudaFuncSetAttribute(pol::k_policy<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
+        pol::k_policy<0><<<grid, pol::TILE_M, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
+    }
+    CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

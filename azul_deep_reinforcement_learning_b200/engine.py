@@ -215,6 +215,49 @@ class BatchedAzul:
         return out
 
 
+class PackedPolicy:
+    """The ``ActorCritic`` parameters (model.py:17-21) in the bf16 shared-memory image of the policy kernel."""
+
+    def __init__(self, engine, ac_net):
+        self.engine = engine
+        lib = engine.lib
+        self.buf = torch.empty(lib.azb_policy_packed_bytes(), dtype=torch.uint8, device=engine.device)
+        self.update(ac_net)
+
+    def update(self, ac_net):
+        """Re-pack after an optimiser step (weights are read from the module's current parameters)."""
+        e = self.engine
+        t = [ac_net.actor_linear1.weight, ac_net.actor_linear1.bias, ac_net.actor_linear2.weight, ac_net.actor_linear2.bias,
+             ac_net.critic_linear1.weight, ac_net.critic_linear1.bias, ac_net.critic_linear2.weight, ac_net.critic_linear2.bias]
+        assert tuple(t[0].shape) == (180, 136) and tuple(t[2].shape) == (180, 180) and tuple(t[6].shape) == (1, 180)
+        t = [x.detach().to(device=e.device, dtype=torch.float32).contiguous() for x in t]
+        _lib.check(e.lib.azb_policy_pack_weights(e._h, *[_ptr(x) for x in t], _ptr(self.buf), e._stream()))
+        self._keep = t          # keep the staging tensors alive until the pack kernel ran
+
+
+def policy_step(engine, packed, mode=0, apply_step=True, want_logits=False, want_mask=True):
+    """K4 in one launch: observation -> MLP (tcgen05) -> masked softmax -> sample / argmax -> [Azul.step].
+
+    Returns dict(action uint8, logp, value, entropy float32, done, status uint8[, mask int32 [6,G]][, logits [G,180]])."""
+    n, dev = engine.n_games, engine.device
+    out = {
+        "action": torch.empty(n, dtype=torch.uint8, device=dev), "logp": torch.empty(n, dtype=torch.float32, device=dev),
+        "value": torch.empty(n, dtype=torch.float32, device=dev), "entropy": torch.empty(n, dtype=torch.float32, device=dev),
+        "done": torch.empty(n, dtype=torch.uint8, device=dev), "status": torch.empty(n, dtype=torch.uint8, device=dev),
+    }
+    mask = torch.empty((MASK_WORDS, n), dtype=torch.int32, device=dev) if want_mask else None
+    logits = torch.empty((n, N_ACTIONS), dtype=torch.float32, device=dev) if want_logits else None
+    _lib.check(engine.lib.azb_policy_step(
+        engine._h, _ptr(engine.state), _ptr(packed.buf), int(mode), int(bool(apply_step)), _ptr(out["action"]),
+        _ptr(out["logp"]), _ptr(out["value"]), _ptr(out["entropy"]), _ptr(mask), _ptr(out["done"]), _ptr(out["status"]),
+        _ptr(logits), engine._stream()))
+    if want_mask:
+        out["mask"] = mask
+    if want_logits:
+        out["logits"] = logits
+    return out
+
+
 def mask_to_bool(mask6):
     """uint32 ``[6, G]`` mask words -> bool ``[G, 180]`` in the reference's action order."""
     m = mask6.to(torch.int64) & 0xFFFFFFFF

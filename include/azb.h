@@ -133,6 +133,28 @@ int azb_count_score(azb_t* h, uint32_t* state, void* stream);
 int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream);
 int azb_round_flags(azb_t* h, const uint32_t* state, uint8_t* flags, void* stream);
 
+/* ---- K4: the policy/value network of azulnet/model.py:12-41 fused with its callers ------------
+ * ActorCritic(136, 180, hidden 180): actor 136 -> 180 -> ReLU -> 180 logits, critic 136 -> 180 -> ReLU -> 1.
+ * azb_policy_pack_weights converts the eight fp32 parameter tensors (torch layout [out][in], device
+ * pointers) into the bf16 image (azb_policy_packed_bytes() bytes, device) the kernel keeps in shared
+ * memory.  azb_policy_step then does, for every 2-player game of the batch, in ONE launch:
+ *   observation from the seat to move        GameRunner.get_state            game_runner.py:56-72
+ *   both dense layers on tcgen05 tensor cores ActorCritic.forward_actor/critic model.py:23-41
+ *   logits[~mask] = -inf, softmax/log_softmax  model.py:37-40
+ *   action ~ policy (mode 0) or argmax (mode 1) Agent.get_ac_output          agent.py:64-81
+ *   log pi(action), -mean(log pi over legal)   NNRunner.run_episode          nn_runner.py:32-40
+ *   and, when apply_step != 0, Azul.step with that action (Philox refill)   azul.py:296-313.
+ * Outputs (device, each optional / NULL): action uint8 [G] (AZB_ACTION_SKIP when no action is legal),
+ * logp, value, entropy float [G], mask6 uint32 [6][G] (the mask the decision used), done / status uint8 [G]
+ * (AZB_ST_ENDED / AZB_ST_STUCK instead of model.py:33-34 IllegalMask), logits float [G][180] (unmasked). */
+int azb_policy_packed_bytes(void);
+int azb_policy_pack_weights(azb_t* h, const float* w1a, const float* b1a, const float* w2a, const float* b2a,
+                            const float* w1c, const float* b1c, const float* w2c, const float* b2c, void* packed,
+                            void* stream);
+int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int apply_step, uint8_t* action_out,
+                    float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
+                    uint8_t* status_out, float* logits_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
