@@ -5,7 +5,8 @@
 //
 // Shape of the work: 128 games per tile (one game per thread, one tile per pass of a persistent CTA).
 //   layer 1   [128 x 144] x [144 x 368]   obs (136, zero-padded to 144) times [W1_actor ; W1_critic]^T
-//             (180 + 180 hidden units, padded to 192 + 176)                    -> TMEM columns [0,368)
+//             (180 + 180 hidden units back to back, padded to 368; two MMAs of N = 192 + 176)
+//                                                                              -> TMEM columns [0,368)
 //   layer 2   [128 x 192] x [192 x 192]   relu(hidden_actor) times W2_actor^T   -> TMEM columns [0,192)
 //   critic    value = w2c . relu(hidden_critic) + b2c on CUDA cores straight from the TMEM row
 // Both dense layers run on the 5th-generation tensor cores: tcgen05.mma (kind::f16, bf16 inputs, fp32
@@ -25,7 +26,7 @@ namespace pol {
 
 constexpr int TILE_M = 128;                 // games per tile == threads per CTA
 constexpr int K1 = 144, K1_CHUNKS = K1 / 8; // obs 136 -> 144 (multiple of the MMA K = 16)
-constexpr int N1A = 192, N1C = 176;         // hidden units per head, padded to a multiple of 16
+constexpr int N1A = 192, N1C = 176;         // the two layer-1 MMA N blocks (rows 0..191 and 192..367 of W1)
 constexpr int N1 = N1A + N1C, N1_GROUPS = N1 / 8;
 constexpr int K2 = 192, K2_CHUNKS = K2 / 8;
 constexpr int N2 = 192, N2_GROUPS = N2 / 8;
@@ -40,15 +41,15 @@ constexpr int W2_BYTES = K2_CHUNKS * N2_GROUPS * 128;        //  73,728
 constexpr int A_BYTES = K2_CHUNKS * M_GROUPS * 128;          //  49,152 (layer-2 A; layer-1 A aliases its start)
 constexpr int OFF_W1 = 0;
 constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
-constexpr int OFF_VEC = OFF_W2 + W2_BYTES;                    // fp32 vectors: b1a[192] b1c[176] w2c[176] b2a[192] b2c[1] pad[3]
-constexpr int VEC_FLOATS = N1A + N1C + N1C + N2 + 4;
+constexpr int OFF_VEC = OFF_W2 + W2_BYTES;                    // fp32 vectors: b1[368] (actor 0..179, critic 180..359) w2c[192] b2a[192] b2c[1] pad[3]
+constexpr int VEC_FLOATS = N1 + 192 + N2 + 4;
 constexpr int PACKED_BYTES = OFF_VEC + VEC_FLOATS * 4;        // what azb_policy_pack_weights produces
 constexpr int OFF_A = (PACKED_BYTES + 127) / 128 * 128;
 constexpr int OFF_BAR = OFF_A + A_BYTES;                      // 2 mbarriers + tmem base
 constexpr int SMEM_BYTES = OFF_BAR + 32;
 static_assert(SMEM_BYTES <= 232448, "policy kernel exceeds the 227 KB shared memory of an SM");
 
-constexpr int V_B1A = 0, V_B1C = N1A, V_W2C = N1A + N1C, V_B2A = N1A + 2 * N1C, V_B2C = N1A + 2 * N1C + N2;
+constexpr int V_B1 = 0, V_W2C = N1, V_B2A = N1 + 192, V_B2C = N1 + 192 + N2;
 
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -117,20 +118,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
-{
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    tc_wait_ld();
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
@@ -312,8 +299,9 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
                 uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const int j = c0 + 8 * q + 2 * e;
-                    ow[e] = pack_bf16(fmaxf(v[8 * q + 2 * e] + vec[V_B1A + j], 0.0f), fmaxf(v[8 * q + 2 * e + 1] + vec[V_B1A + j + 1], 0.0f));
+                    const int j = c0 + 8 * q + 2 * e;                  // hidden unit (even, so j and j + 1 are both < or >= 180)
+                    ow[e] = j < HID ? pack_bf16(fmaxf(v[8 * q + 2 * e] + vec[V_B1 + j], 0.0f),
+                                                fmaxf(v[8 * q + 2 * e + 1] + vec[V_B1 + j + 1], 0.0f)) : 0u;
                 }
                 *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (tid >> 3)) * 128 + (tid & 7) * 16) = o;
             }
@@ -321,17 +309,12 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
         // ---- critic head on CUDA cores straight from TMEM: value = w2c . relu(h_c + b1c) + b2c ----
         float value = vec[V_B2C];
 #pragma unroll 1
-        for (int c0 = 0; c0 < 160; c0 += 32) {
+        for (int c0 = 0; c0 < 192; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem_row + N1A + c0, v);
+            tmem_ld32(tmem_row + HID + c0, v);                          // critic hidden units c0 .. c0+31 live in columns 180 + unit
 #pragma unroll
-            for (int i = 0; i < 32; i++) value = fmaf(fmaxf(v[i] + vec[V_B1C + c0 + i], 0.0f), vec[V_W2C + c0 + i], value);
-        }
-        {
-            float v[16];
-            tmem_ld16(tmem_row + N1A + 160, v);
-#pragma unroll
-            for (int i = 0; i < 16; i++) value = fmaf(fmaxf(v[i] + vec[V_B1C + 160 + i], 0.0f), vec[V_W2C + 160 + i], value);
+            for (int i = 0; i < 32; i++)
+                if (c0 + i < HID) value = fmaf(fmaxf(v[i] + vec[V_B1 + HID + c0 + i], 0.0f), vec[V_W2C + c0 + i], value);
         }
         fence_async_smem();
         tc_fence_before();
@@ -467,7 +450,7 @@ __global__ void k_pack_weights(const float* __restrict__ w1a, const float* __res
         float v = 0.0f;
         if (k < OBS) {
             if (n < HID) v = w1a[n * OBS + k];
-            else if (n >= N1A && n - N1A < HID) v = w1c[(n - N1A) * OBS + k];
+            else if (n < 2 * HID) v = w1c[(n - HID) * OBS + k];
         }
         __nv_bfloat16 b = __float2bfloat16_rn(v);
         *reinterpret_cast<__nv_bfloat16*>(out + OFF_W1 + ((k >> 3) * N1_GROUPS + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2) = b;
@@ -479,8 +462,7 @@ __global__ void k_pack_weights(const float* __restrict__ w1a, const float* __res
     } else if (i < N1 * K1 + N2 * K2 + VEC_FLOATS) {
         const int j = i - N1 * K1 - N2 * K2;
         float v = 0.0f;
-        if (j < V_B1C) { if (j < HID) v = b1a[j]; }
-        else if (j < V_W2C) { if (j - V_B1C < HID) v = b1c[j - V_B1C]; }
+        if (j < V_W2C) { if (j < HID) v = b1a[j]; else if (j < 2 * HID) v = b1c[j - HID]; }
         else if (j < V_B2A) { if (j - V_W2C < HID) v = w2c[j - V_W2C]; }
         else if (j < V_B2C) { if (j - V_B2A < ACT) v = b2a[j - V_B2A]; }
         else if (j == V_B2C) v = b2c[0];
