@@ -365,8 +365,10 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
         }
         const float lse = mx + __logf(se);              // log sum exp over the legal actions
         uint32_t action = (uint32_t)amax;
-        if (A.mode == 0 && n_valid > 0) {
-            // pass 2: inverse-CDF sampling with one Philox word (agent.py:69 np.random.choice(p = policy))
+        float la = mx;                                  // logit of the chosen action (argmax mode: the max)
+        if (A.mode == 0) {
+            // pass 2: inverse-CDF sampling with one Philox word (agent.py:69 np.random.choice(p = policy)).
+            // tcgen05.ld is warp-collective: every lane runs the loop, lanes without a legal action only idle.
             uint32_t w[4];
             rng(A.gid0 + (uint32_t)gl, gm.steps >> 2, PURPOSE_POLICY, 0u, w);
             const uint32_t idx = gm.steps & 3u;
@@ -374,7 +376,6 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
             const float target = (float)(word >> 8) * (1.0f / 16777216.0f) * se;
             float cum = 0.0f;
             bool found = false;
-            int last = amax;
 #pragma unroll 1
             for (int c0 = 0; c0 < 192; c0 += 32) {
                 float v[32];
@@ -383,28 +384,16 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
                     if (((bits >> i) & 1u) && !found) {
-                        cum += __expf(v[i] + vec[V_B2A + c0 + i] - mx);
-                        last = c0 + i;
-                        if (cum > target) { found = true; }
+                        const float l = v[i] + vec[V_B2A + c0 + i];
+                        cum += __expf(l - mx);
+                        action = (uint32_t)(c0 + i);     // falls back to the last legal action if rounding leaves cum <= target
+                        la = l;
+                        if (cum > target) found = true;
                     }
                 }
             }
-            action = (uint32_t)last;
         }
-        // log pi(action) needs that one logit again: one more 32-column read of the right block
-        float logp = 0.0f;
-        if (n_valid > 0) {
-            float la = 0.0f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 192; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_row + c0, v);
-#pragma unroll
-                for (int i = 0; i < 32; i++)
-                    if ((uint32_t)(c0 + i) == action) la = v[i] + vec[V_B2A + c0 + i];
-            }
-            logp = la - lse;
-        }
+        const float logp = n_valid > 0 ? la - lse : 0.0f;
         const float entropy = n_valid > 0 ? -(sl / (float)n_valid - lse) : 0.0f;
 
         uint32_t status = n_valid > 0 ? 0u : (gm.ended() ? (uint32_t)ST_ENDED : (uint32_t)ST_STUCK);
