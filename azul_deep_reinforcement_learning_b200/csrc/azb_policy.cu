@@ -209,7 +209,9 @@ struct PolicyArgs {
     const unsigned char* __restrict__ packed;
     uint32_t k0, k1, gid0;
     int mode;            // 0 sample from the masked policy, 1 argmax (agent.py action_selection)
-    int apply_step;      // also execute Azul.step with the chosen action (Philox refill)
+    int apply_step;      // 1: also execute Azul.step with the chosen action (Philox refill); 2: and start a fresh game when it ends
+    int first_rule;
+    unsigned long long* __restrict__ counters;   // rollout counters (apply_step == 2), may be null
     float* __restrict__ logits_out;          // [n][180] raw logits (debug / parity), may be null
     float* __restrict__ value_out;           // [n]
     uint8_t* __restrict__ action_out;        // [n]
@@ -222,6 +224,14 @@ struct PolicyArgs {
 
 constexpr uint32_t PURPOSE_POLICY = 4;
 
+struct SmemSink {
+    unsigned long long* c;
+    __device__ __forceinline__ void add(int i, uint32_t v)
+    {
+        if (v) atomicAdd(&c[i], (unsigned long long)v);
+    }
+};
+
 template <int POOL>
 __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
 {
@@ -231,6 +241,9 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
     const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
     const uint32_t bar1 = smem_u32(smem + OFF_BAR), bar2 = bar1 + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+    __shared__ unsigned long long cnt[AZB_N_COUNTERS];
+    if (tid < AZB_N_COUNTERS) cnt[tid] = 0ull;
+    SmemSink sink{cnt};
 
     // one-time: weights image -> shared memory, barriers, tensor memory
     {
@@ -407,13 +420,29 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
             if (A.logp_out) A.logp_out[g] = logp;
             if (A.entropy_out) A.entropy_out[g] = entropy;
         }
+        bool finished = false;
         if (A.apply_step && n_valid > 0 && !gm.ended()) {
             const uint32_t gid = A.gid0 + (uint32_t)gl;
-            advance<2, POOL>(gm, action, [&](Game<2>& gg) { new_round_philox<2, POOL>(gg, rng, gid, PURPOSE_REFILL); });
-            if (valid) gm.store(A.state, A.n, g);
+            const uint32_t turn_before = gm.turn_counter();
+            finished = advance<2, POOL>(gm, action, [&](Game<2>& gg) { new_round_philox<2, POOL>(gg, rng, gid, PURPOSE_REFILL); });
+            if (valid && A.apply_step == 2) {
+                sink.add(0, 1);
+                if (gm.turn_counter() != turn_before) sink.add(2, 1);
+            }
         }
+        const bool done_now = gm.ended();
+        if (A.apply_step == 2 && (done_now || (n_valid == 0 && !gm.ended()))) {
+            // game over (or stuck): count it and start a fresh game in the slot (GameRunner.reset, game_runner.py:76-80)
+            if (valid) {
+                if (finished) tally_finished(gm, sink);
+                else if (!done_now) sink.add(6, 1);
+                sink.add(2, 1);
+            }
+            reset_game<2, POOL>(gm, rng, A.gid0 + (uint32_t)gl, A.first_rule);
+        }
+        if (valid && A.apply_step) gm.store(A.state, A.n, g);
         if (valid) {
-            if (A.done_out) A.done_out[g] = gm.ended() ? 1 : 0;
+            if (A.done_out) A.done_out[g] = done_now ? 1 : 0;
             if (A.status_out) A.status_out[g] = (uint8_t)(status | gm.status());
         }
         // every thread's TMEM reads are complete before the next tile's layer 1 overwrites the accumulators
@@ -422,6 +451,7 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
     }
 
     __syncthreads();
+    if (A.counters && tid < AZB_N_COUNTERS && cnt[tid]) atomicAdd(&A.counters[tid], cnt[tid]);
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -480,7 +510,7 @@ int azb_policy_pack_weights(azb_t* h, const float* w1a, const float* b1a, const 
 
 int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int apply_step, uint8_t* action_out,
                     float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
-                    uint8_t* status_out, float* logits_out, void* stream)
+                    uint8_t* status_out, float* logits_out, unsigned long long* counters, void* stream)
 {
     CHECK_HANDLE(h);
     if (!state || !packed) return azb_fail(AZB_E_INVALID, "null buffer%s");
@@ -489,7 +519,8 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
     pol::PolicyArgs A;
     A.state_in = state; A.state = state; A.n = h->n_games; A.packed = (const unsigned char*)packed;
     A.k0 = (uint32_t)h->seed; A.k1 = (uint32_t)(h->seed >> 32); A.gid0 = (uint32_t)h->game_id_base;
-    A.mode = mode; A.apply_step = apply_step;
+    if (apply_step < 0 || apply_step > 2) return azb_fail(AZB_E_INVALID, "apply_step must be 0, 1 or 2%s");
+    A.mode = mode; A.apply_step = apply_step; A.first_rule = h->first_player; A.counters = counters;
     A.logits_out = logits_out; A.value_out = value_out; A.action_out = action_out; A.logp_out = logp_out;
     A.entropy_out = entropy_out; A.done_out = done_out; A.status_out = status_out; A.mask6_out = mask6_out;
     const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;

@@ -43,7 +43,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=65536, help="games per GPU (BASELINE configs[1])")
+    ap.add_argument("--mode", default="random", choices=["random", "policy"],
+                    help="random: fused random-agent rollout (configs[1], the headline); policy: self-play with the "
+                         "fused ActorCritic policy kernel, one env step per launch (configs[3])")
+    ap.add_argument("--games", type=int, default=0, help="games per GPU (default 65536 random / 131072 policy)")
     ap.add_argument("--players", type=int, default=2)
     ap.add_argument("--pool", default="lid", choices=["lid", "random"],
                     help="tile pool; 'lid' + random first player = GameRunner's default rules (game_runner.py:23)")
@@ -347,8 +350,116 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_policy(args):
+    """BASELINE.json configs[3]: self-play, every seat sampled from a random-init ActorCritic (model.py:17-21
+    under torch.manual_seed(0)); one bench step = ONE launch of the fused policy kernel = one env step per game."""
+    import torch
+    from azul_deep_reinforcement_learning_b200 import parallel
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul, PackedPolicy, policy_step
+
+    rank, world, local = parallel.world()
+    if world > 1:
+        parallel.init("nccl", local)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pool = 1 if args.pool == "lid" else 0
+    G = args.games
+    torch.manual_seed(0)
+    net = ActorCritic(136, 180)
+    eng = BatchedAzul(G, 2, pool, 0, seed=args.seed, device=local, game_id_base=parallel.shard(rank, G))
+    packed = PackedPolicy(eng, net)
+    lib, h = eng.lib, eng._h
+    import ctypes
+    out = policy_step(eng, packed, mode=0, apply_step=True, auto_reset=True)      # allocates the output tensors once
+
+    def launch():
+        rc = lib.azb_policy_step(h, ctypes.c_void_p(eng.state.data_ptr()), ctypes.c_void_p(packed.buf.data_ptr()), 0, 2,
+                                 ctypes.c_void_p(out["action"].data_ptr()), ctypes.c_void_p(out["logp"].data_ptr()),
+                                 ctypes.c_void_p(out["value"].data_ptr()), ctypes.c_void_p(out["entropy"].data_ptr()),
+                                 ctypes.c_void_p(out["mask"].data_ptr()), ctypes.c_void_p(out["done"].data_ptr()),
+                                 ctypes.c_void_p(out["status"].data_ptr()), None, ctypes.c_void_p(eng.counters.data_ptr()),
+                                 ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        assert rc == 0
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3) + 40):            # warm-up also spreads the games over all phases of a game
+        launch()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        launch()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = parallel.max_over_ranks(ev0.elapsed_time(ev1), dev)
+
+    host_state = torch.empty(eng.state.shape, dtype=torch.int32).pin_memory()
+    host_state.copy_(eng.state)
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if k != "mask"}
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.state.copy_(host_state, non_blocking=True)
+        launch()
+        host_state.copy_(eng.state, non_blocking=True)
+        for k in host_out:
+            host_out[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    cnt = parallel.reduce_counters(eng.counters.clone()).cpu().tolist()
+    if rank == 0:
+        value = world * G * args.steps / (dev_ms * 1e-3)
+        flop = 2 * (136 * 360 + 180 * 180 + 180)                                  # SURVEY §8d: 163,080 per decision
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        achieved = flop * G * args.steps / (dev_ms * 1e-3) / 1e12 / world * world / world
+        cfg = workload_config(args, world)
+        cfg["workload"] = ("%d parallel 2-player self-play games per GPU, every seat sampled from a random-init "
+                           "ActorCritic(136,180) by the fused policy kernel (BASELINE.json configs[3])" % G)
+        cfg["env_steps_per_game_per_launch"] = 1
+        cfg["l2"] = "working set (%.1f MB state + outputs per launch) re-read from L2/HBM every launch; no flush" % (
+            eng.state.numel() * 4 / 1e6)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3) + 40, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (MLP) / u32 (rules)", "data": "synthetic", "config": cfg,
+            "e2e": {"value": world * G * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": host_state.numel() * 4,
+                    "d2h_bytes_per_step": host_state.numel() * 4 + sum(v.numel() * v.element_size() for v in host_out.values()),
+                    "steps": e2e_steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback",
+                         "algorithmic_flop_per_decision": flop, "decisions_per_launch": G, "kernel": "pol::k_policy<%d>" % pool},
+            "clocks": clocks,
+            "decisions_per_sec": value, "games_per_sec": (cnt[1] / max(cnt[0], 1)) * value,
+            "rollout_counters": {"steps": cnt[0], "games": cnt[1], "rounds": cnt[2], "stuck": cnt[6]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if not args.games:
+        args.games = 131072 if args.mode == "policy" else 65536
+    if args.mode == "policy" and args.impl != "reference":
+        return run_policy(args)
     if args.impl == "reference":
         run_reference(args)
     else:

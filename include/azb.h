@@ -143,7 +143,9 @@ int azb_round_flags(azb_t* h, const uint32_t* state, uint8_t* flags, void* strea
  *   logits[~mask] = -inf, softmax/log_softmax  model.py:37-40
  *   action ~ policy (mode 0) or argmax (mode 1) Agent.get_ac_output          agent.py:64-81
  *   log pi(action), -mean(log pi over legal)   NNRunner.run_episode          nn_runner.py:32-40
- *   and, when apply_step != 0, Azul.step with that action (Philox refill)   azul.py:296-313.
+ *   and, when apply_step != 0, Azul.step with that action (Philox refill)   azul.py:296-313;
+ *   apply_step == 2 additionally starts a fresh game in slots whose game ended (self-play rollouts) and
+ *   accumulates the rollout counters (device uint64[AZB_N_COUNTERS], optional).
  * Outputs (device, each optional / NULL): action uint8 [G] (AZB_ACTION_SKIP when no action is legal),
  * logp, value, entropy float [G], mask6 uint32 [6][G] (the mask the decision used), done / status uint8 [G]
  * (AZB_ST_ENDED / AZB_ST_STUCK instead of model.py:33-34 IllegalMask), logits float [G][180] (unmasked). */
@@ -153,7 +155,7 @@ int azb_policy_pack_weights(azb_t* h, const float* w1a, const float* b1a, const 
                             void* stream);
 int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int apply_step, uint8_t* action_out,
                     float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
-                    uint8_t* status_out, float* logits_out, void* stream);
+                    uint8_t* status_out, float* logits_out, unsigned long long* counters, void* stream);
 
 #ifdef __cplusplus
 }

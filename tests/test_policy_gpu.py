@@ -143,3 +143,23 @@ def test_policy_selfplay_runs_to_game_end_and_ragged_batch():
         assert bool(((out["status"][ended] & 2) != 0).all())      # ended games: flagged GameEnded ...
         assert torch.equal(before[:, ended], eng.state[:, ended])  # ... and left untouched
         assert bool((out["action"][ended] == 255).all())
+
+
+def test_policy_selfplay_auto_reset_counters():
+    """apply_step = 2: finished games are tallied and replaced; counters stay consistent with the states."""
+    from azul_deep_reinforcement_learning_b200.engine import policy_step
+    with torch.no_grad():
+        net, eng, packed = _setup(n=2048, k=0)
+        steps = 260
+        n_done = 0
+        for _ in range(steps):
+            out = policy_step(eng, packed, mode=0, apply_step=True, auto_reset=True, want_mask=False)
+            n_done += int(out["done"].sum())
+            assert int(out["status"].max()) == 0
+        c = eng.read_counters()
+        assert c["steps"] == 2048 * steps and c["games"] == n_done > 0 and c["stuck"] == 0
+        rec = eng.export_records().cpu().numpy()
+        from azul_deep_reinforcement_learning_b200.layout import UnpackedLayout
+        L = UnpackedLayout(2)
+        assert (rec[:, L.end_of_game] == 0).all() and (rec[:, 0:30].sum(axis=1) > 0).all()
+        assert c["rounds"] == 2048 + c["games"] + (c["turns"] - c["games"]) + int(rec[:, L.turn_counter].sum()) - 2048
