@@ -162,4 +162,5 @@ def test_policy_selfplay_auto_reset_counters():
         from azul_deep_reinforcement_learning_b200.layout import UnpackedLayout
         L = UnpackedLayout(2)
         assert (rec[:, L.end_of_game] == 0).all() and (rec[:, 0:30].sum(axis=1) > 0).all()
-        assert c["rounds"] == 2048 + c["games"] + (c["turns"] - c["games"]) + int(rec[:, L.turn_counter].sum()) - 2048
+        # every new_round after the initial azb_reset is counted once: finished games' rounds + running games' rounds
+        assert c["rounds"] == c["turns"] + int(rec[:, L.turn_counter].sum()) - 2048
