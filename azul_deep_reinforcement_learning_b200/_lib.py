@@ -12,7 +12,7 @@ SYMBOLS = [
     "azb_create", "azb_destroy", "azb_set_block_threads", "azb_set_rollout_defer", "azb_reset", "azb_legal_mask", "azb_step",
     "azb_rollout_random", "azb_score_preview", "azb_import_state", "azb_export_state", "azb_observe",
     "azb_stats", "azb_move", "azb_next_player", "azb_count_score", "azb_new_round", "azb_round_flags",
-    "azb_policy_packed_bytes", "azb_policy_pack_weights", "azb_policy_step",
+    "azb_opponent_random", "azb_policy_packed_bytes", "azb_policy_pack_weights", "azb_policy_step",
 ]
 
 
@@ -53,6 +53,7 @@ def load():
     L.azb_count_score.argtypes = [vp, vp, vp]
     L.azb_new_round.argtypes = [vp, vp, vp, vp]
     L.azb_round_flags.argtypes = [vp, vp, vp, vp]
+    L.azb_opponent_random.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.azb_policy_pack_weights.argtypes = [vp] * 11
     L.azb_policy_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     if L.azb_abi_version() != ABI_VERSION:

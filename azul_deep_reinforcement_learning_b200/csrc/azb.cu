@@ -287,6 +287,29 @@ __global__ void k_op(Launch L, const uint8_t* __restrict__ action, const int8_t*
     gm.store(L.state, L.n, g);
 }
 
+// a14: GameRunner.step after the agent's own move: opponent loop, reward, done, next mask
+template <int P, int POOL>
+__global__ void k_opponent_random(Launch L, int require_two, int16_t* __restrict__ player_score,
+                                  int16_t* __restrict__ reward_out, uint8_t* __restrict__ done_out,
+                                  uint8_t* __restrict__ status_out, uint32_t* __restrict__ mask6_out)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= L.n) return;
+    Game<P> gm;
+    gm.load(L.state, L.n, g);
+    const Philox rng{L.k0, L.k1};
+    uint32_t m[6];
+    const int32_t diff = opponent_random<P, POOL>(gm, rng, L.gid0 + (uint32_t)g, require_two != 0, m);
+    gm.store(L.state, L.n, g);
+    if (player_score) {
+        if (reward_out) reward_out[g] = (int16_t)(diff - (int32_t)player_score[g]);    // game_runner.py:51
+        player_score[g] = (int16_t)diff;                                                // game_runner.py:52
+    }
+    if (done_out) done_out[g] = gm.ended() ? 1 : 0;
+    if (status_out) status_out[g] = (uint8_t)gm.status();
+    if (mask6_out) store_mask(mask6_out, L.n, g, m);
+}
+
 template <int P>
 __global__ void k_round_flags(const uint32_t* __restrict__ s, int64_t n, uint8_t* __restrict__ flags)
 {
@@ -494,6 +517,18 @@ int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream
     if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     const Launch L = make_launch(h, state);
     DISPATCH_PP(h, (k_op<P, POOL, 3><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(L, nullptr, draws20)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_opponent_random(azb_t* h, uint32_t* state, int require_two, int16_t* player_score, int16_t* reward_out,
+                        uint8_t* done_out, uint8_t* status_out, uint32_t* mask6_out, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
+    const Launch L = make_launch(h, state);
+    DISPATCH_PP(h, (k_opponent_random<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
+                       L, require_two, player_score, reward_out, done_out, status_out, mask6_out)));
     CHECK_LAUNCH();
     return 0;
 }

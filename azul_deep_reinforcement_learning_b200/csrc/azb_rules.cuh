@@ -746,4 +746,30 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
     if (valid) { sink.add(0, (uint32_t)k_steps); sink.add(2, rounds); }
 }
 
+// ---- GameRunner.step's opponent loop + reward (game_runner.py:46-52), random-agent opponent ----
+// Plays random-agent moves (Philox ACTION words, like the rollout) until it is seat 1's turn with at
+// least two legal actions (require_two: the reference also lets the opponent agent play seat 1's
+// forced moves, game_runner.py:46; GameRunner.reset does not, :84-85) or the game is over.  Returns
+// the score difference seat 1 - seat 2 after a count_score on a copy (game_runner.py:48-50).
+template <int P, int POOL>
+AZB_HD int32_t opponent_random(Game<P>& g, const Philox& rng, uint32_t gid, bool require_two, uint32_t m[6])
+{
+    AZB_ROLLED
+    for (;;) {
+        legal_mask(g, m);
+        if (g.ended()) break;
+        const int n_valid = popc(m[0]) + popc(m[1]) + popc(m[2]) + popc(m[3]) + popc(m[4]) + popc(m[5]);
+        if (g.current_player() == 1u && (!require_two || n_valid >= 2)) break;
+        if (n_valid == 0) { g.add_status(ST_STUCK); break; }
+        uint32_t w[4];
+        rng(gid, g.steps >> 2, PURPOSE_ACTION, 0u, w);
+        const uint32_t idx = g.steps & 3u;
+        const uint32_t word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
+        advance<P, POOL>(g, random_action(m, word), [&](Game<P>& gg) { new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL); });
+    }
+    Game<P> cp = g;
+    count_score<P, POOL>(cp);
+    return (int32_t)(cp.scf[0] & 0xFFFFu) - (int32_t)(cp.scf[1] & 0xFFFFu);
+}
+
 }  // namespace azb

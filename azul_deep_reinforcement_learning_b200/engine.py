@@ -209,6 +209,19 @@ class BatchedAzul:
             assert draws.numel() == 20 * self.n_games
         _lib.check(self.lib.azb_new_round(self._h, _ptr(self.state), _ptr(draws), self._stream()))
 
+    def opponent_random(self, player_score, require_two=True, want_mask=True):
+        """``GameRunner.step``'s opponent loop + reward for every game (K a14).  ``player_score`` (int16 [G]) is
+        updated in place; returns dict(reward int16, done, status uint8[, mask])."""
+        n = self.n_games
+        reward, done, status = self._new((n,), torch.int16), self._new((n,), torch.uint8), self._new((n,), torch.uint8)
+        mask = self._new((MASK_WORDS, n), torch.int32) if want_mask else None
+        _lib.check(self.lib.azb_opponent_random(self._h, _ptr(self.state), int(bool(require_two)), _ptr(player_score),
+                                               _ptr(reward), _ptr(done), _ptr(status), _ptr(mask), self._stream()))
+        out = {"reward": reward, "done": done, "status": status}
+        if want_mask:
+            out["mask"] = mask
+        return out
+
     def round_flags(self):
         out = self._new((self.n_games,), torch.uint8)
         _lib.check(self.lib.azb_round_flags(self._h, _ptr(self.state), _ptr(out), self._stream()))

@@ -1,0 +1,104 @@
+"""Batched counterparts of ``GameRunner`` / ``NNRunner`` (reference game_runner.py:9-85, nn_runner.py:13-84).
+
+``BatchedGameRunner`` is G copies of the reference's 2-player env wrapper advancing in lock-step on one
+GPU: seat 1 is the learning agent, seat 2 a random agent (``RandomAgent``, game_runner.py:87-97, drawing
+from the Philox schedule).  One agent decision costs three launches: observation (``azb_observe``, only
+when the caller records it), the fused policy kernel (``azb_policy_step``: MLP on tcgen05 + masked
+softmax + sampling + the agent's ``Azul.step``) and the opponent loop + reward (``azb_opponent_random``).
+"""
+import torch
+
+from .engine import BatchedAzul, PackedPolicy, mask_to_bool, policy_step, rules_to_ints
+
+DEFAULT_RULES = {"first_player": "Random", "tile_pool": "Lid"}      # game_runner.py:23
+
+
+class BatchedGameRunner:
+    def __init__(self, n_games, rules=None, seed=0, device=0, game_id_base=0):
+        rules = DEFAULT_RULES if rules is None else rules
+        pool, first = rules_to_ints(2, rules)
+        self.engine = BatchedAzul(n_games, 2, pool, first, seed=seed, device=device, game_id_base=game_id_base, reset=False)
+        self.n_games, self.device = n_games, self.engine.device
+        self.player_score = torch.zeros(n_games, dtype=torch.int16, device=self.device)
+        self.mask = None
+        self.reset()
+
+    def reset(self):
+        """``GameRunner.reset`` (game_runner.py:76-85): fresh games, the opponent plays until seat 1 is to move."""
+        self.engine.reset()
+        self.player_score.zero_()
+        out = self.engine.opponent_random(self.player_score, require_two=False)
+        self.player_score.zero_()                     # game_runner.py:81: the score baseline restarts at 0
+        self.mask = out["mask"]
+        return out
+
+    def get_state(self):
+        """``GameRunner.get_state()`` for every game: float32 [G, 136] from seat 1's perspective."""
+        return self.engine.observe(0)
+
+    def get_valid_moves(self):
+        return mask_to_bool(self.mask)
+
+    def _after_agent_move(self):
+        out = self.engine.opponent_random(self.player_score, require_two=True)
+        self.mask = out["mask"]
+        return out
+
+    def step(self, actions):
+        """``GameRunner.step`` (game_runner.py:43-55) with one action per game (uint8, 255 = skip that game).
+        Returns dict(reward int16, done uint8, status uint8 [step status | opponent status], mask)."""
+        st = self.engine.step(actions, None, want_mask=False)
+        out = self._after_agent_move()
+        out["status"] = out["status"] | st["status"]
+        return out
+
+    def step_policy(self, packed, mode=0):
+        """Agent decision by the fused policy kernel + its env step, then the opponent loop and the reward."""
+        pol = policy_step(self.engine, packed, mode=mode, apply_step=True, want_mask=False)
+        out = self._after_agent_move()
+        out.update(action=pol["action"], logp=pol["logp"], value=pol["value"], entropy=pol["entropy"],
+                   policy_status=pol["status"])
+        return out
+
+
+def run_episodes(runner, packed, max_decisions=160, check_every=8, record_obs=True):
+    """``NNRunner.run_episode`` for every game of ``runner`` at once (nn_runner.py:17-47).
+
+    Returns a dict of [T, G] tensors: reward (float32), value, logp, entropy (from the kernel), action
+    (int64), active (bool: the game was still running when the decision was taken), mask (int32
+    [T, 6, G] legal-mask words) and, when ``record_obs``, obs (bfloat16 [T, G, 136]) for the autograd
+    recomputation."""
+    G, dev = runner.n_games, runner.device
+    runner.reset()
+    alive = torch.ones(G, dtype=torch.bool, device=dev)
+    rec = {k: [] for k in ("reward", "value", "logp", "entropy", "action", "active", "mask", "obs")}
+    for t in range(max_decisions):
+        if record_obs:
+            rec["obs"].append(runner.get_state().to(torch.bfloat16))
+        rec["mask"].append(runner.mask.clone())
+        out = runner.step_policy(packed)
+        acted = alive & ((out["policy_status"] & 6) == 0)         # a decision was actually taken for this game
+        rec["active"].append(acted)
+        rec["reward"].append(out["reward"].to(torch.float32))
+        rec["value"].append(out["value"])
+        rec["logp"].append(out["logp"])
+        rec["entropy"].append(out["entropy"])
+        rec["action"].append(out["action"].to(torch.int64))
+        alive = acted & ~out["done"].bool()
+        if (t + 1) % check_every == 0 and not bool(alive.any()):
+            break
+    out = {k: torch.stack(v) for k, v in rec.items() if v}
+    out["unfinished"] = int(alive.sum())
+    return out
+
+
+def discounted_returns(reward, active, gamma):
+    """q_t = r_t + gamma * q_{t+1} per episode (nn_runner.py:72-75), [T, G]; inactive slots contribute 0."""
+    T = reward.shape[0]
+    q = torch.zeros_like(reward)
+    run = torch.zeros_like(reward[0])
+    r = reward * active
+    for t in range(T - 1, -1, -1):
+        run = r[t] + gamma * run
+        q[t] = run
+    return q

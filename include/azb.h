@@ -133,6 +133,14 @@ int azb_count_score(azb_t* h, uint32_t* state, void* stream);
 int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream);
 int azb_round_flags(azb_t* h, const uint32_t* state, uint8_t* flags, void* stream);
 
+/* GameRunner.step after the agent's own move (game_runner.py:46-55), random-agent opponent
+ * (RandomAgent, :87-97, Philox words): opponent moves until it is seat 1's turn with >= 2 legal actions
+ * (require_two != 0, :46) or just seat 1's turn (require_two == 0, GameRunner.reset :84-85) or the game
+ * is over; then reward = (score1 - score2 after count_score on a copy) - player_score, player_score updated
+ * in place (int16 [G], :48-52), done = is_end_of_game, mask6 = legal mask of the resulting state. */
+int azb_opponent_random(azb_t* h, uint32_t* state, int require_two, int16_t* player_score, int16_t* reward_out,
+                        uint8_t* done_out, uint8_t* status_out, uint32_t* mask6_out, void* stream);
+
 /* ---- K4: the policy/value network of azulnet/model.py:12-41 fused with its callers ------------
  * ActorCritic(136, 180, hidden 180): actor 136 -> 180 -> ReLU -> 180 logits, critic 136 -> 180 -> ReLU -> 1.
  * azb_policy_pack_weights converts the eight fp32 parameter tensors (torch layout [out][in], device

@@ -523,6 +523,29 @@ int ao_step(int32_t *rec, int players, int pool, int action, const int8_t *draws
     return rc;
 }
 
+/* SPEC of azb_opponent_random = GameRunner.step after the agent's move (game_runner.py:46-52) with a
+ * random-agent opponent on the Philox ACTION words; returns score[0]-score[1] after count_score on a copy. */
+int ao_opponent_random(int32_t *rec, int players, int pool, uint64_t seed, uint32_t gid, int require_two, uint32_t *mask6)
+{
+    ao_game g; from_record(&g, rec, players);
+    for (;;) {
+        legal_mask(&g, mask6);
+        if (g.end_of_game) break;                                        /* game_runner.py:46 "and not is_end_of_game()" */
+        int n_valid = 0;
+        for (int p = 0; p < 6; p++) n_valid += __builtin_popcount(mask6[p]);
+        if (g.current_player == 1 && (!require_two || n_valid >= 2)) break;
+        if (n_valid == 0) { g.status |= ST_STUCK; break; }
+        uint32_t w[4];
+        draw_words(seed, gid, g.total_steps >> 2, PURPOSE_ACTION, 0, w);
+        int a = random_action(mask6, w[g.total_steps & 3]);
+        step(&g, pool, a % 6, (a / 6) % 5, a / 30, NULL, seed, gid);     /* opponent_move, game_runner.py:37-42 */
+    }
+    to_record(&g, rec, players);
+    ao_game cp = g;                                                      /* game_runner.py:48 deepcopy */
+    count_score(&cp, pool);                                              /* :49 */
+    return cp.score[0] - cp.score[1];                                    /* :50 */
+}
+
 int ao_random_action(const uint32_t *mask6, uint32_t word) { return random_action(mask6, word); }
 
 /* SPEC of azb_rollout_random: K env steps per slot, random agents on every seat, auto-reset.

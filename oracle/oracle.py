@@ -46,6 +46,7 @@ def lib():
         L.ao_legal_mask.argtypes = [i32p, I, u32p]
         L.ao_step.argtypes = [i32p, I, I, I, i8p, U64, U32]
         L.ao_random_action.argtypes = [u32p, U32]
+        L.ao_opponent_random.argtypes = [i32p, I, I, U64, U32, I, u32p]
         L.ao_philox4x32_10.argtypes = [u32p, u32p, u32p]
         L.ao_rollout_random.argtypes = [i32p, ctypes.c_int64, I, I, I, U64, U32, I, i64p]
         L.ao_rollout_random_mt.argtypes = [i32p, ctypes.c_int64, I, I, I, U64, U32, I, i64p, I]
@@ -163,3 +164,10 @@ def rollout_random(recs, players, tile_pool, first_rule, seed, gid0, k_steps, th
         lib().ao_rollout_random_mt(_rec(recs), recs.shape[0], players, tile_pool, first_rule, seed, gid0,
                                    k_steps, _p(cnt, ctypes.c_int64), threads)
     return cnt
+
+
+def opponent_random(rec, players, tile_pool, seed, gid, require_two=True):
+    """In place on one record; returns (score diff seat1 - seat2 after a count_score on a copy, next mask)."""
+    m = np.zeros(6, dtype=np.uint32)
+    d = lib().ao_opponent_random(_rec(rec), players, tile_pool, seed, gid, int(require_two), _p(m, ctypes.c_uint32))
+    return int(d), m

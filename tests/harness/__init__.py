@@ -28,6 +28,8 @@ def lib():
                             ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.hh_rollout.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+        L.hh_opponent.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p]
         L.hh_random_action.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
         _lib = L
     return _lib
@@ -57,3 +59,11 @@ def rollout(recs, players, pool, first_rule, seed, gid0, k):
 def random_action(mask6, word):
     m = np.ascontiguousarray(mask6, dtype=np.uint32)
     return lib().hh_random_action(m.ctypes.data, int(word) & 0xFFFFFFFF)
+
+
+def opponent(rec, players, pool, seed, gid, require_two=True):
+    mask = np.zeros(6, np.uint32)
+    diff = np.zeros(1, np.int32)
+    rc = lib().hh_opponent(rec.ctypes.data, players, pool, seed, gid, int(require_two), mask.ctypes.data, diff.ctypes.data)
+    assert rc == 0
+    return int(diff[0]), mask

@@ -84,4 +84,23 @@ extern "C" int hh_rollout(int32_t* recs, int64_t n, int players, int pool, int f
     return -101;
 }
 
+template <int P, int POOL>
+static int run_opponent(int32_t* rec, uint64_t seed, uint32_t gid, int require_two, uint32_t* mask6, int32_t* diff)
+{
+    Game<P> g;
+    if (!import_record<P>(g, [&](int i) { return rec[i]; })) return -16;
+    Philox rng{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    *diff = opponent_random<P, POOL>(g, rng, gid, require_two != 0, mask6);
+    export_record<P>(g, [&](int i, int32_t v) { rec[i] = v; });
+    return 0;
+}
+
+extern "C" int hh_opponent(int32_t* rec, int players, int pool, uint64_t seed, uint32_t gid, int require_two,
+                           uint32_t* mask6, int32_t* diff)
+{
+#define CALL_OPP(P, POOL) if (players == P && pool == POOL) return run_opponent<P, POOL>(rec, seed, gid, require_two, mask6, diff);
+    CALL_OPP(2, 0) CALL_OPP(2, 1) CALL_OPP(3, 0) CALL_OPP(3, 1) CALL_OPP(4, 0) CALL_OPP(4, 1)
+    return -101;
+}
+
 extern "C" int hh_random_action(const uint32_t* mask6, uint32_t word) { return (int)random_action(mask6, word); }

@@ -132,3 +132,26 @@ def test_import_rejects_unrepresentable():
     rec[L.pattern_lines + 5 * 2 + 0] = 1
     rec[L.pattern_lines + 5 * 2 + 3] = 1          # two colours in one pattern row
     assert H.op(rec, 2, 0, H.OP_ROUNDTRIP)[0] == -16
+
+
+@pytest.mark.parametrize("pool", [0, 1])
+def test_packed_opponent_loop_matches_oracle(pool):
+    """GameRunner.step's opponent loop + reward preview (game_runner.py:46-52): packed rules vs oracle."""
+    seed, n = 99 + pool, 64
+    recs = O.fresh_records(n, 2, pool, 0, seed, 0)
+    rng = np.random.default_rng(3)
+    for it in range(70):
+        for i in range(n):
+            a, b = recs[i].copy(), recs[i].copy()
+            da, ma = O.opponent_random(a, 2, pool, seed, i, require_two=(it > 0))
+            db, mb = H.opponent(b, 2, pool, seed, i, require_two=(it > 0))
+            assert da == db and np.array_equal(ma, mb) and np.array_equal(a, b)
+            L = UnpackedLayout(2)
+            if not a[L.end_of_game] and ma.any():
+                assert a[L.current_player] == 1
+                g = O.Game(2, pool, record=a)
+                act = O.random_action(ma, int(rng.integers(0, 2 ** 32)))
+                assert g.step(act, None, seed, i) == 0          # the agent's own move, then the opponent again
+                recs[i] = g.rec
+            else:
+                recs[i] = O.fresh_records(1, 2, pool, 0, seed + it + 1, i)[0]

@@ -1,0 +1,83 @@
+"""Batched GameRunner semantics and the self-play training loop on the GPU."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from azul_deep_reinforcement_learning_b200.layout import UnpackedLayout  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batched_game_runner_matches_oracle_runner():
+    """GameRunner.reset / step (game_runner.py:43-55,76-85) for 512 games against the C oracle's statement of
+    the same loop: agent actions are fed in, opponent moves come from the shared Philox schedule."""
+    from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner
+    n, seed = 512, 77
+    gr = BatchedGameRunner(n, seed=seed)
+    recs = O.fresh_records(n, 2, 1, 0, seed, 0)
+    pscore = np.zeros(n, np.int64)
+    masks = np.zeros((n, 6), np.uint32)
+    for i in range(n):
+        _, masks[i] = O.opponent_random(recs[i], 2, 1, seed, i, require_two=False)
+    assert np.array_equal(gr.engine.export_records().cpu().numpy(), recs)
+    assert np.array_equal(gr.mask.cpu().numpy().astype(np.uint32).T, masks)
+    L = UnpackedLayout(2)
+    rng = np.random.default_rng(0)
+    for t in range(45):
+        act = np.full(n, 255, np.uint8)
+        want_reward = np.zeros(n, np.int64)
+        want_done = np.zeros(n, np.uint8)
+        for i in range(n):
+            g = O.Game(2, 1, record=recs[i])
+            if not g.rec[L.end_of_game] and masks[i].any():
+                a = O.random_action(masks[i], int(rng.integers(0, 2 ** 32)))
+                act[i] = a
+                assert g.step(a, None, seed, i) == 0
+            recs[i] = g.rec
+            d, masks[i] = O.opponent_random(recs[i], 2, 1, seed, i, require_two=True)
+            want_reward[i] = d - pscore[i]
+            pscore[i] = d
+            want_done[i] = recs[i][L.end_of_game]
+        out = gr.step(torch.from_numpy(act))
+        assert np.array_equal(gr.engine.export_records().cpu().numpy(), recs), t
+        assert np.array_equal(out["reward"].cpu().numpy().astype(np.int64), want_reward), t
+        assert np.array_equal(out["done"].cpu().numpy(), want_done), t
+        assert np.array_equal(out["mask"].cpu().numpy().astype(np.uint32).T, masks), t
+        assert np.array_equal(gr.player_score.cpu().numpy().astype(np.int64), pscore)
+    assert want_done.sum() > 0
+    # GameRunner invariant after step: seat 1 to move with >= 2 legal actions, or the game is over
+    cur = recs[:, L.current_player]
+    nvalid = np.array([sum(bin(int(w)).count("1") for w in m) for m in masks])
+    assert (((cur == 1) & (nvalid >= 2)) | (recs[:, L.end_of_game] == 1) | (recs[:, L.status] & 4 != 0)).all()
+
+
+def test_reward_kat_from_reference_fixture():
+    """tests/test_game_runner.py:52-62: from game_end_of_round_3 with player_score 49-32, stepping (0,3,0)
+    yields reward -6 (deterministic: the move ends the round, seat 1 starts the next with 72 legal moves)."""
+    from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner
+    from tests.helpers import load_kat
+    kat = load_kat()
+    rec = kat["fixture_records"][list(kat["fixture_names"]).index("game_end_of_round_3")].astype(np.int32)[None, :].copy()
+    L = UnpackedLayout(2)
+    rec[0, L.box:L.box + 5] = 20
+    gr = BatchedGameRunner(1, seed=3)
+    assert bool(gr.engine.import_records(rec).all())
+    gr.player_score.fill_(49 - 32)
+    out = gr.step(torch.tensor([0 + 6 * 3 + 30 * 0], dtype=torch.uint8))
+    assert int(out["reward"][0]) == -6 and int(out["done"][0]) == 0
+    r = gr.engine.export_records().cpu().numpy()[0]
+    assert int(gr.player_score[0]) == r[L.score] - r[L.score + 1] and r[L.current_player] == 1
+
+
+def test_selfplay_training_runs_and_learns_something():
+    from azul_deep_reinforcement_learning_b200.train import SelfPlayTrainer
+    tr = SelfPlayTrainer(games_per_rank=512, seed=1)
+    before = [p.detach().clone() for p in tr.net.parameters()]
+    hist = tr.train(batches=3, log=None)
+    assert len(hist) == 3 and all(np.isfinite(h["ac_loss"]) for h in hist)
+    assert all(h["games"] == 512 and h["unfinished"] == 0 for h in hist)
+    assert all(25 * 512 < h["transitions"] < 80 * 512 for h in hist)            # ~30-36 decisions per game
+    assert any(not torch.equal(a, b) for a, b in zip(before, tr.net.parameters()))
+    assert 0 <= hist[0]["win_percent"] <= 1 and 3 <= hist[0]["rounds"] <= 12

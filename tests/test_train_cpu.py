@@ -1,0 +1,92 @@
+"""Host-side training logic on CPU: the batched A2C loss equals ``Agent.update``'s (agent.py:39-62) on the same
+transitions, discounted returns follow nn_runner.py:72-75, and the 2-rank gradient all-reduce (gloo)
+reproduces the single-process global-batch gradient."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _fake_batch(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randint(0, 5, (n, 136), generator=g).float()
+    mask = torch.rand(n, 180, generator=g) < 0.15
+    mask[:, 0] = True
+    action = torch.multinomial(mask.float(), 1, generator=g).squeeze(1)
+    qval = torch.randn(n, generator=g) * 3
+    return obs, mask, action, qval
+
+
+def test_batched_loss_equals_agent_update_formula():
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.train import ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF, a2c_loss_terms
+    torch.manual_seed(0)
+    net = ActorCritic(136, 180)
+    obs, mask, action, qval = _fake_batch(57, 1)
+    a, c, e = a2c_loss_terms(net, obs, mask, action, qval)
+    loss = (ACTOR_COEFF * a + CRITIC_COEFF * c + ENTROPY_COEFF * e) / 57
+    grads = torch.autograd.grad(loss, list(net.parameters()))
+    # the reference formulation: per-decision lists, then Agent.update's means (agent.py:39-57)
+    values, log_probs, entropy = [], [], []
+    for i in range(57):
+        s = obs[i:i + 1]
+        values.append(net.forward_critic(s))
+        _, logp = net.forward_actor(s, mask[i:i + 1])
+        log_probs.append(logp.squeeze(0)[action[i]])
+        entropy.append(-logp.masked_select(mask[i:i + 1]).mean())
+    v = torch.stack(values).squeeze(2)
+    adv = qval.reshape(-1, 1) - v
+    ref = (-torch.stack(log_probs) * adv.squeeze(1)).mean() + 0.5 * adv.pow(2).mean() + 0.1 * torch.stack(entropy).mean()
+    ref_grads = torch.autograd.grad(ref, list(net.parameters()))
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    for g1, g2 in zip(grads, ref_grads):
+        assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-5)
+
+
+def test_discounted_returns():
+    from azul_deep_reinforcement_learning_b200.selfplay import discounted_returns
+    r = torch.tensor([[1.0, 2.0], [0.0, -1.0], [3.0, 5.0]])
+    act = torch.tensor([[True, True], [True, True], [True, False]])
+    q = discounted_returns(r, act, 0.99)
+    assert torch.allclose(q[:, 0], torch.tensor([1 + 0.99 * (0 + 0.99 * 3), 0 + 0.99 * 3, 3.0]))
+    assert torch.allclose(q[:2, 1], torch.tensor([2 + 0.99 * -1.0, -1.0]))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from azul_deep_reinforcement_learning_b200 import parallel
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.train import a2c_loss_terms, allreduce_gradients, global_count
+    parallel.init("gloo")
+    torch.manual_seed(0)
+    net = ActorCritic(136, 180)
+    n = 40 + 25 * rank                                      # ranks hold different numbers of transitions
+    obs, mask, action, qval = _fake_batch(n, 10 + rank)
+    n_global = global_count(n, "cpu")
+    a, c, e = a2c_loss_terms(net, obs, mask, action, qval)
+    ((a + 0.5 * c + 0.1 * e) / n_global).backward()
+    params = list(net.parameters())
+    allreduce_gradients(params)
+    torch.save([p.grad.clone() for p in params], os.path.join(out_dir, "grads%d.pt" % rank))
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_global_batch(tmp_path):
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.train import a2c_loss_terms
+    mp.spawn(_worker, args=(2, 29577, str(tmp_path)), nprocs=2, join=True)
+    torch.manual_seed(0)
+    net = ActorCritic(136, 180)
+    parts = [_fake_batch(40, 10), _fake_batch(65, 11)]
+    obs, mask, action, qval = [torch.cat([p[i] for p in parts]) for i in range(4)]
+    a, c, e = a2c_loss_terms(net, obs, mask, action, qval)
+    ref = torch.autograd.grad((a + 0.5 * c + 0.1 * e) / 105, list(net.parameters()))
+    for r in range(2):
+        got = torch.load(tmp_path / ("grads%d.pt" % r))
+        for g1, g2 in zip(got, ref):
+            assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-6)
