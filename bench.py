@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="random", choices=["random", "policy"],
+    ap.add_argument("--mode", default="random", choices=["random", "policy", "train"],
                     help="random: fused random-agent rollout (configs[1], the headline); policy: self-play with the "
                          "fused ActorCritic policy kernel, one env step per launch (configs[3])")
     ap.add_argument("--games", type=int, default=0, help="games per GPU (default 65536 random / 131072 policy)")
@@ -454,10 +454,84 @@ def run_policy(args):
         torch.distributed.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE.json configs[4]: the scripts/training.py-equivalent loop -- GPU self-play rollouts of --games
+    episodes per rank against the random opponent + one A2C update with a flat NCCL gradient all-reduce per
+    bench step."""
+    import torch
+    from azul_deep_reinforcement_learning_b200 import parallel
+    from azul_deep_reinforcement_learning_b200.train import SelfPlayTrainer
+
+    rank, world, local = parallel.world()
+    if world > 1:
+        parallel.init("nccl", local)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    tr = SelfPlayTrainer(args.games, seed=args.seed & 0x7FFFFFFF, device=local, rank=rank, world=world)
+    steps_word = lambda: int(tr.runner.engine.state[6].to(torch.int64).sum())   # noqa: E731  env steps executed so far
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        tr.update(tr.rollout())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env_steps, games, trans, upd_ms, roll_ms = 0, 0, 0.0, [], []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        s0 = steps_word()
+        batch = tr.rollout()
+        env_steps += steps_word() - s0           # (rollout resets keep the per-slot step counters running)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        st = tr.update(batch)
+        torch.cuda.synchronize()
+        upd_ms.append(1e3 * (time.perf_counter() - t1)); roll_ms.append(1e3 * (t1 - t0))
+        games += args.games; trans = st["transitions"]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = parallel.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    tot = torch.tensor([float(env_steps), float(games)], dtype=torch.float64, device=dev)
+    parallel.reduce_counters(tot)
+    if rank == 0:
+        cfg = workload_config(args, world)
+        cfg["workload"] = ("self-play A2C training: %d episodes per GPU per batch vs the random opponent (fused policy kernel "
+                           "rollouts), discounted returns, Agent.update loss, Adam, flat NCCL gradient all-reduce "
+                           "(BASELINE.json configs[4])" % args.games)
+        cfg.pop("env_steps_per_game_per_launch", None)
+        cfg["l2"] = "n/a (multi-kernel training step; working set is re-generated every batch)"
+        value = float(tot[0]) / (dev_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 rollout MLP / fp32 update / u32 rules", "data": "synthetic", "config": cfg,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 32,
+                    "note": "a training batch is end to end by construction: statistics are read back to the host every batch"},
+            "gpu_launches": None, "clocks": clocks,
+            "games_per_sec": float(tot[1]) / (dev_ms * 1e-3), "agent_decisions_per_batch": trans,
+            "rollout_ms": statistics.median(roll_ms), "update_ms": statistics.median(upd_ms),
+            "last": {k: tr.history[-1][k] if tr.history else None for k in ()},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if not args.games:
-        args.games = 131072 if args.mode == "policy" else 65536
+        args.games = {"policy": 131072, "train": 1024}.get(args.mode, 65536)
+    if args.mode == "train" and args.impl != "reference":
+        return run_train(args)
     if args.mode == "policy" and args.impl != "reference":
         return run_policy(args)
     if args.impl == "reference":
