@@ -3,7 +3,9 @@
 // action sampling (agent.py:64-81), the entropy term of nn_runner.py:36-40 and, optionally, the
 // env step, for a batch of 2-player games.
 //
-// Shape of the work: 128 games per tile (one game per thread, one tile per pass of a persistent CTA).
+// Shape of the work: 128 games per tile, one tile per pass of a persistent CTA of 512 threads: thread t
+// works on game (row) t & 127 and on column part t >> 7 (four threads share a game and split the
+// epilogue columns 4 x 48, so that an SM holds 16 warps although shared memory allows one CTA).
 //   layer 1   [128 x 144] x [144 x 368]   obs (136, zero-padded to 144) times [W1_actor ; W1_critic]^T
 //             (180 + 180 hidden units back to back, padded to 368; two MMAs of N = 192 + 176)
 //                                                                              -> TMEM columns [0,368)
@@ -24,7 +26,10 @@ using namespace azb;
 
 namespace pol {
 
-constexpr int TILE_M = 128;                 // games per tile == threads per CTA
+constexpr int TILE_M = 128;                 // games per tile (rows of the MMA)
+constexpr int PARTS = 4;                    // threads per game: each handles 48 of the 192 epilogue columns
+constexpr int THREADS = TILE_M * PARTS;
+constexpr int PART_COLS = 48;
 constexpr int K1 = 144, K1_CHUNKS = K1 / 8; // obs 136 -> 144 (multiple of the MMA K = 16)
 constexpr int N1A = 192, N1C = 176;         // the two layer-1 MMA N blocks (rows 0..191 and 192..367 of W1)
 constexpr int N1 = N1A + N1C, N1_GROUPS = N1 / 8;
@@ -118,6 +123,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
@@ -161,7 +181,7 @@ __device__ __forceinline__ float obs_value(const Game<2>& g, uint32_t pat_me, ui
     }
 }
 
-template <int CH>
+template <int CH, int STRIDE>
 __device__ __forceinline__ void obs_chunks(const Game<2>& g, uint32_t pat_me, uint32_t pat_ot, uint32_t wall_me,
                                            uint32_t wall_ot, uint32_t scf_me, uint32_t scf_ot, int persp,
                                            unsigned char* a_tile, int row)
@@ -173,17 +193,23 @@ __device__ __forceinline__ void obs_chunks(const Game<2>& g, uint32_t pat_me, ui
         v.z = pack_bf16(OV(4), OV(5)); v.w = pack_bf16(OV(6), OV(7));
 #undef OV
         *reinterpret_cast<uint4*>(a_tile + (CH * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = v;
-        obs_chunks<CH + 1>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row);
+        obs_chunks<CH + STRIDE, STRIDE>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row);
     }
 }
 
-__device__ __forceinline__ void build_obs_tile(const Game<2>& g, unsigned char* a_tile, int row)
+// the four threads of a game build the 18 observation chunks round-robin (part is warp-uniform)
+__device__ __forceinline__ void build_obs_tile(const Game<2>& g, unsigned char* a_tile, int row, int part)
 {
     const int persp = g.seat();
     const uint32_t pat_me = g.sel(g.pat, persp), pat_ot = g.sel(g.pat, 1 - persp);
     const uint32_t wall_me = g.sel(g.wall, persp), wall_ot = g.sel(g.wall, 1 - persp);
     const uint32_t scf_me = g.sel(g.scf, persp), scf_ot = g.sel(g.scf, 1 - persp);
-    obs_chunks<0>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row);
+    switch (part) {
+    case 0: obs_chunks<0, PARTS>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row); break;
+    case 1: obs_chunks<1, PARTS>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row); break;
+    case 2: obs_chunks<2, PARTS>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row); break;
+    default: obs_chunks<3, PARTS>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row); break;
+    }
 }
 
 // 6 x 30-bit mask words (word p = destination p) -> 180 contiguous bits, bit a = action a
@@ -232,15 +258,31 @@ struct SmemSink {
     }
 };
 
+// bits [start, start + 48) of the 180-bit linear mask; start is 0, 48, 96 or 144
+__device__ __forceinline__ uint64_t mask_window(const uint32_t (&lin)[6], int start)
+{
+    const int w = start >> 5, sh = start & 31;
+    const uint64_t x = (((uint64_t)pick6(lin, w + 1) << 32) | pick6(lin, w)) >> sh;
+    return x & 0xFFFFFFFFFFFFull;
+}
+
+// cross-part scratch (aliases the A tile, which is idle between the layer-2 MMA and the next tile)
+struct RowPart { float m, s, sl, value; int amax, n; };
+constexpr int OFF_PARTS = 0;                                             // RowPart[PARTS][TILE_M]
+constexpr int OFF_RESULT = OFF_PARTS + PARTS * TILE_M * (int)sizeof(RowPart);   // int2[TILE_M]: sampled action, logit bits
+static_assert(OFF_RESULT + TILE_M * 8 <= A_BYTES, "scratch exceeds the A tile");
+
 template <int POOL>
-__global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
+__global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TILE_M - 1), part = tid >> 7;
     unsigned char* a_tile = smem + OFF_A;
     const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
     const uint32_t bar1 = smem_u32(smem + OFF_BAR), bar2 = bar1 + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+    RowPart* parts = reinterpret_cast<RowPart*>(a_tile + OFF_PARTS);
+    int2* result = reinterpret_cast<int2*>(a_tile + OFF_RESULT);
     __shared__ unsigned long long cnt[AZB_N_COUNTERS];
     if (tid < AZB_N_COUNTERS) cnt[tid] = 0ull;
     SmemSink sink{cnt};
@@ -249,7 +291,7 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
     {
         const uint4* src = reinterpret_cast<const uint4*>(A.packed);
         uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < PACKED_BYTES / 16; i += TILE_M) dst[i] = src[i];
+        for (int i = tid; i < PACKED_BYTES / 16; i += THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
         mbar_init(bar1, 1);
@@ -265,22 +307,23 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches TMEM lanes 32*(warp%4)..+31
 
     const uint32_t w1_addr = smem_u32(smem + OFF_W1), w2_addr = smem_u32(smem + OFF_W2), a_addr = smem_u32(a_tile);
     const Philox rng{A.k0, A.k1};
     uint32_t phase = 0;
     const int64_t tiles = (A.n + TILE_M - 1) / TILE_M;
+    const int col0 = part * PART_COLS;                 // this thread's 48 epilogue columns
 
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t g = tile * TILE_M + tid;
+        const int64_t g = tile * TILE_M + row;
         const bool valid = g < A.n;
         const int64_t gl = valid ? g : A.n - 1;
         Game<2> gm;
         gm.load(A.state_in, A.n, gl);
 
         // ---- observation tile -> shared memory (layer-1 A operand) ----
-        build_obs_tile(gm, a_tile, tid);
+        build_obs_tile(gm, a_tile, row, part);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -303,11 +346,11 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
 
         // ---- epilogue 1: actor hidden -> relu -> bf16 -> shared memory (layer-2 A operand, aliases the obs tile) ----
 #pragma unroll 1
-        for (int c0 = 0; c0 < N1A; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_row + c0, v);
+        for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_row + c0, v);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 2; q++) {
                 uint4 o;
                 uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
@@ -316,18 +359,8 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
                     ow[e] = j < HID ? pack_bf16(fmaxf(v[8 * q + 2 * e] + vec[V_B1 + j], 0.0f),
                                                 fmaxf(v[8 * q + 2 * e + 1] + vec[V_B1 + j + 1], 0.0f)) : 0u;
                 }
-                *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (tid >> 3)) * 128 + (tid & 7) * 16) = o;
+                *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = o;
             }
-        }
-        // ---- critic head on CUDA cores straight from TMEM: value = w2c . relu(h_c + b1c) + b2c ----
-        float value = vec[V_B2C];
-#pragma unroll 1
-        for (int c0 = 0; c0 < 192; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_row + HID + c0, v);                          // critic hidden units c0 .. c0+31 live in columns 180 + unit
-#pragma unroll
-            for (int i = 0; i < 32; i++)
-                if (c0 + i < HID) value = fmaf(fmaxf(v[i] + vec[V_B1 + HID + c0 + i], 0.0f), vec[V_W2C + c0 + i], value);
         }
         fence_async_smem();
         tc_fence_before();
@@ -348,26 +381,34 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
         tc_fence_after();
         phase ^= 1;
 
-        // ---- epilogue 2: masked softmax / log-softmax, sampling, entropy term ----
+        // ---- epilogue 2a: per part -- critic partial sum and online softmax over its 48 columns ----
         uint32_t m[6], lin[6];
         legal_mask(gm, m);
         linear_mask(m, lin);
-        const int n_valid = __popc(lin[0]) + __popc(lin[1]) + __popc(lin[2]) + __popc(lin[3]) + __popc(lin[4]) + __popc(lin[5]);
-        // pass 1: running max and sum of exp over the legal logits (online softmax), sum of legal logits, argmax
+        const uint64_t mybits = mask_window(lin, col0);
+        float value_p = 0.0f;
+#pragma unroll 1
+        for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {      // critic hidden unit u lives in TMEM column 180 + u
+            float v[16];
+            tmem_ld16(tmem_row + HID + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (c0 + i < HID) value_p = fmaf(fmaxf(v[i] + vec[V_B1 + HID + c0 + i], 0.0f), vec[V_W2C + c0 + i], value_p);
+        }
         float mx = -INFINITY, se = 0.0f, sl = 0.0f;
         int amax = 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 192; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_row + c0, v);
-            const uint32_t bits = pick6(lin, c0 >> 5);
+        for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_row + c0, v);
+            const uint32_t bits = (uint32_t)(mybits >> (c0 - col0)) & 0xFFFFu;
             if (A.logits_out && valid) {
 #pragma unroll
-                for (int i = 0; i < 32; i++)
+                for (int i = 0; i < 16; i++)
                     if (c0 + i < ACT) A.logits_out[g * ACT + c0 + i] = v[i] + vec[V_B2A + c0 + i];
             }
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
+            for (int i = 0; i < 16; i++) {
                 if ((bits >> i) & 1u) {
                     const float l = v[i] + vec[V_B2A + c0 + i];
                     sl += l;
@@ -376,77 +417,128 @@ __global__ void __launch_bounds__(TILE_M, 1) k_policy(PolicyArgs A)
                 }
             }
         }
-        const float lse = mx + __logf(se);              // log sum exp over the legal actions
-        uint32_t action = (uint32_t)amax;
-        float la = mx;                                  // logit of the chosen action (argmax mode: the max)
+        {
+            RowPart rp;
+            rp.m = mx; rp.s = se; rp.sl = sl; rp.value = value_p; rp.amax = amax; rp.n = __popcll(mybits);
+            parts[part * TILE_M + row] = rp;
+            if (part == 0) result[row] = make_int2(-1, 0);
+        }
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- epilogue 2b: merge the four parts of the row (every thread of the row computes the same numbers) ----
+        float gmx = -INFINITY, gsl = 0.0f, value = vec[V_B2C];
+        int n_valid = 0, gamax = 0;
+#pragma unroll
+        for (int q = 0; q < PARTS; q++) {
+            const RowPart rp = parts[q * TILE_M + row];
+            if (rp.n > 0 && rp.m > gmx) { gmx = rp.m; gamax = rp.amax; }
+            gsl += rp.sl; value += rp.value; n_valid += rp.n;
+        }
+        // slices of the cumulative distribution: part q owns [run_{q-1}, run_q); every thread of the row adds the
+        // same numbers in the same order, so the four threads agree on the owner bit for bit
+        float gse = 0.0f, prefix = 0.0f;
+        float wq[PARTS];
+        int last_part = 0;
+#pragma unroll
+        for (int q = 0; q < PARTS; q++) {
+            const RowPart rp = parts[q * TILE_M + row];
+            wq[q] = rp.n > 0 ? rp.s * __expf(rp.m - gmx) : 0.0f;
+            if (rp.n > 0) last_part = q;
+            if (q < part) prefix += wq[q];
+            gse += wq[q];
+        }
+        const float lse = gmx + __logf(gse);
         if (A.mode == 0) {
-            // pass 2: inverse-CDF sampling with one Philox word (agent.py:69 np.random.choice(p = policy)).
-            // tcgen05.ld is warp-collective: every lane runs the loop, lanes without a legal action only idle.
+            // inverse-CDF sampling with one Philox word (agent.py:69 np.random.choice(p = policy)).  tcgen05.ld is
+            // warp-collective, so every lane runs the loop; only the owning part does arithmetic.
             uint32_t w[4];
             rng(A.gid0 + (uint32_t)gl, gm.steps >> 2, PURPOSE_POLICY, 0u, w);
             const uint32_t idx = gm.steps & 3u;
             const uint32_t word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
-            const float target = (float)(word >> 8) * (1.0f / 16777216.0f) * se;
-            float cum = 0.0f;
-            bool found = false;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 192; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_row + c0, v);
-                const uint32_t bits = pick6(lin, c0 >> 5);
+            const float target = (float)(word >> 8) * (1.0f / 16777216.0f) * gse;
+            int owner = -1;
+            float run = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    if (((bits >> i) & 1u) && !found) {
+            for (int q = 0; q < PARTS; q++) {
+                run += wq[q];
+                if (owner < 0 && target < run) owner = q;
+            }
+            if (owner < 0) owner = last_part;
+            const bool mine = owner == part && n_valid > 0;
+            float cum = prefix;
+            bool found = false;
+            int chosen = -1;
+            float chosen_l = 0.0f;
+#pragma unroll 1
+            for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_row + c0, v);
+                const uint32_t bits = (uint32_t)(mybits >> (c0 - col0)) & 0xFFFFu;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (mine && ((bits >> i) & 1u) && !found) {
                         const float l = v[i] + vec[V_B2A + c0 + i];
-                        cum += __expf(l - mx);
-                        action = (uint32_t)(c0 + i);     // falls back to the last legal action if rounding leaves cum <= target
-                        la = l;
+                        cum += __expf(l - gmx);
+                        chosen = c0 + i;                     // rounding may leave cum <= target: then the part's last legal action
+                        chosen_l = l;
                         if (cum > target) found = true;
                     }
                 }
             }
+            if (mine) result[row] = make_int2(chosen, __float_as_int(chosen_l));
         }
-        const float logp = n_valid > 0 ? la - lse : 0.0f;
-        const float entropy = n_valid > 0 ? -(sl / (float)n_valid - lse) : 0.0f;
-
-        uint32_t status = n_valid > 0 ? 0u : (gm.ended() ? (uint32_t)ST_ENDED : (uint32_t)ST_STUCK);
-        if (valid) {
-            if (A.mask6_out) {
-#pragma unroll
-                for (int p = 0; p < 6; p++) A.mask6_out[p * A.n + g] = m[p];
-            }
-            if (A.value_out) A.value_out[g] = value;
-            if (A.action_out) A.action_out[g] = n_valid > 0 ? (uint8_t)action : (uint8_t)AZB_ACTION_SKIP;
-            if (A.logp_out) A.logp_out[g] = logp;
-            if (A.entropy_out) A.entropy_out[g] = entropy;
-        }
-        bool finished = false;
-        if (A.apply_step && n_valid > 0 && !gm.ended()) {
-            const uint32_t gid = A.gid0 + (uint32_t)gl;
-            const uint32_t turn_before = gm.turn_counter();
-            finished = advance<2, POOL>(gm, action, [&](Game<2>& gg) { new_round_philox<2, POOL>(gg, rng, gid, PURPOSE_REFILL); });
-            if (valid && A.apply_step == 2) {
-                sink.add(0, 1);
-                if (gm.turn_counter() != turn_before) sink.add(2, 1);
-            }
-        }
-        const bool done_now = gm.ended();
-        if (A.apply_step == 2 && (done_now || (n_valid == 0 && !gm.ended()))) {
-            // game over (or stuck): count it and start a fresh game in the slot (GameRunner.reset, game_runner.py:76-80)
-            if (valid) {
-                if (finished) tally_finished(gm, sink);
-                else if (!done_now) sink.add(6, 1);
-                sink.add(2, 1);
-            }
-            reset_game<2, POOL>(gm, rng, A.gid0 + (uint32_t)gl, A.first_rule);
-        }
-        if (valid && A.apply_step) gm.store(A.state, A.n, g);
-        if (valid) {
-            if (A.done_out) A.done_out[g] = done_now ? 1 : 0;
-            if (A.status_out) A.status_out[g] = (uint8_t)(status | gm.status());
-        }
-        // every thread's TMEM reads are complete before the next tile's layer 1 overwrites the accumulators
         tc_fence_before();
+        __syncthreads();
+
+        // ---- epilogue 2c: one thread per game publishes the decision and plays the move ----
+        if (part == 0) {
+            uint32_t action = (uint32_t)gamax;
+            float la = gmx;                             // argmax mode, and the fallback if rounding left no part a winner
+            if (A.mode == 0) {
+                const int2 r = result[row];
+                if (r.x >= 0) { action = (uint32_t)r.x; la = __int_as_float(r.y); }
+            }
+            const float logp = n_valid > 0 ? la - lse : 0.0f;
+            const float entropy = n_valid > 0 ? -(gsl / (float)n_valid - lse) : 0.0f;
+            uint32_t status = n_valid > 0 ? 0u : (gm.ended() ? (uint32_t)ST_ENDED : (uint32_t)ST_STUCK);
+            if (valid) {
+                if (A.mask6_out) {
+#pragma unroll
+                    for (int p = 0; p < 6; p++) A.mask6_out[p * A.n + g] = m[p];
+                }
+                if (A.value_out) A.value_out[g] = value;
+                if (A.action_out) A.action_out[g] = n_valid > 0 ? (uint8_t)action : (uint8_t)AZB_ACTION_SKIP;
+                if (A.logp_out) A.logp_out[g] = logp;
+                if (A.entropy_out) A.entropy_out[g] = entropy;
+            }
+            bool finished = false;
+            if (A.apply_step && n_valid > 0 && !gm.ended()) {
+                const uint32_t gid = A.gid0 + (uint32_t)gl;
+                const uint32_t turn_before = gm.turn_counter();
+                finished = advance<2, POOL>(gm, action, [&](Game<2>& gg) { new_round_philox<2, POOL>(gg, rng, gid, PURPOSE_REFILL); });
+                if (valid && A.apply_step == 2) {
+                    sink.add(0, 1);
+                    if (gm.turn_counter() != turn_before) sink.add(2, 1);
+                }
+            }
+            const bool done_now = gm.ended();
+            if (A.apply_step == 2 && (done_now || (n_valid == 0 && !gm.ended()))) {
+                // game over (or stuck): count it and start a fresh game in the slot (GameRunner.reset, game_runner.py:76-80)
+                if (valid) {
+                    if (finished) tally_finished(gm, sink);
+                    else if (!done_now) sink.add(6, 1);
+                    sink.add(2, 1);
+                }
+                reset_game<2, POOL>(gm, rng, A.gid0 + (uint32_t)gl, A.first_rule);
+            }
+            if (valid && A.apply_step) gm.store(A.state, A.n, g);
+            if (valid) {
+                if (A.done_out) A.done_out[g] = done_now ? 1 : 0;
+                if (A.status_out) A.status_out[g] = (uint8_t)(status | gm.status());
+            }
+        }
+        // all TMEM reads and scratch reads of this tile are complete before the next tile overwrites them
         __syncthreads();
     }
 
@@ -527,10 +619,10 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     if (h->tile_pool == AZB_POOL_LID) {
         AZB_CUDA(cudaFuncSetAttribute(pol::k_policy<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
-        pol::k_policy<1><<<grid, pol::TILE_M, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
+        pol::k_policy<1><<<grid, pol::THREADS, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
     } else {
         AZB_CUDA(cudaFuncSetAttribute(pol::k_policy<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
-        pol::k_policy<0><<<grid, pol::TILE_M, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
+        pol::k_policy<0><<<grid, pol::THREADS, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
     }
     CHECK_LAUNCH();
     return 0;
