@@ -362,6 +362,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = o;
             }
         }
+        // ---- critic head, partial sum over this part's units (before layer 2 reuses TMEM columns 180..191) ----
+        float value_p = 0.0f;
+#pragma unroll 1
+        for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {      // critic hidden unit u lives in TMEM column 180 + u
+            float v[16];
+            tmem_ld16(tmem_row + HID + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (c0 + i < HID) value_p = fmaf(fmaxf(v[i] + vec[V_B1 + HID + c0 + i], 0.0f), vec[V_W2C + c0 + i], value_p);
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -386,15 +396,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         legal_mask(gm, m);
         linear_mask(m, lin);
         const uint64_t mybits = mask_window(lin, col0);
-        float value_p = 0.0f;
-#pragma unroll 1
-        for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {      // critic hidden unit u lives in TMEM column 180 + u
-            float v[16];
-            tmem_ld16(tmem_row + HID + c0, v);
-#pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (c0 + i < HID) value_p = fmaf(fmaxf(v[i] + vec[V_B1 + HID + c0 + i], 0.0f), vec[V_W2C + c0 + i], value_p);
-        }
         float mx = -INFINITY, se = 0.0f, sl = 0.0f;
         int amax = 0;
 #pragma unroll 1
