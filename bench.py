@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="random", choices=["random", "policy", "train"],
+    ap.add_argument("--mode", default="random", choices=["random", "policy", "train", "step"],
                     help="random: fused random-agent rollout (configs[1], the headline); policy: self-play with the "
                          "fused ActorCritic policy kernel, one env step per launch (configs[3])")
     ap.add_argument("--games", type=int, default=0, help="games per GPU (default 65536 random / 131072 policy)")
@@ -454,6 +454,60 @@ def run_policy(args):
         torch.distributed.destroy_process_group()
 
 
+def run_step(args):
+    """The single-step entry point the reference's callers use (one Azul.step + next legal mask per call,
+    actions supplied by the caller): a genuinely HBM-bound pass -- packed state read + written, 1 action byte in,
+    24 mask bytes + done + status out per game -- on a batch larger than L2."""
+    import torch
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul
+    from azul_deep_reinforcement_learning_b200.layout import algorithmic_bytes_per_step
+    import ctypes
+    dev = torch.device("cuda", 0)
+    pool = 1 if args.pool == "lid" else 0
+    G = args.games
+    eng = BatchedAzul(G, args.players, pool, 0, seed=args.seed)
+    eng.rollout_random(17)
+    mask = eng.legal_mask()
+    done = torch.empty(G, dtype=torch.uint8, device=dev)
+    status = torch.empty(G, dtype=torch.uint8, device=dev)
+    # a legal action per game: the lowest set bit of the first non-empty mask word (computed once, outside the timing)
+    m = (mask.to(torch.int64) & 0xFFFFFFFF)
+    word = (m != 0).to(torch.int64).argmax(dim=0)
+    w = m.gather(0, word[None, :]).squeeze(0)
+    low = (w & -w).to(torch.float64).log2().round().to(torch.int64)
+    action = (30 * word + low).to(torch.uint8)
+    snapshot = eng.state.clone()
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+
+    def launch():
+        assert eng.lib.azb_step(eng._h, p(eng.state), p(action), None, p(mask), None, p(done), p(status), st) == 0
+
+    ms = []
+    for i in range(max(args.warmup, 3) + args.steps):
+        eng.state.copy_(snapshot)                 # same legal actions every iteration; also evicts nothing we time
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); launch(); e1.record()
+        torch.cuda.synchronize()
+        if i >= max(args.warmup, 3):
+            ms.append(e0.elapsed_time(e1))
+    assert int(status.max()) & 3 == 0
+    b_alg = algorithmic_bytes_per_step(args.players) + 2
+    t = statistics.median(ms) * 1e-3
+    peak, src = hbm_peak()
+    cfg = workload_config(args, 1)
+    cfg["workload"] = "%d parallel %d-player games, ONE Azul.step + next legal mask per launch, caller-supplied actions" % (G, args.players)
+    cfg["env_steps_per_game_per_launch"] = 1
+    cfg["l2"] = "working set %.0f MB per launch (state %d B + 28 B per game) exceeds the 126 MB L2" % (G * b_alg / 1e6, 4 * eng.W)
+    print(json.dumps({
+        "metric": METRIC, "value": G / t, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": cfg, "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": G * b_alg / t / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": G * b_alg / t / 1e9 / peak, "traffic": None, "peak_source": src,
+                     "algorithmic_bytes_per_env_step": b_alg, "kernel": "k_step<%d,%d>" % (args.players, pool)}}))
+
+
 def run_train(args):
     """BASELINE.json configs[4]: the scripts/training.py-equivalent loop -- GPU self-play rollouts of --games
     episodes per rank against the random opponent + one A2C update with a flat NCCL gradient all-reduce per
@@ -529,9 +583,11 @@ def run_train(args):
 def main():
     args = parse_args()
     if not args.games:
-        args.games = {"policy": 131072, "train": 1024}.get(args.mode, 65536)
+        args.games = {"policy": 131072, "train": 1024, "step": 1 << 22}.get(args.mode, 65536)
     if args.mode == "train" and args.impl != "reference":
         return run_train(args)
+    if args.mode == "step" and args.impl != "reference":
+        return run_step(args)
     if args.mode == "policy" and args.impl != "reference":
         return run_policy(args)
     if args.impl == "reference":
