@@ -128,6 +128,13 @@ struct BlockSink {
     {
         if (v) atomicAdd(&c[i], (unsigned long long)v);
     }
+    // all currently converged lanes call this together: one REDUX + at most one shared atomic per warp
+    __device__ __forceinline__ void add_group(int i, uint32_t v)
+    {
+        const unsigned lanes = __activemask();
+        const uint32_t tot = __reduce_add_sync(lanes, v);
+        if (tot && (threadIdx.x & 31) == (unsigned)(__ffs((int)lanes) - 1)) atomicAdd(&c[i], (unsigned long long)tot);
+    }
 };
 
 template <int P, int POOL>

@@ -256,6 +256,7 @@ struct SmemSink {
     {
         if (v) atomicAdd(&c[i], (unsigned long long)v);
     }
+    __device__ __forceinline__ void add_group(int i, uint32_t v) { add(i, v); }
 };
 
 // bits [start, start + 48) of the 180-bit linear mask; start is 0, 48, 96 or 144

@@ -199,50 +199,47 @@ AZB_HD uint32_t floor_add(uint32_t scf, uint32_t n)
 template <int P, int POOL>
 AZB_HD void apply_move(Game<P>& g, uint32_t action)
 {
+    // Branch-free: a warp holds 32 different games, so "display or centre" and "pattern line or floor"
+    // are selects, not branches.  A centre take is the display case with an empty "rest".
     const uint32_t p = action / 30u, b = action - 30u * p, c = b / 6u, d = b - 6u * c;
     const int s = g.seat();
-    uint32_t scf = g.sel(g.scf, s);
-    uint32_t n = ((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2);
+    const bool from_display = d != 0u;
     const uint32_t cbit = 1u << (6u * c);
-    if (d != 0) {
-        // azul.py:125-133: chosen colour leaves, the rest of display d is added to the centre,
-        // as a bit-sliced 4-bit ripple add over all five colours at once
-        const uint32_t r0 = (g.pl0 >> d) & M6 & ~cbit, r1 = (g.pl1 >> d) & M6 & ~cbit, r2 = (g.pl2 >> d) & M6 & ~cbit;
-        const uint32_t c0 = g.pl0 & M6, c1 = g.pl1 & M6, c2 = g.pl2 & M6, c3 = spread5to6(g.misc & 31u);
-        const uint32_t s0 = c0 ^ r0, k0 = c0 & r0;
-        const uint32_t s1 = c1 ^ r1 ^ k0, k1 = (c1 & r1) | (k0 & (c1 ^ r1));
-        const uint32_t s2 = c2 ^ r2 ^ k1, k2 = (c2 & r2) | (k1 & (c2 ^ r2));
-        const uint32_t s3 = c3 ^ k2;
-        const uint32_t keep = ~((M6 << d) | M6);
-        g.pl0 = (g.pl0 & keep) | s0; g.pl1 = (g.pl1 & keep) | s1; g.pl2 = (g.pl2 & keep) | s2;
-        g.misc = (g.misc & ~31u) | gather6to5(s3);
-    } else {
-        // azul.py:134-143: take from the centre; the token goes to the floor first
-        n |= ((g.misc >> c) & 1u) << 3;
-        g.pl0 &= ~cbit; g.pl1 &= ~cbit; g.pl2 &= ~cbit;
-        g.misc &= ~(1u << c);
-        if (g.misc & 32u) {
-            g.misc &= ~32u;
-            g.set_next_first_player(g.current_player());
-            scf = floor_add(scf, 1u);
-        }
-    }
-    uint32_t to_floor = n;
-    if (p != 0) {
-        // azul.py:145-157: fill row p-1 up to its capacity p, the rest falls to the floor
-        uint32_t pat = g.sel(g.pat, s);
-        const uint32_t sh = 6u * (p - 1u);
-        const uint32_t cnt = (pat >> (sh + 3u)) & 7u;
-        const uint32_t room = p - cnt;                 // p >= cnt always
-        const uint32_t placed = n < room ? n : room;
-        to_floor = n - placed;
-        const uint32_t newcnt = cnt + placed;
-        pat = (pat & ~(63u << sh)) | ((newcnt ? (c | (newcnt << 3)) : 0u) << sh);
-        g.put(g.pat, s, pat);
-    }
-    scf = floor_add(scf, to_floor);
-    g.put(g.scf, s, scf);
-    if (POOL == POOL_LID) g.lid += to_floor << (6u * c);          // azul.py:156-157,160-161
+    uint32_t n = ((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2) |
+                 (from_display ? 0u : ((g.misc >> c) & 1u) << 3);
+    // azul.py:125-133: the chosen colour leaves, the rest of display d joins the centre -- a bit-sliced
+    // 4-bit ripple add over all five colours at once.  azul.py:134-138: from the centre only colour c leaves.
+    const uint32_t rest = from_display ? (M6 & ~cbit) : 0u;
+    const uint32_t r0 = (g.pl0 >> d) & rest, r1 = (g.pl1 >> d) & rest, r2 = (g.pl2 >> d) & rest;
+    const uint32_t c0 = g.pl0 & M6, c1 = g.pl1 & M6, c2 = g.pl2 & M6, c3 = spread5to6(g.misc & 31u);
+    const uint32_t keepc = from_display ? M6 : (M6 & ~cbit);
+    const uint32_t s0 = c0 ^ r0, k0 = c0 & r0;
+    const uint32_t s1 = c1 ^ r1 ^ k0, k1 = (c1 & r1) | (k0 & (c1 ^ r1));
+    const uint32_t s2 = c2 ^ r2 ^ k1, k2 = (c2 & r2) | (k1 & (c2 ^ r2));
+    const uint32_t s3 = c3 ^ k2;
+    const uint32_t clear = ~((M6 << d) | M6);           // the emptied display (or nothing more, d = 0) and the old centre
+    g.pl0 = (g.pl0 & clear) | (s0 & keepc);
+    g.pl1 = (g.pl1 & clear) | (s1 & keepc);
+    g.pl2 = (g.pl2 & clear) | (s2 & keepc);
+    uint32_t misc = (g.misc & ~31u) | gather6to5(s3 & keepc);
+    // azul.py:139-143: the first-player token goes with the first centre take, onto the floor first
+    const uint32_t tok = from_display ? 0u : (misc >> 5) & 1u;
+    misc &= ~(tok << 5);
+    misc = tok ? ((misc & ~(7u << 9)) | (((misc >> 6) & 7u) << 9)) : misc;
+    g.misc = misc;
+    // azul.py:145-161: fill row p-1 up to its capacity p, the rest (everything when p = 0) falls to the floor
+    const bool to_row = p != 0u;
+    const uint32_t pat = g.sel(g.pat, s);
+    const uint32_t sh = to_row ? 6u * (p - 1u) : 0u;
+    const uint32_t cnt = (pat >> (sh + 3u)) & 7u;
+    const uint32_t room = to_row ? p - cnt : 0u;        // p >= cnt always
+    const uint32_t placed = n < room ? n : room;
+    const uint32_t to_floor = n - placed;
+    const uint32_t newcnt = cnt + placed;
+    const uint32_t newpat = (pat & ~(63u << sh)) | ((newcnt ? (c | (newcnt << 3)) : 0u) << sh);
+    g.put(g.pat, s, to_row ? newpat : pat);
+    g.put(g.scf, s, floor_add(g.sel(g.scf, s), tok + to_floor));     // azul.py:119-123 (cap 7)
+    if (POOL == POOL_LID) g.lid += to_floor << (6u * c);              // azul.py:156-157,160-161
 }
 
 // azul.py:177-181
@@ -511,23 +508,23 @@ AZB_HD uint32_t select_bit(uint32_t m, uint32_t k)
 
 // The integer random agent (game_runner.py:87-97): legal floor actions (p = 0) weigh 1, every
 // other legal action 100; the point r = mulhi(word, total) walks words 1..5 first, then word 0.
-// Returns 180 when no action is legal.
+// Returns 180 when no action is legal.  Branch-free up to the final bit select.
 AZB_HD uint32_t random_action(const uint32_t m[6], uint32_t word)
 {
     const uint32_t n1 = (uint32_t)popc(m[1]), n2 = (uint32_t)popc(m[2]), n3 = (uint32_t)popc(m[3]),
                    n4 = (uint32_t)popc(m[4]), n5 = (uint32_t)popc(m[5]), n0 = (uint32_t)popc(m[0]);
-    const uint32_t n_hi = n1 + n2 + n3 + n4 + n5;
+    const uint32_t e1 = n1, e2 = e1 + n2, e3 = e2 + n3, e4 = e3 + n4, n_hi = e4 + n5;
     const uint32_t total = 100u * n_hi + n0;
-    if (total == 0u) return 180u;
     const uint32_t r = mulhi(word, total);
-    if (r >= 100u * n_hi) return select_bit(m[0], r - 100u * n_hi);
-    uint32_t k = r / 100u;
-    uint32_t w = m[1], base = 30u;
-    if (k >= n1) { k -= n1; w = m[2]; base = 60u;
-        if (k >= n2) { k -= n2; w = m[3]; base = 90u;
-            if (k >= n3) { k -= n3; w = m[4]; base = 120u;
-                if (k >= n4) { k -= n4; w = m[5]; base = 150u; } } } }
-    return base + select_bit(w, k);
+    const bool heavy = r < 100u * n_hi;
+    const uint32_t kh = r / 100u;                        // rank among the heavy actions
+    const uint32_t i = (uint32_t)(kh >= e1) + (uint32_t)(kh >= e2) + (uint32_t)(kh >= e3) + (uint32_t)(kh >= e4);
+    const uint32_t before = i == 0u ? 0u : i == 1u ? e1 : i == 2u ? e2 : i == 3u ? e3 : e4;
+    const uint32_t wh = i == 0u ? m[1] : i == 1u ? m[2] : i == 2u ? m[3] : i == 3u ? m[4] : m[5];
+    const uint32_t w = heavy ? wh : m[0];
+    const uint32_t k = heavy ? kh - before : r - 100u * n_hi;
+    const uint32_t base = heavy ? 30u * (i + 1u) : 0u;
+    return total == 0u ? 180u : base + select_bit(w, k);
 }
 
 // ---- unpacked record <-> packed game (kernel K7; record layout in layout.py) -----------------
@@ -643,24 +640,27 @@ AZB_HD void export_record(const Game<P>& g, Wr wr)
 // bag empty, 8 sum turn_counter, 9 sum -floor_penalty seat 0, 10 sum max_combo seat 0, 11 completed
 // rows, 12 completed columns, 13 completed colours (seat 0), 14 sum first_player_stats seat 0,
 // 15 sum of all seats' scores.  Sink::add(index, value) receives the increments.
+// `fin` selects the games of the calling group that just ended; Sink::add_group may aggregate the
+// increments of all calling lanes (the kernels reduce them with one REDUX per counter and warp).
 template <int P, typename Sink>
-AZB_HD void tally_finished(const Game<P>& g, Sink& sink)
+AZB_HD void tally_finished(const Game<P>& g, Sink& sink, bool fin = true)
 {
-    sink.add(1, 1);
-    sink.add(3, g.scf[0] & 0xFFFFu);
-    sink.add(4, g.scf[1] & 0xFFFFu);
-    sink.add(5, (g.scf[0] & 0xFFFFu) > (g.scf[1] & 0xFFFFu) ? 1u : 0u);
-    sink.add(8, g.turn_counter());
-    sink.add(9, (g.sta[0] >> 12) & 0xFFFFu);
-    sink.add(10, g.sta[0] >> 28);
-    sink.add(11, g.stb[0] & 255u);
-    sink.add(12, (g.stb[0] >> 16) & 255u);
-    sink.add(13, (g.stb[0] >> 8) & 255u);
-    sink.add(14, g.sta[0] & 0xFFFu);
+    const uint32_t s0 = g.scf[0] & 0xFFFFu, s1 = g.scf[1] & 0xFFFFu, f = fin ? 1u : 0u;
     uint32_t all = 0;
 #pragma unroll
     for (int p = 0; p < P; p++) all += g.scf[p] & 0xFFFFu;
-    sink.add(15, all);
+    sink.add_group(1, f);
+    sink.add_group(3, f * s0);
+    sink.add_group(4, f * s1);
+    sink.add_group(5, f * (s0 > s1 ? 1u : 0u));
+    sink.add_group(8, f * g.turn_counter());
+    sink.add_group(9, f * ((g.sta[0] >> 12) & 0xFFFFu));
+    sink.add_group(10, f * (g.sta[0] >> 28));
+    sink.add_group(11, f * (g.stb[0] & 255u));
+    sink.add_group(12, f * ((g.stb[0] >> 16) & 255u));
+    sink.add_group(13, f * ((g.stb[0] >> 8) & 255u));
+    sink.add_group(14, f * (g.sta[0] & 0xFFFu));
+    sink.add_group(15, f * all);
 }
 
 // Warp-vote policies for rollout_steps: the kernels vote across the 32 games of a warp, the host
@@ -716,14 +716,14 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 bool fresh = phase == 2;
                 phase = 0;
                 rounds++;
+                bool over = false;
                 if (!fresh) {
                     count_score<P, POOL>(g);                          // azul.py:307
-                    if (is_end_of_game(g)) {                          // azul.py:308-309
-                        g.misc |= 1u << 12;
-                        tally_finished(g, sink);
-                        fresh = true;
-                    }
+                    over = is_end_of_game(g);                         // azul.py:308-309
+                    if (over) g.misc |= 1u << 12;
                 }
+                tally_finished(g, sink, over);                        // every waiting game calls it: one aggregated add
+                fresh = fresh || over;
                 uint32_t purpose = PURPOSE_REFILL;
                 if (fresh) {                                          // Azul(rules), game_runner.py:79
                     uint32_t first = (uint32_t)first_rule;

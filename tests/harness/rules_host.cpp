@@ -11,6 +11,7 @@ using namespace azb;
 struct HostSink {
     int64_t* c;
     void add(int i, uint32_t v) { c[i] += v; }
+    void add_group(int i, uint32_t v) { c[i] += v; }
 };
 
 template <int P, int POOL>
