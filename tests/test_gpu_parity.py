@@ -316,3 +316,46 @@ def test_rollout_independent_of_launch_shape():
         eng.rollout_random(k)
         assert np.array_equal(eng.export_records().cpu().numpy(), ref), (block, defer)
         assert np.array_equal(eng.counters.cpu().numpy(), cref), (block, defer)
+
+
+def test_maximum_batch_indexing():
+    """2^27 games (9.1 GB of packed state, word offsets beyond 2^31): reset, a few fused steps, spot checks
+    against the oracle at both ends of the id range."""
+    n = 1 << 27
+    free, _ = torch.cuda.mem_get_info()
+    if free < 12 * (1 << 30):
+        pytest.skip("needs 12 GB of free device memory")
+    seed, k = 321, 3
+    eng = engine(n, 2, 1, 0, seed=seed)
+    eng.rollout_random(k)
+    c = eng.read_counters()
+    assert c["steps"] == n * k
+    L = UnpackedLayout(2)
+    for lo in (0, n - 64):
+        ref = O.fresh_records(64, 2, 1, 0, seed, lo)
+        O.rollout_random(ref, 2, 1, 0, seed, lo, k)
+        sub = engine(64, 2, 1, 0, seed=seed, game_id_base=lo, reset=False)
+        sub.state.copy_(eng.state[:, lo:lo + 64])
+        assert np.array_equal(sub.export_records().cpu().numpy(), ref), lo
+    del eng
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("players", [3, 4])
+def test_full_size_three_and_four_players(players):
+    """BASELINE config 3 batch (262,144 games per GPU) for the 3- and 4-player variants: conservation, counters."""
+    n, k = 262144, 300
+    eng = engine(n, players, 1, 0, seed=9)
+    eng.rollout_random(k)
+    c = eng.read_counters()
+    assert c["steps"] == n * k and c["games"] > 0 and c["stuck"] == 0
+    per_game = c["steps"] / c["games"]
+    assert (55 < per_game < 80) if players == 3 else (60 < per_game < 90)      # SURVEY §6: ~63 / ~71 steps per game
+    rec = eng.export_records().cpu().numpy()
+    L = UnpackedLayout(players)
+    total = (rec[:, L.box:L.box + 10].sum(axis=1) + rec[:, 0:30].sum(axis=1) +
+             rec[:, L.pattern_lines:L.pattern_lines + 25 * players].sum(axis=1) +
+             rec[:, L.walls:L.walls + 25 * players].sum(axis=1))
+    ok = (rec[:, L.status] & 8) == 0
+    assert (total[ok] == 100).all() and ok.mean() > 0.99
+    assert ((rec[:, L.current_player] >= 1) & (rec[:, L.current_player] <= players)).all()
