@@ -55,7 +55,7 @@ def load():
     L.azb_round_flags.argtypes = [vp, vp, vp, vp]
     L.azb_opponent_random.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.azb_policy_pack_weights.argtypes = [vp] * 11
-    L.azb_policy_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.azb_policy_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     if L.azb_abi_version() != ABI_VERSION:
         raise AzbError("libazb.so ABI %d != binding ABI %d: rebuild" % (L.azb_abi_version(), ABI_VERSION))
     _lib = L

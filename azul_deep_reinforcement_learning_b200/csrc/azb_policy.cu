@@ -237,6 +237,8 @@ struct PolicyArgs {
     int mode;            // 0 sample from the masked policy, 1 argmax (agent.py action_selection)
     int apply_step;      // 1: also execute Azul.step with the chosen action (Philox refill); 2: and start a fresh game when it ends
     int first_rule;
+    int act_filter;      // 0 every game decides; 1 only games where it is NOT (seat 1 to move with >= 2 legal actions),
+                         // i.e. the opponent's turns of GameRunner.step (game_runner.py:46); 2 only the agent's turns
     unsigned long long* __restrict__ counters;   // rollout counters (apply_step == 2), may be null
     float* __restrict__ logits_out;          // [n][180] raw logits (debug / parity), may be null
     float* __restrict__ value_out;           // [n]
@@ -504,6 +506,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             const float logp = n_valid > 0 ? la - lse : 0.0f;
             const float entropy = n_valid > 0 ? -(gsl / (float)n_valid - lse) : 0.0f;
             uint32_t status = n_valid > 0 ? 0u : (gm.ended() ? (uint32_t)ST_ENDED : (uint32_t)ST_STUCK);
+            const bool agent_turn = gm.current_player() == 1u && n_valid >= 2;
+            const bool acts = A.act_filter == 0 || (A.act_filter == 1 ? !agent_turn : agent_turn);
+            if (!acts) { n_valid = 0; status = 0u; }      // filtered out: reported as AZB_ACTION_SKIP, state untouched
             if (valid) {
                 if (A.mask6_out) {
 #pragma unroll
@@ -604,7 +609,7 @@ int azb_policy_pack_weights(azb_t* h, const float* w1a, const float* b1a, const 
 
 int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int apply_step, uint8_t* action_out,
                     float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
-                    uint8_t* status_out, float* logits_out, unsigned long long* counters, void* stream)
+                    uint8_t* status_out, float* logits_out, unsigned long long* counters, int act_filter, void* stream)
 {
     CHECK_HANDLE(h);
     if (!state || !packed) return azb_fail(AZB_E_INVALID, "null buffer%s");
@@ -615,6 +620,8 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
     A.k0 = (uint32_t)h->seed; A.k1 = (uint32_t)(h->seed >> 32); A.gid0 = (uint32_t)h->game_id_base;
     if (apply_step < 0 || apply_step > 2) return azb_fail(AZB_E_INVALID, "apply_step must be 0, 1 or 2%s");
     A.mode = mode; A.apply_step = apply_step; A.first_rule = h->first_player; A.counters = counters;
+    if (act_filter < 0 || act_filter > 2) return azb_fail(AZB_E_INVALID, "act_filter must be 0, 1 or 2%s");
+    A.act_filter = act_filter;
     A.logits_out = logits_out; A.value_out = value_out; A.action_out = action_out; A.logp_out = logp_out;
     A.entropy_out = entropy_out; A.done_out = done_out; A.status_out = status_out; A.mask6_out = mask6_out;
     const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;

@@ -248,7 +248,8 @@ class PackedPolicy:
         self._keep = t          # keep the staging tensors alive until the pack kernel ran
 
 
-def policy_step(engine, packed, mode=0, apply_step=True, want_logits=False, want_mask=True, auto_reset=False):
+def policy_step(engine, packed, mode=0, apply_step=True, want_logits=False, want_mask=True, auto_reset=False,
+                act_filter=0):
     """K4 in one launch: observation -> MLP (tcgen05) -> masked softmax -> sample / argmax -> [Azul.step].
 
     Returns dict(action uint8, logp, value, entropy float32, done, status uint8[, mask int32 [6,G]][, logits [G,180]])."""
@@ -263,7 +264,7 @@ def policy_step(engine, packed, mode=0, apply_step=True, want_logits=False, want
     _lib.check(engine.lib.azb_policy_step(
         engine._h, _ptr(engine.state), _ptr(packed.buf), int(mode), (2 if auto_reset else 1) if apply_step else 0, _ptr(out["action"]),
         _ptr(out["logp"]), _ptr(out["value"]), _ptr(out["entropy"]), _ptr(mask), _ptr(out["done"]), _ptr(out["status"]),
-        _ptr(logits), _ptr(engine.counters) if auto_reset else None, engine._stream()))
+        _ptr(logits), _ptr(engine.counters) if auto_reset else None, int(act_filter), engine._stream()))
     if want_mask:
         out["mask"] = mask
     if want_logits:

@@ -14,7 +14,10 @@ DEFAULT_RULES = {"first_player": "Random", "tile_pool": "Lid"}      # game_runne
 
 
 class BatchedGameRunner:
-    def __init__(self, n_games, rules=None, seed=0, device=0, game_id_base=0):
+    def __init__(self, n_games, rules=None, seed=0, device=0, game_id_base=0, opponent=None, opponent_mode=0):
+        """``opponent``: None = RandomAgent (game_runner.py:29-30) or a ``PackedPolicy`` = a frozen ``Agent``
+        (scripts/run_batch.py:6-8) whose moves come from the fused policy kernel."""
+        self.opponent, self.opponent_mode = opponent, opponent_mode
         rules = DEFAULT_RULES if rules is None else rules
         pool, first = rules_to_ints(2, rules)
         self.engine = BatchedAzul(n_games, 2, pool, first, seed=seed, device=device, game_id_base=game_id_base, reset=False)
@@ -27,6 +30,8 @@ class BatchedGameRunner:
         """``GameRunner.reset`` (game_runner.py:76-85): fresh games, the opponent plays until seat 1 is to move."""
         self.engine.reset()
         self.player_score.zero_()
+        if self.opponent is not None:                 # a fresh board always offers seat 1 >= 2 actions, so the
+            self._opponent_policy_moves()             # ":46" and ":84" loop conditions coincide here
         out = self.engine.opponent_random(self.player_score, require_two=False)
         self.player_score.zero_()                     # game_runner.py:81: the score baseline restarts at 0
         self.mask = out["mask"]
@@ -39,7 +44,19 @@ class BatchedGameRunner:
     def get_valid_moves(self):
         return mask_to_bool(self.mask)
 
+    def _opponent_policy_moves(self, max_rounds=16):
+        """``while (current_player != 1 or #valid < 2) and not end: opponent_move()`` (game_runner.py:46-47) with an
+        Agent opponent: each launch lets every game that is still in the opponent's hands take one policy decision
+        (``act_filter = 1``); typically one or two launches per agent decision."""
+        for _ in range(max_rounds):
+            out = policy_step(self.engine, self.opponent, mode=self.opponent_mode, apply_step=True, want_mask=False,
+                              act_filter=1)
+            if not bool((out["action"] != 255).any()):
+                return
+
     def _after_agent_move(self):
+        if self.opponent is not None:
+            self._opponent_policy_moves()
         out = self.engine.opponent_random(self.player_score, require_two=True)
         self.mask = out["mask"]
         return out

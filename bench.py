@@ -378,7 +378,7 @@ def run_policy(args):
                                  ctypes.c_void_p(out["action"].data_ptr()), ctypes.c_void_p(out["logp"].data_ptr()),
                                  ctypes.c_void_p(out["value"].data_ptr()), ctypes.c_void_p(out["entropy"].data_ptr()),
                                  ctypes.c_void_p(out["mask"].data_ptr()), ctypes.c_void_p(out["done"].data_ptr()),
-                                 ctypes.c_void_p(out["status"].data_ptr()), None, ctypes.c_void_p(eng.counters.data_ptr()),
+                                 ctypes.c_void_p(out["status"].data_ptr()), None, ctypes.c_void_p(eng.counters.data_ptr()), 0,
                                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         assert rc == 0
 

@@ -154,6 +154,9 @@ int azb_opponent_random(azb_t* h, uint32_t* state, int require_two, int16_t* pla
  *   and, when apply_step != 0, Azul.step with that action (Philox refill)   azul.py:296-313;
  *   apply_step == 2 additionally starts a fresh game in slots whose game ended (self-play rollouts) and
  *   accumulates the rollout counters (device uint64[AZB_N_COUNTERS], optional).
+ * act_filter selects which games decide in this launch: 0 all; 1 only the opponent's turns of GameRunner.step
+ * (not "seat 1 to move with >= 2 legal actions", game_runner.py:46: a frozen Agent as opponent_move); 2 only the
+ * agent's turns.  Games filtered out report AZB_ACTION_SKIP and are left untouched.
  * Outputs (device, each optional / NULL): action uint8 [G] (AZB_ACTION_SKIP when no action is legal),
  * logp, value, entropy float [G], mask6 uint32 [6][G] (the mask the decision used), done / status uint8 [G]
  * (AZB_ST_ENDED / AZB_ST_STUCK instead of model.py:33-34 IllegalMask), logits float [G][180] (unmasked). */
@@ -163,7 +166,7 @@ int azb_policy_pack_weights(azb_t* h, const float* w1a, const float* b1a, const 
                             void* stream);
 int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int apply_step, uint8_t* action_out,
                     float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
-                    uint8_t* status_out, float* logits_out, unsigned long long* counters, void* stream);
+                    uint8_t* status_out, float* logits_out, unsigned long long* counters, int act_filter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -81,3 +81,31 @@ def test_selfplay_training_runs_and_learns_something():
     assert all(25 * 512 < h["transitions"] < 80 * 512 for h in hist)            # ~30-36 decisions per game
     assert any(not torch.equal(a, b) for a, b in zip(before, tr.net.parameters()))
     assert 0 <= hist[0]["win_percent"] <= 1 and 3 <= hist[0]["rounds"] <= 12
+
+
+def test_agent_opponent_in_batched_runner():
+    """GameRunner(opponent=Agent) (scripts/run_batch.py:6-8): the frozen policy plays seat 2 and seat 1's forced moves."""
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul, PackedPolicy, mask_to_bool
+    from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner, run_episodes
+    torch.manual_seed(3)
+    net, opp = ActorCritic(136, 180), ActorCritic(136, 180)
+    n = 1024
+    helper = BatchedAzul(n, 2, 1, 0, seed=5, reset=False)
+    gr = BatchedGameRunner(n, seed=5, opponent=PackedPolicy(helper, opp))
+    packed = PackedPolicy(gr.engine, net)
+    L = UnpackedLayout(2)
+    for t in range(30):
+        rec = gr.engine.export_records().cpu().numpy()
+        nvalid = mask_to_bool(gr.mask).sum(dim=1).cpu().numpy()
+        live = rec[:, L.end_of_game] == 0
+        assert ((rec[live, L.current_player] == 1) & (nvalid[live] >= 2)).all(), t      # invariant of GameRunner.step
+        before_steps = rec[:, L.total_steps].copy()
+        out = gr.step_policy(packed)
+        after = gr.engine.export_records().cpu().numpy()
+        moved = after[:, L.total_steps] - before_steps
+        assert (moved[live] >= 1).all() and (moved[~live] == 0).all()
+        assert int((out["status"] & 1).max()) == 0
+    # a whole batch of episodes against the Agent opponent terminates and produces rewards
+    batch = run_episodes(gr, packed, max_decisions=200)
+    assert batch["unfinished"] < n // 20 and float(batch["reward"].abs().sum()) > 0
