@@ -359,3 +359,32 @@ def test_full_size_three_and_four_players(players):
     ok = (rec[:, L.status] & 8) == 0
     assert (total[ok] == 100).all() and ok.mean() > 0.99
     assert ((rec[:, L.current_player] >= 1) & (rec[:, L.current_player] <= players)).all()
+
+
+def test_replay_cli_and_json_io(tmp_path):
+    """The trace replay tool and the batch JSON import/export (azul.py:90-117 schema) of the product package."""
+    import json
+    from azul_deep_reinforcement_learning_b200 import io as azio
+    from azul_deep_reinforcement_learning_b200.replay import replay_trace
+    tr = load_trace(2, "lid")
+    rep = replay_trace(tr)
+    assert rep["ok"] and rep["games"] == 64, rep["mismatches"][:3]
+    tr["actions"] = tr["actions"].copy()
+    tr["actions"][5] = (int(tr["actions"][5]) + 1) % 180          # a corrupted recording must be detected
+    assert not replay_trace(tr)["ok"]
+    kat = load_kat()
+    recs = kat["fixture_records"].astype(np.int32)
+    paths = []
+    for i, r in enumerate(recs):
+        p = tmp_path / ("b%d.json" % i)
+        p.write_text(json.dumps(azio.json_dict_from_record(r)))
+        paths.append(str(p))
+    eng = engine(len(recs), 2, 0, 1, reset=False)
+    assert bool(azio.import_json_files(eng, paths).all())
+    L = UnpackedLayout(2)
+    got = eng.export_records().cpu().numpy()
+    assert np.array_equal(got[:, :L.end_of_game], recs[:, :L.end_of_game])      # the 10 JSON keys round-trip
+    out = [str(tmp_path / ("o%d.json" % i)) for i in range(len(recs))]
+    azio.export_json_files(eng, out)
+    for a, b in zip(paths, out):
+        assert json.load(open(a)) == json.load(open(b))
