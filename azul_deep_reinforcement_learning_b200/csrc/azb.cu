@@ -68,58 +68,19 @@ __global__ void k_legal_mask(const uint32_t* __restrict__ s, int64_t n, uint32_t
     store_mask(mask6, n, g, m);
 }
 
-// K1 (+K2, K5): one Azul.step per game.
-// The move itself is cheap and uniform; the end-of-round work (count_score, game-over test, new_round) hits
-// ~10 % of the games of a launch.  Running it where it falls leaves ~3 of 32 lanes active, so the block
-// compacts those games through shared memory and a few dense warps finish them; global memory still sees
-// only the coalesced structure-of-arrays loads and stores of the owning threads.
-template <int P>
-__device__ __forceinline__ void stage_put(uint32_t* stage, int cap, int slot, const Game<P>& g)
-{
-    stage[0 * cap + slot] = g.pl0; stage[1 * cap + slot] = g.pl1; stage[2 * cap + slot] = g.pl2;
-    stage[3 * cap + slot] = g.misc; stage[4 * cap + slot] = g.box; stage[5 * cap + slot] = g.lid;
-    stage[6 * cap + slot] = g.steps;
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-        stage[(7 + 5 * p) * cap + slot] = g.pat[p];  stage[(8 + 5 * p) * cap + slot] = g.wall[p];
-        stage[(9 + 5 * p) * cap + slot] = g.scf[p];  stage[(10 + 5 * p) * cap + slot] = g.sta[p];
-        stage[(11 + 5 * p) * cap + slot] = g.stb[p];
-    }
-}
-template <int P>
-__device__ __forceinline__ void stage_get(const uint32_t* stage, int cap, int slot, Game<P>& g)
-{
-    g.pl0 = stage[0 * cap + slot]; g.pl1 = stage[1 * cap + slot]; g.pl2 = stage[2 * cap + slot];
-    g.misc = stage[3 * cap + slot]; g.box = stage[4 * cap + slot]; g.lid = stage[5 * cap + slot];
-    g.steps = stage[6 * cap + slot];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-        g.pat[p] = stage[(7 + 5 * p) * cap + slot];  g.wall[p] = stage[(8 + 5 * p) * cap + slot];
-        g.scf[p] = stage[(9 + 5 * p) * cap + slot];  g.sta[p] = stage[(10 + 5 * p) * cap + slot];
-        g.stb[p] = stage[(11 + 5 * p) * cap + slot];
-    }
-}
-
+// K1 (+K2, K5): one Azul.step per game
 template <int P, int POOL>
 __global__ void k_step(Launch L, const uint8_t* __restrict__ action, const int8_t* __restrict__ draws,
                        uint32_t* __restrict__ mask6_out, int16_t* __restrict__ preview_out,
                        uint8_t* __restrict__ done_out, uint8_t* __restrict__ status_out)
 {
-    extern __shared__ uint32_t stage[];                 // [W + 1][blockDim.x]: packed words + owner thread
-    __shared__ int n_round_over;
-    constexpr int W = Game<P>::WORDS;
-    const int cap = blockDim.x;
-    if (threadIdx.x == 0) n_round_over = 0;
-    __syncthreads();
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool valid = g < L.n;
-    const int64_t gl = valid ? g : L.n - 1;
+    if (g >= L.n) return;
     Game<P> gm;
-    gm.load(L.state, L.n, gl);
-    const uint32_t a = valid ? action[gl] : (uint32_t)AZB_ACTION_SKIP;
+    gm.load(L.state, L.n, g);
+    const uint32_t a = action[g];
     uint32_t status = 0;
     uint32_t m[6];
-    bool moved = false, round_over = false;
     if (a != AZB_ACTION_SKIP) {
         if (gm.ended()) {
             status = ST_ENDED;                                        // azul.py:298-299
@@ -128,42 +89,22 @@ __global__ void k_step(Launch L, const uint8_t* __restrict__ action, const int8_
             if (!action_is_legal(m, a)) {
                 status = ST_ILLEGAL;                                  // azul.py:301-302
             } else {
-                apply_move<P, POOL>(gm, a);                           // azul.py:304
-                gm.steps += 1u;
-                moved = true;
-                round_over = is_end_of_round(gm);                     // azul.py:306
-                if (!round_over) next_player(gm);                     // azul.py:313
+                const Philox rng{L.k0, L.k1};
+                const uint32_t gid = L.gid0 + (uint32_t)g;
+                if (draws) {
+                    const int8_t* d = draws + 20 * g;
+                    advance<P, POOL>(gm, a, [&](Game<P>& gg) {
+                        new_round_injected<P, POOL>(gg, [&](int k) { return (int)d[k]; });
+                    });
+                } else {
+                    advance<P, POOL>(gm, a, [&](Game<P>& gg) {
+                        new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL);
+                    });
+                }
+                gm.store(L.state, L.n, g);
             }
         }
     }
-    int slot = -1;
-    if (round_over) {
-        slot = atomicAdd(&n_round_over, 1);
-        stage_put<P>(stage, cap, slot, gm);
-        stage[W * cap + slot] = threadIdx.x;
-    }
-    __syncthreads();
-    const int todo = n_round_over;
-    for (int i = threadIdx.x; i < todo; i += blockDim.x) {            // dense: the first `todo` threads of the block
-        Game<P> h;
-        stage_get<P>(stage, cap, i, h);
-        const int64_t hg = blockIdx.x * (int64_t)blockDim.x + stage[W * cap + i];
-        count_score<P, POOL>(h);                                      // azul.py:307
-        if (is_end_of_game(h)) {                                      // azul.py:308-309
-            h.misc |= 1u << 12;
-        } else if (draws) {                                           // azul.py:311
-            const int8_t* d = draws + 20 * hg;
-            new_round_injected<P, POOL>(h, [&](int k) { return (int)d[k]; });
-        } else {
-            const Philox rng{L.k0, L.k1};
-            new_round_philox<P, POOL>(h, rng, L.gid0 + (uint32_t)hg, PURPOSE_REFILL);
-        }
-        stage_put<P>(stage, cap, i, h);
-    }
-    __syncthreads();
-    if (round_over) stage_get<P>(stage, cap, slot, gm);
-    if (!valid) return;
-    if (moved) gm.store(L.state, L.n, g);
     if (mask6_out || status_out) {
         legal_mask(gm, m);
         if (!gm.ended() && (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u && gm.current_player() != 0u)
@@ -482,9 +423,7 @@ int azb_step(azb_t* h, uint32_t* state, const uint8_t* action, const int8_t* dra
     CHECK_HANDLE(h);
     if (!state || !action) return azb_fail(AZB_E_INVALID, "null buffer%s");
     const Launch L = make_launch(h, state);
-    const size_t stage_bytes = (size_t)(azb_state_words(h->players) + 1) * h->block_threads * sizeof(uint32_t);
-    if (stage_bytes > 48 * 1024) return azb_fail(AZB_E_INVALID, "block threads too large for the step kernel's staging buffer%s");
-    DISPATCH_PP(h, (k_step<P, POOL><<<grid_of(h), h->block_threads, stage_bytes, (cudaStream_t)stream>>>(
+    DISPATCH_PP(h, (k_step<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
                        L, action, draws20, mask6_out, preview_out, done_out, status_out)));
     CHECK_LAUNCH();
     return 0;
