@@ -137,10 +137,43 @@ struct BlockSink {
     }
 };
 
+// Action words of a whole round, computed by the full warp during the end-of-round pass (when all of its games
+// are at the same point) and parked in shared memory: ROUND_WORDS words per game, [word][thread] so that a warp
+// reads 32 consecutive banks.  A round that outlasts them falls back to computing a block in place.
+constexpr int ROUND_WORDS = 20;
+struct RoundWords {
+    uint32_t* base;          // &buf[threadIdx.x]
+    uint32_t stride;         // blockDim.x
+    uint32_t first_block;
+    uint32_t w[4];
+    uint32_t block;
+    __device__ __forceinline__ void prefetch(const Philox& rng, uint32_t gid, uint32_t T)
+    {
+        first_block = T >> 2;
+#pragma unroll 1
+        for (uint32_t j = 0; j < ROUND_WORDS / 4; j++) {
+            uint32_t r[4];
+            rng(gid, first_block + j, PURPOSE_ACTION, 0u, r);
+            base[(4 * j + 0) * stride] = r[0]; base[(4 * j + 1) * stride] = r[1];
+            base[(4 * j + 2) * stride] = r[2]; base[(4 * j + 3) * stride] = r[3];
+        }
+        block = 0xFFFFFFFFu;
+    }
+    __device__ __forceinline__ uint32_t get(const Philox& rng, uint32_t gid, uint32_t T)
+    {
+        const uint32_t idx = T - 4u * first_block;
+        if (idx < (uint32_t)ROUND_WORDS) return base[idx * stride];
+        if (block != (T >> 2)) { block = T >> 2; rng(gid, block, PURPOSE_ACTION, 0u, w); }
+        const uint32_t i = T & 3u;
+        return i == 0u ? w[0] : i == 1u ? w[1] : i == 2u ? w[2] : w[3];
+    }
+};
+
 template <int P, int POOL>
 __global__ void k_rollout_random(Launch L, int k_steps, int defer, uint32_t* __restrict__ mask6_out,
                                  unsigned long long* __restrict__ counters)
 {
+    extern __shared__ uint32_t round_words[];          // [ROUND_WORDS][blockDim.x]
     __shared__ unsigned long long cnt[AZB_N_COUNTERS];
     if (threadIdx.x < AZB_N_COUNTERS) cnt[threadIdx.x] = 0ull;
     __syncthreads();
@@ -151,7 +184,10 @@ __global__ void k_rollout_random(Launch L, int k_steps, int defer, uint32_t* __r
     gm.load(L.state, L.n, gl);
     const Philox rng{L.k0, L.k1};
     BlockSink sink{cnt};
-    rollout_steps<P, POOL>(gm, rng, L.gid0 + (uint32_t)gl, L.first_rule, k_steps, sink, WarpLanes{}, valid, defer);
+    RoundWords words;
+    words.base = round_words + threadIdx.x;
+    words.stride = blockDim.x;
+    rollout_steps<P, POOL>(gm, rng, L.gid0 + (uint32_t)gl, L.first_rule, k_steps, sink, WarpLanes{}, valid, defer, words);
     if (valid) {
         gm.store(L.state, L.n, g);
         if (mask6_out) {
@@ -436,7 +472,9 @@ int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_o
     if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     if (k_steps < 0) return azb_fail(AZB_E_INVALID, "k_steps < 0%s");
     const Launch L = make_launch(h, state);
-    DISPATCH_PP(h, (k_rollout_random<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
+    const size_t words_bytes = (size_t)ROUND_WORDS * h->block_threads * sizeof(uint32_t);
+    if (words_bytes > 48 * 1024) return azb_fail(AZB_E_INVALID, "block threads too large for the rollout kernel's word buffer%s");
+    DISPATCH_PP(h, (k_rollout_random<P, POOL><<<grid_of(h), h->block_threads, words_bytes, (cudaStream_t)stream>>>(
                        L, k_steps, h->defer, mask6_out, counters)));
     CHECK_LAUNCH();
     return 0;

@@ -357,26 +357,34 @@ AZB_HD void new_round_header(Game<P>& g)
     g.pl0 = g.pl1 = g.pl2 = 0u;                                   // :73
 }
 
+// Lid pool: the five box counts unpacked into registers for the duration of a refill
+struct BoxRegs {
+    uint32_t b0, b1, b2, b3, b4, total;
+    AZB_M void unpack(uint32_t w)
+    {
+        b0 = w & 63u; b1 = (w >> 6) & 63u; b2 = (w >> 12) & 63u; b3 = (w >> 18) & 63u; b4 = (w >> 24) & 63u;
+        total = b0 + b1 + b2 + b3 + b4;
+    }
+    AZB_M uint32_t pack() const { return b0 | (b1 << 6) | (b2 << 12) | (b3 << 18) | (b4 << 24); }
+};
+
 // Lid pool, one draw (azul.py:79-89): pour the lid into an empty box, pick colour c when the
 // point r in [0,total) falls in its cumulative count.  Returns colour or -1 when no tile is left.
 template <int P>
-AZB_HD int lid_draw(Game<P>& g, uint32_t& x)
+AZB_HD int lid_draw(Game<P>& g, BoxRegs& B, uint32_t& x)
 {
-    uint32_t b0 = g.box & 63u, b1 = (g.box >> 6) & 63u, b2 = (g.box >> 12) & 63u, b3 = (g.box >> 18) & 63u,
-             b4 = (g.box >> 24) & 63u;
-    uint32_t total = b0 + b1 + b2 + b3 + b4;
-    if (total == 0u) {                                            // :81-83
-        g.box = g.lid; g.lid = 0u;
-        b0 = g.box & 63u; b1 = (g.box >> 6) & 63u; b2 = (g.box >> 12) & 63u; b3 = (g.box >> 18) & 63u;
-        b4 = (g.box >> 24) & 63u;
-        total = b0 + b1 + b2 + b3 + b4;
-        if (total == 0u) { g.add_status(ST_BAG_EMPTY); return -1; }   // :86 TODO in the reference
+    if (B.total == 0u) {                                          // :81-83
+        B.unpack(g.lid);
+        g.lid = 0u;
+        if (B.total == 0u) { g.add_status(ST_BAG_EMPTY); return -1; }   // :86 TODO in the reference
     }
-    const uint32_t r = mulhi(x, total);
-    x *= total;
-    const uint32_t e1 = b0 + b1, e2 = e1 + b2, e3 = e2 + b3;
-    const int c = (int)(r >= b0) + (int)(r >= e1) + (int)(r >= e2) + (int)(r >= e3);
-    g.box -= 1u << (6 * c);                                       // :89
+    const uint32_t r = mulhi(x, B.total);
+    x *= B.total;
+    const uint32_t e1 = B.b0 + B.b1, e2 = e1 + B.b2, e3 = e2 + B.b3;
+    const int c = (int)(r >= B.b0) + (int)(r >= e1) + (int)(r >= e2) + (int)(r >= e3);
+    B.b0 -= c == 0 ? 1u : 0u; B.b1 -= c == 1 ? 1u : 0u; B.b2 -= c == 2 ? 1u : 0u;
+    B.b3 -= c == 3 ? 1u : 0u; B.b4 -= c == 4 ? 1u : 0u;           // :89
+    B.total -= 1u;
     return c;
 }
 
@@ -389,6 +397,8 @@ AZB_HD void new_round_philox(Game<P>& g, const Philox& rng, uint32_t gid, uint32
 {
     new_round_header(g);
     constexpr uint32_t CALLS = POOL == POOL_LID ? 3u : 2u;
+    BoxRegs B;
+    if (POOL == POOL_LID) B.unpack(g.box);
     AZB_ROLLED
     for (uint32_t j = 0; j < CALLS; j++) {
         uint32_t w[4];
@@ -414,12 +424,13 @@ AZB_HD void new_round_philox(Game<P>& g, const Philox& rng, uint32_t gid, uint32
                 const uint32_t d = 2u * j + (q >> 1) + 1u;
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
-                    const int c = lid_draw(g, x);
+                    const int c = lid_draw(g, B, x);
                     if (c >= 0) plane_inc(g.pl0, g.pl1, g.pl2, d + 6u * (uint32_t)c);
                 }
             }
         }
     }
+    if (POOL == POOL_LID) g.box = B.pack();
 }
 
 // azul.py:64-89 with the 20 colours injected (replay of recorded draws; -1 leaves a slot empty)
@@ -663,6 +674,24 @@ AZB_HD void tally_finished(const Game<P>& g, Sink& sink, bool fin = true)
     sink.add_group(15, f * all);
 }
 
+// Where the random agent's action words come from.  The word of env step T of a slot is always
+// Philox(gid, T >> 2, ACTION, 0)[T & 3]; the policies differ in WHEN the Philox blocks are computed.
+// InlineWords computes a block when a game first needs it (every fourth step of each game, at a
+// different time for every lane of a warp).
+struct InlineWords {
+    uint32_t w[4];
+    uint32_t block;
+    bool have;
+    AZB_M InlineWords() : block(0u), have(false) { w[0] = w[1] = w[2] = w[3] = 0u; }
+    AZB_M void prefetch(const Philox&, uint32_t, uint32_t) {}
+    AZB_M uint32_t get(const Philox& rng, uint32_t gid, uint32_t T)
+    {
+        if (!have || block != (T >> 2)) { block = T >> 2; rng(gid, block, PURPOSE_ACTION, 0u, w); have = true; }
+        const uint32_t i = T & 3u;
+        return i == 0u ? w[0] : i == 1u ? w[1] : i == 2u ? w[2] : w[3];
+    }
+};
+
 // Warp-vote policies for rollout_steps: the kernels vote across the 32 games of a warp, the host
 // harness (one game at a time) votes with itself.
 struct SingleLane {
@@ -681,16 +710,15 @@ struct WarpLanes {
 //          warp only once `defer` of its games are waiting for it (or nothing else can move).
 // A game that finished its round simply waits for the next heavy pass; its trajectory, and so every
 // result, is independent of `defer` and of which games share its warp.
-template <int P, int POOL, typename Sink, typename Vote>
+template <int P, int POOL, typename Sink, typename Vote, typename Words>
 AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first_rule, int k_steps, Sink& sink,
-                          const Vote vote, bool valid, int defer)
+                          const Vote vote, bool valid, int defer, Words& words)
 {
-    uint32_t aw[4] = {0u, 0u, 0u, 0u};
-    bool have_words = false;
     uint32_t rounds = 0;
     int remaining = valid ? k_steps : 0;
     // 0 playing, 1 round over: waits for score + refill, 2 waits for a fresh game (stuck / ended on entry)
     int phase = (remaining > 0 && g.ended()) ? 2 : 0;
+    words.prefetch(rng, gid, g.steps);
     for (;;) {
         if (remaining > 0 && phase == 0) {
             uint32_t m[6];
@@ -699,10 +727,7 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 sink.add(6, 1);                                       // stuck round: abort the game
                 phase = 2;
             } else {
-                if (!have_words || (g.steps & 3u) == 0u) { rng(gid, g.steps >> 2, PURPOSE_ACTION, 0u, aw); have_words = true; }
-                const uint32_t idx = g.steps & 3u;
-                const uint32_t word = idx == 0u ? aw[0] : idx == 1u ? aw[1] : idx == 2u ? aw[2] : aw[3];
-                apply_move<P, POOL>(g, random_action(m, word));       // azul.py:304
+                apply_move<P, POOL>(g, random_action(m, words.get(rng, gid, g.steps)));   // azul.py:304
                 g.steps += 1u;
                 remaining--;
                 if (is_end_of_round(g)) phase = 1;                    // azul.py:306
@@ -738,6 +763,7 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 const uint32_t bag_before = g.status() & ST_BAG_EMPTY;
                 new_round_philox<P, POOL>(g, rng, gid, purpose);      // azul.py:311 / game_runner.py:80
                 if (!bag_before && (g.status() & ST_BAG_EMPTY)) sink.add(7, 1);
+                words.prefetch(rng, gid, g.steps);                    // the whole warp is here: words for the next round
             }
         } else if (n_movable == 0) {
             break;

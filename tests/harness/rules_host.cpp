@@ -59,7 +59,8 @@ static void run_rollout(int32_t* recs, int64_t n, int first_rule, uint64_t seed,
         int32_t* rec = recs + i * U;
         Game<P> g;
         import_record<P>(g, [&](int j) { return rec[j]; });
-        rollout_steps<P, POOL>(g, rng, gid0 + (uint32_t)i, first_rule, k, sink, SingleLane{}, true, 1);
+        InlineWords words;
+        rollout_steps<P, POOL>(g, rng, gid0 + (uint32_t)i, first_rule, k, sink, SingleLane{}, true, 1, words);
         export_record<P>(g, [&](int j, int32_t v) { rec[j] = v; });
     }
 }
