@@ -404,7 +404,7 @@ int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_p
     AZB_CUDA(cudaSetDevice(device));
     azb_t* h = new azb_handle();
     h->device = device; h->n_games = n_games; h->players = players; h->tile_pool = tile_pool;
-    h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->defer = 32;
+    h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->block_threads_set = 0; h->defer = 32;
     AZB_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     *out = h;
     return 0;
@@ -419,6 +419,7 @@ int azb_destroy(azb_t* h)
 int azb_set_block_threads(azb_t* h, int threads)
 {
     if (!h) return azb_fail(AZB_E_INVALID, "null handle%s");
+    h->block_threads_set = threads != 0;
     if (threads == 0) threads = 128;
     if (threads < 32 || threads > 1024 || threads % 32) return azb_fail(AZB_E_INVALID, "block threads must be a multiple of 32 in 32..1024%s");
     h->block_threads = threads;
@@ -472,9 +473,20 @@ int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_o
     if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     if (k_steps < 0) return azb_fail(AZB_E_INVALID, "k_steps < 0%s");
     const Launch L = make_launch(h, state);
-    const size_t words_bytes = (size_t)ROUND_WORDS * h->block_threads * sizeof(uint32_t);
+    // Grid sizing: the kernel is issue-bound and every game runs for the whole launch, so the slowest SM sets the time.
+    // Unless the caller fixed the block size, give every SM the same number of equally sized blocks:
+    // k = ceil(n / (SMs * 512)) blocks per SM of ceil(n / (SMs * k)) threads (rounded up to a warp).
+    int threads = h->block_threads;
+    if (!h->block_threads_set) {
+        const int64_t per_sm = (h->n_games + h->sm_count - 1) / h->sm_count;
+        const int64_t k = (per_sm + 511) / 512;
+        threads = (int)(((per_sm + k - 1) / k + 31) / 32 * 32);
+        threads = threads < 64 ? 64 : threads > 512 ? 512 : threads;
+    }
+    const size_t words_bytes = (size_t)ROUND_WORDS * threads * sizeof(uint32_t);
     if (words_bytes > 48 * 1024) return azb_fail(AZB_E_INVALID, "block threads too large for the rollout kernel's word buffer%s");
-    DISPATCH_PP(h, (k_rollout_random<P, POOL><<<grid_of(h), h->block_threads, words_bytes, (cudaStream_t)stream>>>(
+    const dim3 grid((unsigned)((h->n_games + threads - 1) / threads));
+    DISPATCH_PP(h, (k_rollout_random<P, POOL><<<grid, threads, words_bytes, (cudaStream_t)stream>>>(
                        L, k_steps, h->defer, mask6_out, counters)));
     CHECK_LAUNCH();
     return 0;

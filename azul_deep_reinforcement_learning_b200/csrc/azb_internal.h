@@ -15,6 +15,7 @@ struct azb_handle {
     uint64_t seed;
     uint64_t game_id_base;
     int block_threads;
+    int block_threads_set; // azb_set_block_threads was called: no automatic choice for the rollout kernel
     int defer;             // rollout: games of a warp that must be waiting before the end-of-round pass runs
     int sm_count;
 };

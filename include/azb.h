@@ -74,7 +74,8 @@ const char* azb_last_error(void);
 int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_pool, int first_player,
                uint64_t seed, uint64_t game_id_base);
 int azb_destroy(azb_t* h);
-/* threads per block for the kernels of this handle (multiple of 32, <= 1024); 0 = default */
+/* threads per block for the kernels of this handle (multiple of 32, <= 1024); 0 = default (128, and an
+ * SM-balanced choice for azb_rollout_random: equal blocks per SM) */
 int azb_set_block_threads(azb_t* h, int threads);
 /* azb_rollout_random tuning: how many of a warp's 32 games must have reached the end of their round
  * before the warp runs the scoring / refill pass for them (1..32, 0 = default 32).  Results do not
