@@ -55,6 +55,7 @@ constexpr int SMEM_BYTES = OFF_BAR + 32;
 static_assert(SMEM_BYTES <= 232448, "policy kernel exceeds the 227 KB shared memory of an SM");
 
 constexpr int V_B1 = 0, V_W2C = N1, V_B2A = N1 + 192, V_B2C = N1 + 192 + N2;
+static_assert(OFF_VEC % 16 == 0 && (V_B1 + HID) % 4 == 0 && V_W2C % 4 == 0 && V_B2A % 4 == 0, "vectors must allow 128-bit loads");
 
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -223,6 +224,17 @@ __device__ __forceinline__ void linear_mask(const uint32_t m[6], uint32_t lin[6]
     lin[5] = m[5] >> 10;
 }
 
+// 16 consecutive fp32 constants (bias / weight vectors in shared memory; 16-byte aligned by construction)
+__device__ __forceinline__ void ld16f(const float* p, float (&b)[16])
+{
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float4 t = q[i];
+        b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+    }
+}
+
 __device__ __forceinline__ uint32_t pick6(const uint32_t (&a)[6], int i)
 {
     return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : i == 3 ? a[3] : i == 4 ? a[4] : a[5];
@@ -350,8 +362,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         // ---- epilogue 1: actor hidden -> relu -> bf16 -> shared memory (layer-2 A operand, aliases the obs tile) ----
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
-            float v[16];
+            float v[16], bb[16];
             tmem_ld16(tmem_row + c0, v);
+            ld16f(vec + V_B1 + c0, bb);
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 uint4 o;
@@ -359,8 +372,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int j = c0 + 8 * q + 2 * e;                  // hidden unit (even, so j and j + 1 are both < or >= 180)
-                    ow[e] = j < HID ? pack_bf16(fmaxf(v[8 * q + 2 * e] + vec[V_B1 + j], 0.0f),
-                                                fmaxf(v[8 * q + 2 * e + 1] + vec[V_B1 + j + 1], 0.0f)) : 0u;
+                    ow[e] = j < HID ? pack_bf16(fmaxf(v[8 * q + 2 * e] + bb[8 * q + 2 * e], 0.0f),
+                                                fmaxf(v[8 * q + 2 * e + 1] + bb[8 * q + 2 * e + 1], 0.0f)) : 0u;
                 }
                 *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = o;
             }
@@ -369,11 +382,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         float value_p = 0.0f;
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {      // critic hidden unit u lives in TMEM column 180 + u
-            float v[16];
+            float v[16], bb[16], ww[16];
             tmem_ld16(tmem_row + HID + c0, v);
+            ld16f(vec + V_B1 + HID + c0, bb);
+            ld16f(vec + V_W2C + c0, ww);
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                if (c0 + i < HID) value_p = fmaf(fmaxf(v[i] + vec[V_B1 + HID + c0 + i], 0.0f), vec[V_W2C + c0 + i], value_p);
+                if (c0 + i < HID) value_p = fmaf(fmaxf(v[i] + bb[i], 0.0f), ww[i], value_p);
         }
         fence_async_smem();
         tc_fence_before();
@@ -399,27 +414,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         legal_mask(gm, m);
         linear_mask(m, lin);
         const uint64_t mybits = mask_window(lin, col0);
+        // online softmax statistics over this part's legal logits, one 16-column chunk at a time and without
+        // per-column branches (32 different games share a warp): chunk maximum first, one rescale, then the sum
         float mx = -INFINITY, se = 0.0f, sl = 0.0f;
         int amax = 0;
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
-            float v[16];
+            float v[16], bb[16];
             tmem_ld16(tmem_row + c0, v);
+            ld16f(vec + V_B2A + c0, bb);
             const uint32_t bits = (uint32_t)(mybits >> (c0 - col0)) & 0xFFFFu;
             if (A.logits_out && valid) {
 #pragma unroll
                 for (int i = 0; i < 16; i++)
-                    if (c0 + i < ACT) A.logits_out[g * ACT + c0 + i] = v[i] + vec[V_B2A + c0 + i];
+                    if (c0 + i < ACT) A.logits_out[g * ACT + c0 + i] = v[i] + bb[i];
             }
+            float cm = -INFINITY;
+            int ci = 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                if ((bits >> i) & 1u) {
-                    const float l = v[i] + vec[V_B2A + c0 + i];
-                    sl += l;
-                    if (l > mx) { se = se * __expf(mx - l) + 1.0f; mx = l; amax = c0 + i; }
-                    else se += __expf(l - mx);
-                }
+                const bool legal = (bits >> i) & 1u;
+                const float l = v[i] + bb[i];
+                v[i] = legal ? l : -INFINITY;
+                sl += legal ? l : 0.0f;
+                if (v[i] > cm) { cm = v[i]; ci = i; }
             }
+            amax = cm > mx ? c0 + ci : amax;
+            const float nm = fmaxf(mx, cm);
+            const float ms = nm == -INFINITY ? 0.0f : nm;          // no legal action so far: every term below is exp(-inf) = 0
+            se *= __expf(mx - ms);
+#pragma unroll
+            for (int i = 0; i < 16; i++) se += __expf(v[i] - ms);
+            mx = nm;
         }
         {
             RowPart rp;
@@ -476,13 +502,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             float chosen_l = 0.0f;
 #pragma unroll 1
             for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
-                float v[16];
+                float v[16], bb[16];
                 tmem_ld16(tmem_row + c0, v);
+                ld16f(vec + V_B2A + c0, bb);
                 const uint32_t bits = (uint32_t)(mybits >> (c0 - col0)) & 0xFFFFu;
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     if (mine && ((bits >> i) & 1u) && !found) {
-                        const float l = v[i] + vec[V_B2A + c0 + i];
+                        const float l = v[i] + bb[i];
                         cum += __expf(l - gmx);
                         chosen = c0 + i;                     // rounding may leave cum <= target: then the part's last legal action
                         chosen_l = l;
