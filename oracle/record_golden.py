@@ -15,6 +15,9 @@ What is recorded (SURVEY.md §8c "trace format"):
   ``N_FULL`` games -- the pre-step 180-bit legal mask and the full post-step state as an unpacked
   record (``azul_deep_reinforcement_learning_b200/layout.py``).  The remaining games keep only
   draws, actions, the final record and a SHA-256 over the (mask, post-state) stream.
+* ``fuzz.npz`` -- 1,500 random (not necessarily reachable) representable boards for P in {2,3,4} x both pools with
+  the reference's legal mask, its ``count_score`` result (dense walls: multi-bonus and long-run cases) and one
+  random legal ``step`` including the draws it consumed.
 * ``kat.npz`` -- the reference's own board fixtures (``tests/resources/*.json``) as unpacked
   records and the op sequences of ``tests/test_azul.py:123-331`` / ``tests/test_game_runner.py:36-69,
   89-114`` replayed on the reference, with the record after every op.
@@ -293,11 +296,96 @@ def record_kats(ref, out_dir):
         len(FIXTURES), len(names), len(ops_all), os.path.getsize(path) / 1024))
 
 
+def random_board(ref, rng, players, pool):
+    """A random (not necessarily reachable) but representable board: one colour per pattern row, counts within
+    capacity, no pattern colour already on that wall row; dense walls so that bonuses and long adjacency runs occur."""
+    g = ref.Azul(players=players, rules={"first_player": 1, "tile_pool": "Lid"} if pool else {})
+    g.turn_counter = int(rng.integers(1, 9))
+    g.current_player = int(rng.integers(1, players + 1))
+    g.next_first_player = int(rng.integers(0, players + 1))
+    density = rng.uniform(0.1, 0.9)
+    g.walls = rng.random((players, 5, 5)) < density
+    for p in range(players):                      # never start from an already complete row (the game would be over)
+        for r in range(5):
+            if g.walls[p, r].all():
+                g.walls[p, r, int(rng.integers(0, 5))] = False
+    g.pattern_lines = np.zeros((players, 5, 5), dtype=int)
+    for p in range(players):
+        for r in range(5):
+            free = [c for c in range(5) if not g.walls[p, r, c]]
+            if free and rng.random() < 0.75:
+                c = int(rng.choice(free))
+                g.pattern_lines[p, r, c] = int(rng.integers(1, r + 2)) if rng.random() < 0.5 else r + 1
+    g.floors = rng.integers(0, 8, size=players)
+    g.score = rng.integers(0, 90, size=players)
+    empty_table = rng.random() < 0.3
+    g.game_board_displays = np.zeros((5, 5), dtype=int)
+    g.game_board_center = np.zeros(6, dtype=int)
+    if not empty_table:
+        for i in range(5):
+            if rng.random() < 0.6:
+                for _ in range(4):
+                    g.game_board_displays[i, int(rng.integers(0, 5))] += 1
+        for c in range(5):
+            g.game_board_center[c] = int(rng.integers(0, 4)) if rng.random() < 0.5 else 0
+        g.game_board_center[5] = int(rng.random() < 0.5)
+    if pool:
+        g.box_tiles = rng.integers(0, 21, size=5)
+        g.lid_tiles = rng.integers(0, 21, size=5)
+    return g
+
+
+def record_fuzz(ref, out_dir, n_per_config=250):
+    """Random boards: legal mask, count_score result, and one random legal step (with its draws) on the reference."""
+    azul_mod = sys.modules["azulnet.azul"]
+    rng = np.random.default_rng(20240607)
+    out = {}
+    for players in (2, 3, 4):
+        for pool in (0, 1):
+            before, masks, scored, stepped, actions, draws = [], [], [], [], [], []
+            for _ in range(n_per_config):
+                g = random_board(ref, rng, players, pool)
+                before.append(ref_to_record(g))
+                valid = ref.check_all_valid(g)
+                masks.append(mask_words(valid))
+                import copy
+                h = copy.deepcopy(g)
+                h.count_score()
+                scored.append(ref_to_record(h))
+                if valid.any():
+                    a = int(rng.choice(np.nonzero(valid)[0]))
+                    proxy = RecordingRandom()
+                    azul_mod.random = proxy
+                    try:
+                        _random.seed(int(rng.integers(0, 2 ** 31)))
+                        g.step(*ref.nn_deserialize(a))
+                    finally:
+                        azul_mod.random = _random
+                    actions.append(a)
+                    draws.append(np.asarray(proxy.draws if proxy.draws else [-1] * 20, dtype=np.int8))
+                    stepped.append(ref_to_record(g, 1))
+                else:
+                    actions.append(255)
+                    draws.append(np.full(20, -1, np.int8))
+                    stepped.append(ref_to_record(g, 0))
+            key = "p%d_%s" % (players, "lid" if pool else "default")
+            out[key + "_before"] = np.stack(before).astype(np.int16)
+            out[key + "_mask"] = np.stack(masks)
+            out[key + "_scored"] = np.stack(scored).astype(np.int16)
+            out[key + "_action"] = np.asarray(actions, dtype=np.uint8)
+            out[key + "_draws"] = np.stack(draws)
+            out[key + "_stepped"] = np.stack(stepped).astype(np.int16)
+    path = os.path.join(out_dir, "fuzz.npz")
+    np.savez_compressed(path, **out)
+    print("fuzz.npz: %d boards, %.1f KiB" % (6 * n_per_config, os.path.getsize(path) / 1024))
+
+
 def main():
     ref = load_reference()
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     record_kats(ref, out_dir)
+    record_fuzz(ref, out_dir)
     for players in (2, 3, 4):
         for rules_name in RULESETS:
             record_traces(ref, players, rules_name, out_dir)

@@ -44,3 +44,15 @@ def stream_digest(masks, states):
         h.update(np.asarray(m, dtype="<u4").tobytes())
         h.update(np.asarray(s, dtype="<i4").tobytes())
     return h.digest()
+
+
+def load_fuzz():
+    z = np.load(os.path.join(GOLDEN, "fuzz.npz"))
+    return {k: z[k] for k in z.files}
+
+
+FUZZ_CONFIGS = [(p, pool) for p in (2, 3, 4) for pool in (0, 1)]
+
+
+def fuzz_key(players, pool):
+    return "p%d_%s" % (players, "lid" if pool else "default")

@@ -388,3 +388,29 @@ def test_replay_cli_and_json_io(tmp_path):
     azio.export_json_files(eng, out)
     for a, b in zip(paths, out):
         assert json.load(open(a)) == json.load(open(b))
+
+
+def test_random_boards_against_reference():
+    """tests/golden/fuzz.npz through the C ABI: mask, count_score and one step of 250 random boards per configuration."""
+    from tests.helpers import FUZZ_CONFIGS, fuzz_key, load_fuzz
+    fz = load_fuzz()
+    for players, pool in FUZZ_CONFIGS:
+        k = fuzz_key(players, pool)
+        before = fz[k + "_before"].astype(np.int32)
+        n = len(before)
+        eng = engine(n, players, pool, 1, reset=False)
+        assert bool(eng.import_records(before).all())
+        assert np.array_equal(eng.export_records().cpu().numpy(), before)
+        assert np.array_equal(eng.legal_mask().cpu().numpy().astype(np.uint32).T, fz[k + "_mask"]), k
+        prev = eng.score_preview().cpu().numpy().T
+        L = UnpackedLayout(players)
+        assert np.array_equal(prev, fz[k + "_scored"][:, L.score:L.score + players]), k
+        snap = eng.state.clone()
+        eng.count_score()
+        assert np.array_equal(eng.export_records().cpu().numpy(), fz[k + "_scored"].astype(np.int32)), k
+        eng.state.copy_(snap)
+        out = eng.step(torch.from_numpy(fz[k + "_action"]), torch.from_numpy(fz[k + "_draws"]))
+        assert int((out["status"] & 3).max()) == 0
+        got = eng.export_records().cpu().numpy()
+        want = fz[k + "_stepped"].astype(np.int32)
+        assert np.array_equal(got, want), (k, np.nonzero((got != want).any(axis=1))[0][:5])

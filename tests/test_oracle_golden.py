@@ -145,3 +145,23 @@ def test_random_agent_sampler_only_legal_and_weighted():
     light = counts[0] + counts[2]
     assert abs(light / n - 2 / 202) < 0.002 and abs(heavy / n - 200 / 202) < 0.002
     assert O.random_action(np.zeros(6, np.uint32), 123) == -1
+
+
+def test_random_boards_against_reference():
+    """tests/golden/fuzz.npz: random representable boards (dense walls, multi-bonus scoring, floor caps, full-row
+    quirk) with the reference's legal mask, count_score result and one random legal step."""
+    from tests.helpers import FUZZ_CONFIGS, fuzz_key, load_fuzz
+    fz = load_fuzz()
+    for players, pool in FUZZ_CONFIGS:
+        k = fuzz_key(players, pool)
+        for i in range(len(fz[k + "_action"])):
+            rec = fz[k + "_before"][i].astype(np.int32)
+            g = O.Game(players, pool, record=rec.copy())
+            assert np.array_equal(g.legal_mask(), fz[k + "_mask"][i]), (k, i)
+            h = g.copy()
+            h.count_score()
+            assert np.array_equal(h.rec, fz[k + "_scored"][i].astype(np.int32)), (k, i)
+            a = int(fz[k + "_action"][i])
+            if a != 255:
+                assert g.step(a, fz[k + "_draws"][i]) == 0
+                assert np.array_equal(g.rec, fz[k + "_stepped"][i].astype(np.int32)), (k, i)

@@ -155,3 +155,21 @@ def test_packed_opponent_loop_matches_oracle(pool):
                 recs[i] = g.rec
             else:
                 recs[i] = O.fresh_records(1, 2, pool, 0, seed + it + 1, i)[0]
+
+
+def test_packed_rules_random_boards():
+    from tests.helpers import FUZZ_CONFIGS, fuzz_key, load_fuzz
+    fz = load_fuzz()
+    for players, pool in FUZZ_CONFIGS:
+        k = fuzz_key(players, pool)
+        for i in range(len(fz[k + "_action"])):
+            rec = fz[k + "_before"][i].astype(np.int32).copy()
+            rc, m, _ = H.op(rec, players, pool, H.OP_ROUNDTRIP, want_mask=True)
+            assert rc == 0 and np.array_equal(m, fz[k + "_mask"][i]), (k, i)
+            sc = rec.copy()
+            assert H.op(sc, players, pool, H.OP_SCORE)[0] == 0
+            assert np.array_equal(sc, fz[k + "_scored"][i].astype(np.int32)), (k, i)
+            a = int(fz[k + "_action"][i])
+            if a != 255:
+                assert H.op(rec, players, pool, H.OP_STEP, a=a, draws=fz[k + "_draws"][i])[0] == 0
+                assert np.array_equal(rec, fz[k + "_stepped"][i].astype(np.int32)), (k, i)
