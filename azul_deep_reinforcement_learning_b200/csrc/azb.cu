@@ -68,57 +68,147 @@ __global__ void k_legal_mask(const uint32_t* __restrict__ s, int64_t n, uint32_t
     store_mask(mask6, n, g, m);
 }
 
-// K1 (+K2, K5): one Azul.step per game
-template <int P, int POOL>
-__global__ void k_step(Launch L, const uint8_t* __restrict__ action, const int8_t* __restrict__ draws,
-                       uint32_t* __restrict__ mask6_out, int16_t* __restrict__ preview_out,
-                       uint8_t* __restrict__ done_out, uint8_t* __restrict__ status_out)
+// K1 (+K2, K5): one Azul.step per game.
+// The move is cheap and uniform; the end-of-round work (count_score, game-over test, new_round) hits ~10 % of
+// the games of a launch, i.e. ~3 of a warp's 32 lanes.  Each warp therefore walks several rows of 32 games and
+// parks the games whose round just ended in a warp-private shared-memory queue (packed state + game index);
+// whenever 32 are waiting, the warp finishes them together with every lane busy.  No block barrier is involved;
+// the finished games are written back with per-lane (scattered) 4-byte stores that merge in L2 with the
+// coalesced row stores of the same 128-byte lines.
+constexpr int STEP_QCAP = 64;            // entries per warp queue: < 32 waiting + up to 32 new ones
+constexpr int STEP_WARPS = 4;            // warps per block
+
+template <int P>
+__device__ __forceinline__ void queue_put(uint32_t* q, int slot, const Game<P>& g, uint32_t gidx, uint32_t status)
 {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= L.n) return;
-    Game<P> gm;
-    gm.load(L.state, L.n, g);
-    const uint32_t a = action[g];
-    uint32_t status = 0;
-    uint32_t m[6];
-    if (a != AZB_ACTION_SKIP) {
-        if (gm.ended()) {
-            status = ST_ENDED;                                        // azul.py:298-299
-        } else {
-            legal_mask(gm, m);
-            if (!action_is_legal(m, a)) {
-                status = ST_ILLEGAL;                                  // azul.py:301-302
-            } else {
-                const Philox rng{L.k0, L.k1};
-                const uint32_t gid = L.gid0 + (uint32_t)g;
-                if (draws) {
-                    const int8_t* d = draws + 20 * g;
-                    advance<P, POOL>(gm, a, [&](Game<P>& gg) {
-                        new_round_injected<P, POOL>(gg, [&](int k) { return (int)d[k]; });
-                    });
-                } else {
-                    advance<P, POOL>(gm, a, [&](Game<P>& gg) {
-                        new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL);
-                    });
-                }
-                gm.store(L.state, L.n, g);
-            }
-        }
+    q[0 * STEP_QCAP + slot] = g.pl0; q[1 * STEP_QCAP + slot] = g.pl1; q[2 * STEP_QCAP + slot] = g.pl2;
+    q[3 * STEP_QCAP + slot] = g.misc; q[4 * STEP_QCAP + slot] = g.box; q[5 * STEP_QCAP + slot] = g.lid;
+    q[6 * STEP_QCAP + slot] = g.steps;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        q[(7 + 5 * p) * STEP_QCAP + slot] = g.pat[p];  q[(8 + 5 * p) * STEP_QCAP + slot] = g.wall[p];
+        q[(9 + 5 * p) * STEP_QCAP + slot] = g.scf[p];  q[(10 + 5 * p) * STEP_QCAP + slot] = g.sta[p];
+        q[(11 + 5 * p) * STEP_QCAP + slot] = g.stb[p];
     }
-    if (mask6_out || status_out) {
+    q[(7 + 5 * P) * STEP_QCAP + slot] = gidx;
+    q[(8 + 5 * P) * STEP_QCAP + slot] = status;
+}
+template <int P>
+__device__ __forceinline__ void queue_get(const uint32_t* q, int slot, Game<P>& g, uint32_t& gidx, uint32_t& status)
+{
+    g.pl0 = q[0 * STEP_QCAP + slot]; g.pl1 = q[1 * STEP_QCAP + slot]; g.pl2 = q[2 * STEP_QCAP + slot];
+    g.misc = q[3 * STEP_QCAP + slot]; g.box = q[4 * STEP_QCAP + slot]; g.lid = q[5 * STEP_QCAP + slot];
+    g.steps = q[6 * STEP_QCAP + slot];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        g.pat[p] = q[(7 + 5 * p) * STEP_QCAP + slot];  g.wall[p] = q[(8 + 5 * p) * STEP_QCAP + slot];
+        g.scf[p] = q[(9 + 5 * p) * STEP_QCAP + slot];  g.sta[p] = q[(10 + 5 * p) * STEP_QCAP + slot];
+        g.stb[p] = q[(11 + 5 * p) * STEP_QCAP + slot];
+    }
+    gidx = q[(7 + 5 * P) * STEP_QCAP + slot];
+    status = q[(8 + 5 * P) * STEP_QCAP + slot];
+}
+
+struct StepOut {
+    uint32_t* __restrict__ mask6;
+    int16_t* __restrict__ preview;
+    uint8_t* __restrict__ done;
+    uint8_t* __restrict__ status;
+};
+
+// state (when the game moved) and the per-game outputs of azb_step
+template <int P, int POOL>
+__device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, Game<P>& gm, int64_t g, uint32_t status, bool moved)
+{
+    if (moved) gm.store(L.state, L.n, g);
+    if (O.mask6 || O.status) {
+        uint32_t m[6];
         legal_mask(gm, m);
         if (!gm.ended() && (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u && gm.current_player() != 0u)
             status |= ST_STUCK;
-        if (mask6_out) store_mask(mask6_out, L.n, g, m);
+        if (O.mask6) store_mask(O.mask6, L.n, g, m);
     }
-    if (preview_out) {
+    if (O.preview) {
         Game<P> cp = gm;
         count_score<P, POOL>(cp);
 #pragma unroll
-        for (int p = 0; p < P; p++) preview_out[p * L.n + g] = (int16_t)(cp.scf[p] & 0xFFFFu);
+        for (int p = 0; p < P; p++) O.preview[p * L.n + g] = (int16_t)(cp.scf[p] & 0xFFFFu);
     }
-    if (done_out) done_out[g] = gm.ended() ? 1 : 0;
-    if (status_out) status_out[g] = (uint8_t)(status | gm.status());
+    if (O.done) O.done[g] = gm.ended() ? 1 : 0;
+    if (O.status) O.status[g] = (uint8_t)(status | gm.status());
+}
+
+template <int P, int POOL>
+__global__ void __launch_bounds__(32 * STEP_WARPS, 5) k_step(Launch L, const uint8_t* __restrict__ action,
+                                                          const int8_t* __restrict__ draws, StepOut O)
+{
+    constexpr int QWORDS = 9 + 5 * P;                       // packed state + game index + status
+    __shared__ uint32_t queues[STEP_WARPS][QWORDS * STEP_QCAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* q = queues[warp];
+    const int64_t n_rows = (L.n + 31) / 32;
+    const int64_t warps_total = (int64_t)gridDim.x * STEP_WARPS;
+    const Philox rng{L.k0, L.k1};
+    int waiting = 0;                                        // warp-uniform: entries in this warp's queue
+
+    auto drain = [&](int count) {                           // finish `count` (<= 32) games from the tail of the queue
+        if (lane < count) {
+            Game<P> h;
+            uint32_t gidx, st;
+            queue_get<P>(q, waiting - count + lane, h, gidx, st);
+            count_score<P, POOL>(h);                                      // azul.py:307
+            if (is_end_of_game(h)) {                                      // azul.py:308-309
+                h.misc |= 1u << 12;
+            } else if (draws) {                                           // azul.py:311
+                const int8_t* d = draws + 20 * (int64_t)gidx;
+                new_round_injected<P, POOL>(h, [&](int k) { return (int)d[k]; });
+            } else {
+                new_round_philox<P, POOL>(h, rng, L.gid0 + gidx, PURPOSE_REFILL);
+            }
+            step_finish<P, POOL>(L, O, h, (int64_t)gidx, st, true);
+        }
+        waiting -= count;
+        __syncwarp();
+    };
+
+    for (int64_t row = (int64_t)blockIdx.x * STEP_WARPS + warp; row < n_rows; row += warps_total) {
+        const int64_t g = row * 32 + lane;
+        const bool valid = g < L.n;
+        bool round_over = false;
+        Game<P> gm;
+        uint32_t status = 0;
+        if (valid) {
+            gm.load(L.state, L.n, g);
+            const uint32_t a = action[g];
+            bool moved = false;
+            if (a != AZB_ACTION_SKIP) {
+                if (gm.ended()) {
+                    status = ST_ENDED;                                    // azul.py:298-299
+                } else {
+                    uint32_t m[6];
+                    legal_mask(gm, m);
+                    if (!action_is_legal(m, a)) {
+                        status = ST_ILLEGAL;                              // azul.py:301-302
+                    } else {
+                        apply_move<P, POOL>(gm, a);                       // azul.py:304
+                        gm.steps += 1u;
+                        moved = true;
+                        round_over = is_end_of_round(gm);                 // azul.py:306
+                        if (!round_over) next_player(gm);                 // azul.py:313
+                    }
+                }
+            }
+            if (!round_over) step_finish<P, POOL>(L, O, gm, g, status, moved);
+        }
+        const uint32_t over = __ballot_sync(0xFFFFFFFFu, round_over);
+        if (over) {
+            if (round_over) queue_put<P>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
+            waiting += __popc(over);
+            __syncwarp();
+            if (waiting >= 32) drain(32);
+        }
+    }
+    if (waiting > 0) drain(waiting);
 }
 
 // K1+K2+K3+K6 fused: k_steps random-agent env steps per game in one launch
@@ -460,8 +550,16 @@ int azb_step(azb_t* h, uint32_t* state, const uint8_t* action, const int8_t* dra
     CHECK_HANDLE(h);
     if (!state || !action) return azb_fail(AZB_E_INVALID, "null buffer%s");
     const Launch L = make_launch(h, state);
-    DISPATCH_PP(h, (k_step<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
-                       L, action, draws20, mask6_out, preview_out, done_out, status_out)));
+    if (h->n_games > (int64_t)0xFFFFFFFFll) return azb_fail(AZB_E_INVALID, "n_games exceeds the step kernel's 32-bit game index%s");
+    StepOut O{mask6_out, preview_out, done_out, status_out};
+    // persistent warps: each walks several rows of 32 games so that its queue of finished rounds fills up
+    const int64_t rows = (h->n_games + 31) / 32;
+    int64_t blocks = (rows + STEP_WARPS - 1) / STEP_WARPS;
+    int per_sm = 0;
+    DISPATCH_PP(h, AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step<P, POOL>, 32 * STEP_WARPS, 0)));
+    const int64_t resident = (int64_t)h->sm_count * (per_sm > 0 ? per_sm : 1);
+    if (blocks > resident) blocks = resident;
+    DISPATCH_PP(h, (k_step<P, POOL><<<dim3((unsigned)blocks), 32 * STEP_WARPS, 0, (cudaStream_t)stream>>>(L, action, draws20, O)));
     CHECK_LAUNCH();
     return 0;
 }
