@@ -139,7 +139,7 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 }
 
 template <int P, int POOL>
-__global__ void __launch_bounds__(32 * STEP_WARPS, 5) k_step(Launch L, const uint8_t* __restrict__ action,
+__global__ void __launch_bounds__(32 * STEP_WARPS, P == 2 ? 5 : 4) k_step(Launch L, const uint8_t* __restrict__ action,
                                                           const int8_t* __restrict__ draws, StepOut O)
 {
     constexpr int QWORDS = 9 + 5 * P;                       // packed state + game index + status
@@ -171,15 +171,23 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, 5) k_step(Launch L, const uin
         __syncwarp();
     };
 
-    for (int64_t row = (int64_t)blockIdx.x * STEP_WARPS + warp; row < n_rows; row += warps_total) {
+    // software pipeline: the loads of the next row are in flight while this row is processed
+    int64_t row = (int64_t)blockIdx.x * STEP_WARPS + warp;
+    Game<P> nxt;
+    uint32_t nxt_a = AZB_ACTION_SKIP;
+    if (row < n_rows && row * 32 + lane < L.n) { nxt.load(L.state, L.n, row * 32 + lane); nxt_a = action[row * 32 + lane]; }
+    for (; row < n_rows; row += warps_total) {
         const int64_t g = row * 32 + lane;
         const bool valid = g < L.n;
         bool round_over = false;
-        Game<P> gm;
+        Game<P> gm = nxt;
+        const uint32_t a = nxt_a;
+        {
+            const int64_t g2 = (row + warps_total) * 32 + lane;
+            if (row + warps_total < n_rows && g2 < L.n) { nxt.load(L.state, L.n, g2); nxt_a = action[g2]; }
+        }
         uint32_t status = 0;
         if (valid) {
-            gm.load(L.state, L.n, g);
-            const uint32_t a = action[g];
             bool moved = false;
             if (a != AZB_ACTION_SKIP) {
                 if (gm.ended()) {
