@@ -90,23 +90,74 @@ def run_episodes(runner, packed, max_decisions=160, check_every=8, record_obs=Tr
     alive = torch.ones(G, dtype=torch.bool, device=dev)
     rec = {k: [] for k in ("reward", "value", "logp", "entropy", "action", "active", "mask", "obs")}
     for t in range(max_decisions):
-        if record_obs:
-            rec["obs"].append(runner.get_state().to(torch.bfloat16))
-        rec["mask"].append(runner.mask.clone())
-        out = runner.step_policy(packed)
-        acted = alive & ((out["policy_status"] & 6) == 0)         # a decision was actually taken for this game
-        rec["active"].append(acted)
-        rec["reward"].append(out["reward"].to(torch.float32))
-        rec["value"].append(out["value"])
-        rec["logp"].append(out["logp"])
-        rec["entropy"].append(out["entropy"])
-        rec["action"].append(out["action"].to(torch.int64))
-        alive = acted & ~out["done"].bool()
+        alive = _one_decision(runner, packed, rec, alive, record_obs)
         if (t + 1) % check_every == 0 and not bool(alive.any()):
             break
     out = {k: torch.stack(v) for k, v in rec.items() if v}
     out["unfinished"] = int(alive.sum())
     return out
+
+
+def _one_decision(runner, packed, rec, alive, record_obs):
+    """One agent decision for every game: record what ``NNRunner.run_episode`` records (nn_runner.py:27-45)."""
+    if record_obs:
+        rec["obs"].append(runner.get_state().to(torch.bfloat16))
+    rec["mask"].append(runner.mask.clone())
+    out = runner.step_policy(packed)
+    acted = alive & ((out["policy_status"] & 6) == 0)         # a decision was actually taken for this game
+    rec["active"].append(acted)
+    rec["reward"].append(out["reward"].to(torch.float32))
+    rec["value"].append(out["value"])
+    rec["logp"].append(out["logp"])
+    rec["entropy"].append(out["entropy"])
+    rec["action"].append(out["action"].to(torch.int64))
+    return acted & ~out["done"].bool()
+
+
+class GraphedEpisodes:
+    """``run_episodes`` with its launch-bound inner loop captured once in a CUDA graph.
+
+    One agent decision is three small kernels plus a handful of bookkeeping ops; at 1,024 games per batch the
+    loop is bound by launch latency, not by the GPU.  The first ``decisions`` decisions of an episode batch
+    (reset included) are therefore recorded into one CUDA graph and replayed per batch; batches in which some
+    game needs more decisions continue eagerly.  Results are identical to :func:`run_episodes`."""
+
+    def __init__(self, runner, packed, decisions=48, record_obs=True):
+        self.runner, self.packed, self.decisions, self.record_obs = runner, packed, decisions, record_obs
+        dev = runner.device
+        # warm-up on a side stream (lazy CUDA initialisation must not happen during capture)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._body(2)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.rec, self.alive = self._body(decisions)
+
+    def _body(self, decisions):
+        runner = self.runner
+        G, dev = runner.n_games, runner.device
+        runner.reset()
+        alive = torch.ones(G, dtype=torch.bool, device=dev)
+        rec = {k: [] for k in ("reward", "value", "logp", "entropy", "action", "active", "mask", "obs")}
+        for _ in range(decisions):
+            alive = _one_decision(runner, self.packed, rec, alive, self.record_obs)
+        return rec, alive
+
+    def run(self, max_decisions=160, check_every=8):
+        self.graph.replay()
+        rec = {k: list(v) for k, v in self.rec.items()}
+        alive = self.alive
+        t = self.decisions
+        while t < max_decisions and bool(alive.any()):
+            for _ in range(check_every):
+                alive = _one_decision(self.runner, self.packed, rec, alive, self.record_obs)
+            t += check_every
+        out = {k: torch.stack(v) for k, v in rec.items() if v}
+        out["unfinished"] = int(alive.sum())
+        return out
 
 
 def discounted_returns(reward, active, gamma):

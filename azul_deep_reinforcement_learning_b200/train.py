@@ -22,7 +22,7 @@ import torch.distributed as dist
 from . import parallel
 from .azulnet.model import ActorCritic
 from .engine import PackedPolicy, mask_to_bool
-from .selfplay import BatchedGameRunner, discounted_returns, run_episodes
+from .selfplay import BatchedGameRunner, GraphedEpisodes, discounted_returns, run_episodes
 
 ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF = 1.0, 0.5, 0.1          # agent.py:47-49
 
@@ -63,7 +63,7 @@ def global_count(n_local, device):
 
 class SelfPlayTrainer:
     def __init__(self, games_per_rank=1024, learning_rate=3e-4, gamma=0.99, seed=0, device=0, rank=0, world=1,
-                 rules=None, max_decisions=160):
+                 rules=None, max_decisions=160, use_cuda_graph=True):
         self.rank, self.world, self.gamma, self.max_decisions = rank, world, gamma, max_decisions
         self.device = torch.device("cuda", device)
         torch.manual_seed(seed)                              # identical initial weights on every rank
@@ -73,12 +73,16 @@ class SelfPlayTrainer:
         self.runner = BatchedGameRunner(games_per_rank, rules=rules, seed=seed, device=device,
                                         game_id_base=parallel.shard(rank, games_per_rank))
         self.packed = PackedPolicy(self.runner.engine, self.net)
+        self.graphed = GraphedEpisodes(self.runner, self.packed) if use_cuda_graph else None
         self.history = []
 
     def rollout(self):
         with torch.no_grad():
             self.packed.update(self.net)
-            batch = run_episodes(self.runner, self.packed, max_decisions=self.max_decisions)
+            if self.graphed is not None:
+                batch = self.graphed.run(max_decisions=self.max_decisions)
+            else:
+                batch = run_episodes(self.runner, self.packed, max_decisions=self.max_decisions)
             batch["qval"] = discounted_returns(batch["reward"], batch["active"], self.gamma)
             batch["stats"] = self.runner.engine.stats().to(torch.float64)
         return batch

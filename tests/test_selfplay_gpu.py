@@ -109,3 +109,29 @@ def test_agent_opponent_in_batched_runner():
     # a whole batch of episodes against the Agent opponent terminates and produces rewards
     batch = run_episodes(gr, packed, max_decisions=200)
     assert batch["unfinished"] < n // 20 and float(batch["reward"].abs().sum()) > 0
+
+
+def test_cuda_graph_rollout_equals_eager():
+    """The CUDA-graph replay of the episode loop produces exactly the eager loop's batch."""
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import PackedPolicy
+    from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner, GraphedEpisodes, run_episodes
+    torch.manual_seed(2)
+    net = ActorCritic(136, 180)
+    a = BatchedGameRunner(768, seed=21)
+    b = BatchedGameRunner(768, seed=21)
+    pa, pb = PackedPolicy(a.engine, net), PackedPolicy(b.engine, net)
+    eager = run_episodes(a, pa)
+    graphed = GraphedEpisodes(b, pb, decisions=40)
+    for rep in range(2):                                  # replaying twice: buffers are reused correctly
+        if rep:
+            eager = run_episodes(a, pa)
+        g = graphed.run()
+        T = min(eager["active"].shape[0], g["active"].shape[0])
+        assert eager["unfinished"] == g["unfinished"] == 0
+        assert not bool(eager["active"][T:].any()) and not bool(g["active"][T:].any())
+        act = eager["active"][:T]
+        assert torch.equal(act, g["active"][:T])
+        for k in ("reward", "action", "logp", "value", "entropy"):
+            assert torch.equal(eager[k][:T][act], g[k][:T][act]), (rep, k)
+        assert torch.equal(a.engine.state, b.engine.state)
