@@ -121,11 +121,10 @@ def test_cuda_graph_rollout_equals_eager():
     a = BatchedGameRunner(768, seed=21)
     b = BatchedGameRunner(768, seed=21)
     pa, pb = PackedPolicy(a.engine, net), PackedPolicy(b.engine, net)
-    eager = run_episodes(a, pa)
-    graphed = GraphedEpisodes(b, pb, decisions=40)
+    graphed = GraphedEpisodes(b, pb, decisions=40)        # (its warm-up advances b's per-slot RNG position)
     for rep in range(2):                                  # replaying twice: buffers are reused correctly
-        if rep:
-            eager = run_episodes(a, pa)
+        a.engine.state.copy_(b.engine.state)              # same RNG position: reset keeps the step counters
+        eager = run_episodes(a, pa)
         g = graphed.run()
         T = min(eager["active"].shape[0], g["active"].shape[0])
         assert eager["unfinished"] == g["unfinished"] == 0
