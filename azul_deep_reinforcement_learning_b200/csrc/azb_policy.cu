@@ -213,6 +213,20 @@ __device__ __forceinline__ void build_obs_tile(const Game<2>& g, unsigned char* 
     }
 }
 
+// parts 1..3 build the NEXT tile's observation (6 chunks each) while part 0 plays this tile's moves
+__device__ __forceinline__ void build_obs_tile_3(const Game<2>& g, unsigned char* a_tile, int row, int part)
+{
+    const int persp = g.seat();
+    const uint32_t pat_me = g.sel(g.pat, persp), pat_ot = g.sel(g.pat, 1 - persp);
+    const uint32_t wall_me = g.sel(g.wall, persp), wall_ot = g.sel(g.wall, 1 - persp);
+    const uint32_t scf_me = g.sel(g.scf, persp), scf_ot = g.sel(g.scf, 1 - persp);
+    switch (part) {
+    case 1: obs_chunks<0, 3>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row); break;
+    case 2: obs_chunks<1, 3>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row); break;
+    default: obs_chunks<2, 3>(g, pat_me, pat_ot, wall_me, wall_ot, scf_me, scf_ot, persp, a_tile, row); break;
+    }
+}
+
 // 6 x 30-bit mask words (word p = destination p) -> 180 contiguous bits, bit a = action a
 __device__ __forceinline__ void linear_mask(const uint32_t m[6], uint32_t lin[6])
 {
@@ -281,11 +295,24 @@ __device__ __forceinline__ uint64_t mask_window(const uint32_t (&lin)[6], int st
     return x & 0xFFFFFFFFFFFFull;
 }
 
-// cross-part scratch (aliases the A tile, which is idle between the layer-2 MMA and the next tile)
+// cross-part scratch: lives in the tail of the A region (dead once the layer-2 MMA has read the hidden tile), behind
+// the first 36,864 bytes that the NEXT tile's observation is written to while the owner threads play this tile's moves
 struct RowPart { float m, s, sl, value; int amax, n; };
-constexpr int OFF_PARTS = 0;                                             // RowPart[PARTS][TILE_M]
-constexpr int OFF_RESULT = OFF_PARTS + PARTS * TILE_M * (int)sizeof(RowPart);   // int2[TILE_M]: sampled action, logit bits
+constexpr int OBS_TILE_BYTES = K1_CHUNKS * M_GROUPS * 128;
+constexpr int OFF_PARTS = OBS_TILE_BYTES;                                // RowPart[PARTS][TILE_M] as 5 words each
+constexpr int PART_WORDS = 5;                                            // m, s, sl, value, amax | n << 8
+constexpr int OFF_RESULT = OFF_PARTS + PARTS * TILE_M * PART_WORDS * 4;  // int2[TILE_M]: sampled action, logit bits
 static_assert(OFF_RESULT + TILE_M * 8 <= A_BYTES, "scratch exceeds the A tile");
+
+__device__ __forceinline__ RowPart load_part(const float* parts, int slot)
+{
+    RowPart rp;
+    rp.m = parts[0 * THREADS + slot]; rp.s = parts[1 * THREADS + slot]; rp.sl = parts[2 * THREADS + slot];
+    rp.value = parts[3 * THREADS + slot];
+    const int an = __float_as_int(parts[4 * THREADS + slot]);
+    rp.amax = an & 255; rp.n = an >> 8;
+    return rp;
+}
 
 template <int POOL>
 __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
@@ -296,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
     const uint32_t bar1 = smem_u32(smem + OFF_BAR), bar2 = bar1 + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
-    RowPart* parts = reinterpret_cast<RowPart*>(a_tile + OFF_PARTS);
+    float* parts = reinterpret_cast<float*>(a_tile + OFF_PARTS);     // [word][part][row]: conflict-free
     int2* result = reinterpret_cast<int2*>(a_tile + OFF_RESULT);
     __shared__ unsigned long long cnt[AZB_N_COUNTERS];
     if (tid < AZB_N_COUNTERS) cnt[tid] = 0ull;
@@ -330,15 +357,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     const int64_t tiles = (A.n + TILE_M - 1) / TILE_M;
     const int col0 = part * PART_COLS;                 // this thread's 48 epilogue columns
 
+    // software pipeline over tiles: the next tile's state is loaded during this tile's epilogues and its observation
+    // is built by parts 1..3 while part 0 plays this tile's moves
+    Game<2> nxt;
+    if ((int64_t)blockIdx.x < tiles) {
+        const int64_t g0 = (int64_t)blockIdx.x * TILE_M + row;
+        nxt.load(A.state_in, A.n, g0 < A.n ? g0 : A.n - 1);
+        build_obs_tile(nxt, a_tile, row, part);
+    }
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t g = tile * TILE_M + row;
         const bool valid = g < A.n;
         const int64_t gl = valid ? g : A.n - 1;
-        Game<2> gm;
-        gm.load(A.state_in, A.n, gl);
+        Game<2> gm = nxt;
+        const bool has_next = tile + gridDim.x < tiles;
 
-        // ---- observation tile -> shared memory (layer-1 A operand) ----
-        build_obs_tile(gm, a_tile, row, part);
+        // ---- the observation tile (layer-1 A operand) is already in shared memory ----
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -355,6 +389,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 umma(tmem_base + N1A, ad, bd_c, instr_desc(N1C), s > 0);
             }
             umma_commit(bar1);
+        }
+        if (has_next) {                                    // in flight while the epilogues run
+            const int64_t g2 = (tile + gridDim.x) * TILE_M + row;
+            nxt.load(A.state_in, A.n, g2 < A.n ? g2 : A.n - 1);
         }
         mbar_wait(bar1, phase);
         tc_fence_after();
@@ -448,9 +486,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             mx = nm;
         }
         {
-            RowPart rp;
-            rp.m = mx; rp.s = se; rp.sl = sl; rp.value = value_p; rp.amax = amax; rp.n = __popcll(mybits);
-            parts[part * TILE_M + row] = rp;
+            const int slot = part * TILE_M + row;
+            parts[0 * THREADS + slot] = mx; parts[1 * THREADS + slot] = se; parts[2 * THREADS + slot] = sl;
+            parts[3 * THREADS + slot] = value_p;
+            parts[4 * THREADS + slot] = __int_as_float(amax | (__popcll(mybits) << 8));
             if (part == 0) result[row] = make_int2(-1, 0);
         }
         tc_fence_before();
@@ -461,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         int n_valid = 0, gamax = 0;
 #pragma unroll
         for (int q = 0; q < PARTS; q++) {
-            const RowPart rp = parts[q * TILE_M + row];
+            const RowPart rp = load_part(parts, q * TILE_M + row);
             if (rp.n > 0 && rp.m > gmx) { gmx = rp.m; gamax = rp.amax; }
             gsl += rp.sl; value += rp.value; n_valid += rp.n;
         }
@@ -472,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         int last_part = 0;
 #pragma unroll
         for (int q = 0; q < PARTS; q++) {
-            const RowPart rp = parts[q * TILE_M + row];
+            const RowPart rp = load_part(parts, q * TILE_M + row);
             wq[q] = rp.n > 0 ? rp.s * __expf(rp.m - gmx) : 0.0f;
             if (rp.n > 0) last_part = q;
             if (q < part) prefix += wq[q];
@@ -571,6 +610,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 if (A.done_out) A.done_out[g] = done_now ? 1 : 0;
                 if (A.status_out) A.status_out[g] = (uint8_t)(status | gm.status());
             }
+        }
+        else if (has_next) {
+            build_obs_tile_3(nxt, a_tile, row, part);      // writes [0, OBS_TILE_BYTES): the scratch above it stays intact
         }
         // all TMEM reads and scratch reads of this tile are complete before the next tile overwrites them
         __syncthreads();
