@@ -21,6 +21,7 @@
 
 #include "azb_internal.h"
 #include "azb_rules.cuh"
+#include "azb_queue.cuh"
 
 using namespace azb;
 
@@ -277,6 +278,8 @@ struct PolicyArgs {
 };
 
 constexpr uint32_t PURPOSE_POLICY = 4;
+// transient MISC bits between k_policy and k_finish_rounds (never visible outside azb_policy_step)
+constexpr uint32_t FLAG_ROUND_OVER = 1u << 28, FLAG_FRESH_GAME = 1u << 29;
 
 struct SmemSink {
     unsigned long long* c;
@@ -585,29 +588,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 if (A.logp_out) A.logp_out[g] = logp;
                 if (A.entropy_out) A.entropy_out[g] = entropy;
             }
-            bool finished = false;
-            if (A.apply_step && n_valid > 0 && !gm.ended()) {
-                const uint32_t gid = A.gid0 + (uint32_t)gl;
-                const uint32_t turn_before = gm.turn_counter();
-                finished = advance<2, POOL>(gm, action, [&](Game<2>& gg) { new_round_philox<2, POOL>(gg, rng, gid, PURPOSE_REFILL); });
-                if (valid && A.apply_step == 2) {
-                    sink.add(0, 1);
-                    if (gm.turn_counter() != turn_before) sink.add(2, 1);
-                }
+            // Only the cheap, uniform part of Azul.step runs here (move, next player).  Games whose round just ended --
+            // and, in self-play mode, slots that need a fresh game -- are flagged in MISC and completed by
+            // k_finish_rounds right after this kernel, 32 at a time with full warps (see azb_queue.cuh).
+            const bool ended_before = gm.ended();
+            const bool stuck = acts && status == (uint32_t)ST_STUCK;
+            uint32_t flags = 0u;
+            if (A.apply_step && n_valid > 0 && !ended_before) {
+                apply_move<2, POOL>(gm, action);                          // azul.py:304
+                gm.steps += 1u;
+                if (is_end_of_round(gm)) flags = FLAG_ROUND_OVER;         // azul.py:306 -> k_finish_rounds
+                else next_player(gm);                                     // azul.py:313
+                if (valid && A.apply_step == 2) sink.add(0, 1);
+            } else if (A.apply_step == 2 && acts && (ended_before || stuck)) {
+                flags = FLAG_FRESH_GAME;                                  // GameRunner.reset, game_runner.py:76-80
+                if (valid && stuck) sink.add(6, 1);
             }
-            const bool done_now = gm.ended();
-            if (A.apply_step == 2 && (done_now || (n_valid == 0 && !gm.ended()))) {
-                // game over (or stuck): count it and start a fresh game in the slot (GameRunner.reset, game_runner.py:76-80)
-                if (valid) {
-                    if (finished) tally_finished(gm, sink);
-                    else if (!done_now) sink.add(6, 1);
-                    sink.add(2, 1);
-                }
-                reset_game<2, POOL>(gm, rng, A.gid0 + (uint32_t)gl, A.first_rule);
-            }
+            gm.misc |= flags;
             if (valid && A.apply_step) gm.store(A.state, A.n, g);
             if (valid) {
-                if (A.done_out) A.done_out[g] = done_now ? 1 : 0;
+                if (A.done_out) A.done_out[g] = ended_before ? 1 : 0;      // finalised by k_finish_rounds for flagged games
                 if (A.status_out) A.status_out[g] = (uint8_t)(status | gm.status());
             }
         }
@@ -623,6 +623,86 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+}
+
+// Completes the steps k_policy started: count_score, game-over test and new_round (azul.py:307-311) for the games
+// whose round ended, fresh games for finished / stuck slots in self-play mode.  Persistent warps scan the MISC word
+// of every game (coalesced), park flagged games in a warp-private queue and finish 32 at a time.
+struct FinishArgs {
+    uint32_t* __restrict__ state;
+    int64_t n;
+    uint32_t k0, k1, gid0;
+    int first_rule;
+    int auto_reset;
+    uint8_t* __restrict__ done_out;
+    uint8_t* __restrict__ status_out;
+    unsigned long long* __restrict__ counters;
+};
+
+template <int POOL>
+__global__ void __launch_bounds__(32 * STEP_WARPS) k_finish_rounds(FinishArgs F)
+{
+    constexpr int QWORDS = 9 + 5 * 2;
+    __shared__ uint32_t queues[STEP_WARPS][QWORDS * STEP_QCAP];
+    __shared__ unsigned long long cnt[AZB_N_COUNTERS];
+    if (threadIdx.x < AZB_N_COUNTERS) cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+    SmemSink sink{cnt};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* q = queues[warp];
+    const int64_t n_rows = (F.n + 31) / 32;
+    const int64_t warps_total = (int64_t)gridDim.x * STEP_WARPS;
+    const Philox rng{F.k0, F.k1};
+    int waiting = 0;
+
+    auto drain = [&](int count) {
+        if (lane < count) {
+            Game<2> h;
+            uint32_t gidx, flags;
+            queue_get<2>(q, waiting - count + lane, h, gidx, flags);
+            const uint32_t gid = F.gid0 + gidx;
+            bool over = false, fresh = (flags & FLAG_FRESH_GAME) != 0u;
+            if (flags & FLAG_ROUND_OVER) {
+                count_score<2, POOL>(h);                                  // azul.py:307
+                over = is_end_of_game(h);                                 // azul.py:308-309
+                if (over) h.misc |= 1u << 12;
+            }
+            if (F.done_out) F.done_out[gidx] = h.ended() ? 1 : 0;
+            if (over && F.auto_reset) { tally_finished(h, sink); fresh = true; }
+            if (fresh) {
+                reset_game<2, POOL>(h, rng, gid, F.first_rule);
+                if (F.auto_reset) sink.add(2, 1);
+            } else if (!over) {
+                new_round_philox<2, POOL>(h, rng, gid, PURPOSE_REFILL);   // azul.py:311
+                if (F.auto_reset) sink.add(2, 1);
+            }
+            h.store(F.state, F.n, (int64_t)gidx);
+            if (F.status_out) F.status_out[gidx] |= (uint8_t)h.status();
+        }
+        waiting -= count;
+        __syncwarp();
+    };
+
+    for (int64_t row = (int64_t)blockIdx.x * STEP_WARPS + warp; row < n_rows; row += warps_total) {
+        const int64_t g = row * 32 + lane;
+        const uint32_t misc = g < F.n ? F.state[3 * F.n + g] : 0u;
+        const uint32_t flags = misc & (FLAG_ROUND_OVER | FLAG_FRESH_GAME);
+        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, flags != 0u);
+        if (hit) {
+            if (flags) {
+                Game<2> gm;
+                gm.load(F.state, F.n, g);
+                gm.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
+                queue_put<2>(q, waiting + __popc(hit & ((1u << lane) - 1u)), gm, (uint32_t)g, flags);
+            }
+            waiting += __popc(hit);
+            __syncwarp();
+            if (waiting >= 32) drain(32);
+        }
+    }
+    if (waiting > 0) drain(waiting);
+    __syncthreads();
+    if (F.counters && threadIdx.x < AZB_N_COUNTERS && cnt[threadIdx.x]) atomicAdd(&F.counters[threadIdx.x], cnt[threadIdx.x]);
 }
 
 // fp32 torch-layout weights -> the bf16 shared-memory image
@@ -703,6 +783,20 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
         pol::k_policy<0><<<grid, pol::THREADS, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
     }
     CHECK_LAUNCH();
+    if (apply_step) {
+        pol::FinishArgs F;
+        F.state = state; F.n = h->n_games; F.k0 = A.k0; F.k1 = A.k1; F.gid0 = A.gid0; F.first_rule = h->first_player;
+        F.auto_reset = apply_step == 2; F.done_out = done_out; F.status_out = status_out; F.counters = counters;
+        const int64_t rows = (h->n_games + 31) / 32;
+        int64_t blocks = (rows + STEP_WARPS - 1) / STEP_WARPS;
+        const int64_t resident = (int64_t)h->sm_count * 4;
+        if (blocks > resident) blocks = resident;
+        if (h->tile_pool == AZB_POOL_LID)
+            pol::k_finish_rounds<1><<<dim3((unsigned)blocks), 32 * STEP_WARPS, 0, (cudaStream_t)stream>>>(F);
+        else
+            pol::k_finish_rounds<0><<<dim3((unsigned)blocks), 32 * STEP_WARPS, 0, (cudaStream_t)stream>>>(F);
+        CHECK_LAUNCH();
+    }
     return 0;
 }
 
