@@ -788,7 +788,8 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
         F.state = state; F.n = h->n_games; F.k0 = A.k0; F.k1 = A.k1; F.gid0 = A.gid0; F.first_rule = h->first_player;
         F.auto_reset = apply_step == 2; F.done_out = done_out; F.status_out = status_out; F.counters = counters;
         const int64_t rows = (h->n_games + 31) / 32;
-        int64_t blocks = (rows + STEP_WARPS - 1) / STEP_WARPS;
+        // ~10 % of the games are flagged: give every warp enough rows (12) to fill its queue of 32 at least once
+        int64_t blocks = (rows + STEP_WARPS * 12 - 1) / (STEP_WARPS * 12);
         const int64_t resident = (int64_t)h->sm_count * 4;
         if (blocks > resident) blocks = resident;
         if (h->tile_pool == AZB_POOL_LID)
