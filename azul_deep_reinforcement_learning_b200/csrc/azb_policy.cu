@@ -18,6 +18,7 @@
 // cross-thread traffic).  The bf16 weights (180 KB) stay resident in shared memory for the lifetime of
 // the CTA; the observation tile is generated in-kernel from the packed state and never touches HBM.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "azb_internal.h"
 #include "azb_rules.cuh"
@@ -788,8 +789,9 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
         F.state = state; F.n = h->n_games; F.k0 = A.k0; F.k1 = A.k1; F.gid0 = A.gid0; F.first_rule = h->first_player;
         F.auto_reset = apply_step == 2; F.done_out = done_out; F.status_out = status_out; F.counters = counters;
         const int64_t rows = (h->n_games + 31) / 32;
-        // ~10 % of the games are flagged: give every warp enough rows (12) to fill its queue of 32 at least once
-        int64_t blocks = (rows + STEP_WARPS * 12 - 1) / (STEP_WARPS * 12);
+        // rows of 32 games per warp (tunable with AZB_FINISH_ROWS): more rows fill the queue better, fewer rows finish sooner
+        static const int rows_per_warp = [] { const char* e = getenv("AZB_FINISH_ROWS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+        int64_t blocks = (rows + STEP_WARPS * rows_per_warp - 1) / (STEP_WARPS * rows_per_warp);
         const int64_t resident = (int64_t)h->sm_count * 4;
         if (blocks > resident) blocks = resident;
         if (h->tile_pool == AZB_POOL_LID)
