@@ -547,14 +547,23 @@ int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_o
     if (k_steps < 0) return azb_fail(AZB_E_INVALID, "k_steps < 0%s");
     const Launch L = make_launch(h, state);
     // Grid sizing: the kernel is issue-bound and every game runs for the whole launch, so the slowest SM sets the time.
-    // Unless the caller fixed the block size, give every SM the same number of equally sized blocks:
-    // k = ceil(n / (SMs * 512)) blocks per SM of ceil(n / (SMs * k)) threads (rounded up to a warp).
+    // Unless the caller fixed the block size: when the whole batch is resident at once give every SM the same number
+    // of equally sized blocks, k = ceil(n / (SMs * 512)) blocks per SM of ceil(n / (SMs * k)) threads (rounded to a warp).
     int threads = h->block_threads;
     if (!h->block_threads_set) {
+        // single wave (everything resident at once, e.g. 65,536 or 131,072 games): equal blocks per SM;
+        // several waves: small blocks, so that the tail of the last wave is short
+        int blocks64 = 0;
+        DISPATCH_PP(h, AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks64, k_rollout_random<P, POOL>, 64,
+                                                                             (size_t)ROUND_WORDS * 64 * sizeof(uint32_t))));
         const int64_t per_sm = (h->n_games + h->sm_count - 1) / h->sm_count;
-        const int64_t k = (per_sm + 511) / 512;
-        threads = (int)(((per_sm + k - 1) / k + 31) / 32 * 32);
-        threads = threads < 64 ? 64 : threads > 512 ? 512 : threads;
+        if (per_sm <= (int64_t)blocks64 * 64) {
+            const int64_t k = (per_sm + 511) / 512;
+            threads = (int)(((per_sm + k - 1) / k + 31) / 32 * 32);
+            threads = threads < 64 ? 64 : threads > 512 ? 512 : threads;
+        } else {
+            threads = 128;
+        }
     }
     const size_t words_bytes = (size_t)ROUND_WORDS * threads * sizeof(uint32_t);
     if (words_bytes > 48 * 1024) return azb_fail(AZB_E_INVALID, "block threads too large for the rollout kernel's word buffer%s");
