@@ -57,3 +57,13 @@ def export_json_files(engine, paths):
     for rec, p in zip(recs, paths):
         with open(p, "w") as f:
             json.dump(json_dict_from_record(rec), f)
+
+
+def records_equal(a, b):
+    """``Azul.__eq__`` (azul.py:63) on unpacked records: displays, centre, pattern lines, walls, floors, score,
+    current / next first player, players, end_of_game, turn_counter -- box / lid and the statistics are not compared.
+    ``a`` and ``b``: int arrays ``[..., U]`` of the same player count; returns a bool array over the leading dims."""
+    a, b = np.asarray(a), np.asarray(b)
+    players = (a.shape[-1] - 48) // 58
+    end = UnpackedLayout(players).box            # everything before box/lid is exactly the __eq__ field set
+    return (a[..., :end] == b[..., :end]).all(axis=-1)
