@@ -105,16 +105,82 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
     if (O.status) O.status[g] = (uint8_t)(status | gm.status());
 }
 
-template <int P, int POOL>
-__global__ void __launch_bounds__(32 * STEP_WARPS, P == 2 ? 5 : 4) k_step(Launch L, const uint8_t* __restrict__ action,
-                                                          const int8_t* __restrict__ draws, StepOut O)
+// ---- k_step: staged, persistent-warp implementation ----
+// Each warp owns (in dynamic shared memory) a ring of STAGES row tiles [word][lane], one output tile for the legal
+// mask and its queue of finished rounds.  Rows are fetched NSTAGE-1 iterations ahead with 16-byte cp.async copies
+// (no registers are held by loads in flight), read from the tile with conflict-free 4-byte shared loads, and --
+// on the aligned path -- written back through the tile with 16-byte global stores, so that a row costs
+// ceil(W/4) + 2 global store instructions instead of W + 6 and every 128-byte line is written whole.
+constexpr int STEP5_QCAP = 48;           // a row that would overflow the queue drains it first
+constexpr int STEP5_WARPS = 2;           // warps per block (fine-grained shared-memory occupancy)
+
+template <int P, int STAGES>
+struct StepSmem {
+    static constexpr int W = 7 + 5 * P;
+    static constexpr int QUEUE = (W + 2) * STEP5_QCAP;
+    static constexpr int TILE = W * 32 + 8;                                  // + the row's 32 action bytes
+    static constexpr int MASK = 6 * 32;
+    static constexpr int WORDS_PER_WARP = QUEUE + STAGES * TILE + MASK;      // multiple of 4 words: 16-byte aligned parts
+    static constexpr size_t bytes(int warps) { return (size_t)warps * WORDS_PER_WARP * sizeof(uint32_t); }
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t* smem_dst, const uint32_t* gsrc)
 {
-    constexpr int QWORDS = 9 + 5 * P;                       // packed state + game index + status
-    __shared__ uint32_t queues[STEP_WARPS][QWORDS * STEP_QCAP];
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// global [word][n] row of 32 games (+ its 32 action bytes on the aligned path) -> tile [word][32] (+ 8 words).
+// The actions travel with the row: a separate register load issued after the copies would return behind them
+// (a warp's memory operations complete in order) and cut the prefetch distance to one row.
+// Lane l moves the 16-byte chunks l, l + 32, ...: chunk c is part (c & 7) of word (c >> 3), so consecutive chunks of a
+// lane are 4 words apart: `lane_off` = (l >> 3) * n + 4 * (l & 7) is fixed per thread and `n4` = 4 * n steps to the next.
+template <int LINES>
+__device__ __forceinline__ void row_fetch(uint32_t* tile, const uint32_t* __restrict__ s, const uint8_t* __restrict__ action,
+                                          int64_t n, int64_t g0, int lane, bool fast, int64_t lane_off, int64_t n4)
+{
+    if (fast) {
+        const uint32_t* src = s + lane_off + g0;
+        uint32_t* dst = tile + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < (LINES * 8 + 31) / 32; k++, src += n4, dst += 128)
+            if (32 * k + 32 <= LINES * 8 || lane < LINES * 8 - 32 * k) cp_async16(dst, src);
+        if (lane < 2) cp_async16(tile + LINES * 32 + 4 * lane, reinterpret_cast<const uint32_t*>(action + g0) + 4 * lane);
+    } else if (g0 + lane < n) {
+#pragma unroll
+        for (int w = 0; w < LINES; w++) cp_async4(tile + 32 * w + lane, s + (int64_t)w * n + g0 + lane);
+    }
+}
+// tile [word][32] -> global [word][n], 16 bytes per lane (aligned, full rows only)
+template <int LINES>
+__device__ __forceinline__ void row_flush(const uint32_t* tile, uint32_t* __restrict__ s, int64_t g0, int lane, int64_t lane_off, int64_t n4)
+{
+    uint32_t* dst = s + lane_off + g0;
+    const uint32_t* src = tile + 4 * lane;
+#pragma unroll
+    for (int k = 0; k < (LINES * 8 + 31) / 32; k++, dst += n4, src += 128)
+        if (32 * k + 32 <= LINES * 8 || lane < LINES * 8 - 32 * k) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+}
+
+template <int P, int POOL, int STAGES>
+__global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const uint8_t* __restrict__ action,
+                                                           const int8_t* __restrict__ draws, StepOut O, int aligned)
+{
+    using S = StepSmem<P, STAGES>;
+    constexpr int W = S::W, QCAP = STEP5_QCAP;
+    extern __shared__ __align__(16) uint32_t step_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* q = queues[warp];
+    uint32_t* q = step_smem + (size_t)warp * S::WORDS_PER_WARP;
+    uint32_t* tiles = q + S::QUEUE;
+    uint32_t* mask_tile = tiles + STAGES * S::TILE;
     const int64_t n_rows = (L.n + 31) / 32;
-    const int64_t warps_total = (int64_t)gridDim.x * STEP_WARPS;
+    const int64_t warps_total = (int64_t)gridDim.x * STEP5_WARPS;
     const Philox rng{L.k0, L.k1};
     int waiting = 0;                                        // warp-uniform: entries in this warp's queue
 
@@ -122,7 +188,7 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, P == 2 ? 5 : 4) k_step(Launch
         if (lane < count) {
             Game<P> h;
             uint32_t gidx, st;
-            queue_get<P>(q, waiting - count + lane, h, gidx, st);
+            queue_get<P, QCAP>(q, waiting - count + lane, h, gidx, st);
             count_score<P, POOL>(h);                                      // azul.py:307
             if (is_end_of_game(h)) {                                      // azul.py:308-309
                 h.misc |= 1u << 12;
@@ -137,52 +203,95 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, P == 2 ? 5 : 4) k_step(Launch
         waiting -= count;
         __syncwarp();
     };
+    auto row_is_fast = [&](int64_t r) { return aligned && r * 32 + 32 <= L.n; };
+    const int64_t lane_off = (int64_t)(lane >> 3) * L.n + 4 * (lane & 7), n4 = 4 * L.n;
 
-    // software pipeline: the loads of the next row are in flight while this row is processed
-    int64_t row = (int64_t)blockIdx.x * STEP_WARPS + warp;
-    Game<P> nxt;
-    uint32_t nxt_a = AZB_ACTION_SKIP;
-    if (row < n_rows && row * 32 + lane < L.n) { nxt.load(L.state, L.n, row * 32 + lane); nxt_a = action[row * 32 + lane]; }
-    for (; row < n_rows; row += warps_total) {
+    const int64_t row0 = (int64_t)blockIdx.x * STEP5_WARPS + warp;
+    // prologue: rows 0 .. STAGES-2 of this warp in flight
+#pragma unroll
+    for (int k = 0; k < STAGES - 1; k++) {
+        const int64_t r = row0 + k * warps_total;
+        if (r < n_rows) row_fetch<W>(tiles + k * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4);
+        cp_async_commit();
+    }
+    int stage = 0;
+    for (int64_t row = row0; row < n_rows; row += warps_total) {
         const int64_t g = row * 32 + lane;
         const bool valid = g < L.n;
-        bool round_over = false;
-        Game<P> gm = nxt;
-        const uint32_t a = nxt_a;
-        {
-            const int64_t g2 = (row + warps_total) * 32 + lane;
-            if (row + warps_total < n_rows && g2 < L.n) { nxt.load(L.state, L.n, g2); nxt_a = action[g2]; }
+        const bool fast = row_is_fast(row);
+        uint32_t* tile = tiles + stage * S::TILE;
+        {   // refill the tile consumed by the previous iteration; every lane is past its reads of it
+            __syncwarp();
+            const int64_t r = row + (STAGES - 1) * warps_total;
+            const int st_fill = stage == 0 ? STAGES - 1 : stage - 1;
+            if (r < n_rows) row_fetch<W>(tiles + st_fill * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4);
+            cp_async_commit();
         }
-        uint32_t status = 0;
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        Game<P> gm;
+        uint32_t a = AZB_ACTION_SKIP;
         if (valid) {
-            bool moved = false;
-            if (a != AZB_ACTION_SKIP) {
-                if (gm.ended()) {
-                    status = ST_ENDED;                                    // azul.py:298-299
+            gm.load(tile, 32, lane);
+            a = fast ? reinterpret_cast<const uint8_t*>(tile + W * 32)[lane] : action[g];
+        }
+        bool round_over = false, moved = false;
+        uint32_t status = 0;
+        if (valid && a != AZB_ACTION_SKIP) {
+            if (gm.ended()) {
+                status = ST_ENDED;                                        // azul.py:298-299
+            } else {
+                if (!move_is_legal(gm, a)) {
+                    status = ST_ILLEGAL;                                  // azul.py:301-302
                 } else {
-                    uint32_t m[6];
-                    legal_mask(gm, m);
-                    if (!action_is_legal(m, a)) {
-                        status = ST_ILLEGAL;                              // azul.py:301-302
-                    } else {
-                        apply_move<P, POOL>(gm, a);                       // azul.py:304
-                        gm.steps += 1u;
-                        moved = true;
-                        round_over = is_end_of_round(gm);                 // azul.py:306
-                        if (!round_over) next_player(gm);                 // azul.py:313
-                    }
+                    apply_move<P, POOL>(gm, a);                           // azul.py:304
+                    gm.steps += 1u;
+                    moved = true;
+                    round_over = is_end_of_round(gm);                     // azul.py:306
+                    if (!round_over) next_player(gm);                     // azul.py:313
                 }
             }
-            if (!round_over) step_finish<P, POOL>(L, O, gm, g, status, moved);
+        }
+        if (fast) {
+            // whole lines through the tile; the lanes whose round ended write their interim state and outputs here
+            // and the final ones in drain() -- later in program order of this warp, ordered by __syncwarp
+            const bool any_moved = __any_sync(0xFFFFFFFFu, moved);
+            uint32_t m[6];
+            legal_mask(gm, m);
+            if (!round_over && !gm.ended() && (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u && gm.current_player() != 0u)
+                status |= ST_STUCK;
+            if (any_moved) gm.store(tile, 32, lane);
+            if (O.mask6) {
+#pragma unroll
+                for (int p = 0; p < 6; p++) mask_tile[32 * p + lane] = m[p];
+            }
+            __syncwarp();
+            if (any_moved) row_flush<W>(tile, L.state, row * 32, lane, lane_off, n4);
+            if (O.mask6) row_flush<6>(mask_tile, O.mask6, row * 32, lane, lane_off, n4);
+            if (!round_over) {
+                if (O.preview) {
+                    Game<P> cp = gm;
+                    count_score<P, POOL>(cp);
+#pragma unroll
+                    for (int p = 0; p < P; p++) O.preview[p * L.n + g] = (int16_t)(cp.scf[p] & 0xFFFFu);
+                }
+                if (O.done) O.done[g] = gm.ended() ? 1 : 0;
+                if (O.status) O.status[g] = (uint8_t)(status | gm.status());
+            }
+        } else if (valid && !round_over) {
+            step_finish<P, POOL>(L, O, gm, g, status, moved);
         }
         const uint32_t over = __ballot_sync(0xFFFFFFFFu, round_over);
         if (over) {
-            if (round_over) queue_put<P>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
+            if (waiting + __popc(over) > QCAP) drain(waiting);            // waiting < 32 here
+            if (round_over) queue_put<P, QCAP>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
             waiting += __popc(over);
             __syncwarp();
             if (waiting >= 32) drain(32);
         }
+        stage = stage + 1 == STAGES ? 0 : stage + 1;
     }
+    cp_async_wait<0>();
     if (waiting > 0) drain(waiting);
 }
 
@@ -444,6 +553,32 @@ __global__ void k_round_flags(const uint32_t* __restrict__ s, int64_t n, uint8_t
 
 static inline dim3 grid_of(const azb_t* h) { return dim3((unsigned)((h->n_games + h->block_threads - 1) / h->block_threads)); }
 
+// persistent warps: each walks many rows of 32 games so that its queue of finished rounds fills up; as many blocks
+// as fit (shared memory decides), never more than there are rows
+template <int P, int POOL>
+static int launch_step(const azb_t* h, const Launch& L, const uint8_t* action, const int8_t* draws, const StepOut& O,
+                       int aligned, cudaStream_t stream)
+{
+    constexpr int STAGES = P == 2 ? 4 : 3;       // measured: 2 / 3 / 4 stages = 244 / 240 / 229 us for 4.2 M two-player games
+    auto kern = k_step<P, POOL, STAGES>;
+    const size_t smem = StepSmem<P, STAGES>::bytes(STEP5_WARPS);
+    static thread_local int per_sm_cached[64] = {0};      // function attributes are per device
+    int uncached = 0;
+    int& per_sm = h->device < 64 ? per_sm_cached[h->device] : uncached;
+    if (per_sm == 0) {
+        AZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * STEP5_WARPS, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    const int64_t rows = (h->n_games + 31) / 32;
+    int64_t blocks = (rows + STEP5_WARPS - 1) / STEP5_WARPS;
+    const int64_t resident = (int64_t)h->sm_count * per_sm;
+    if (blocks > resident) blocks = resident;
+    kern<<<dim3((unsigned)blocks), 32 * STEP5_WARPS, smem, stream>>>(L, action, draws, O, aligned);
+    return 0;
+}
+
 extern "C" {
 
 int azb_abi_version(void) { return AZB_ABI_VERSION; }
@@ -527,14 +662,11 @@ int azb_step(azb_t* h, uint32_t* state, const uint8_t* action, const int8_t* dra
     const Launch L = make_launch(h, state);
     if (h->n_games > (int64_t)0xFFFFFFFFll) return azb_fail(AZB_E_INVALID, "n_games exceeds the step kernel's 32-bit game index%s");
     StepOut O{mask6_out, preview_out, done_out, status_out};
-    // persistent warps: each walks several rows of 32 games so that its queue of finished rounds fills up
-    const int64_t rows = (h->n_games + 31) / 32;
-    int64_t blocks = (rows + STEP_WARPS - 1) / STEP_WARPS;
-    int per_sm = 0;
-    DISPATCH_PP(h, AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step<P, POOL>, 32 * STEP_WARPS, 0)));
-    const int64_t resident = (int64_t)h->sm_count * (per_sm > 0 ? per_sm : 1);
-    if (blocks > resident) blocks = resident;
-    DISPATCH_PP(h, (k_step<P, POOL><<<dim3((unsigned)blocks), 32 * STEP_WARPS, 0, (cudaStream_t)stream>>>(L, action, draws20, O)));
+    // 16-byte copies need every [word] plane (offset w * n_games words), the mask planes and the actions 16-byte aligned
+    const int aligned = h->n_games % 4 == 0 && (((uintptr_t)state | (uintptr_t)mask6_out | (uintptr_t)action) & 15u) == 0;
+    int rc = 0;
+    DISPATCH_PP(h, (rc = launch_step<P, POOL>(h, L, action, draws20, O, aligned, (cudaStream_t)stream)));
+    if (rc) return rc;
     CHECK_LAUNCH();
     return 0;
 }

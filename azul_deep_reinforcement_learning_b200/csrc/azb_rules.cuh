@@ -505,6 +505,22 @@ AZB_HD bool action_is_legal(const uint32_t m[6], uint32_t action)
     return (w >> b) & 1u;
 }
 
+// is_legal_move (azul.py:162-176) for one action, without building the 180-bit mask; same result as
+// action_is_legal(legal_mask(g), action)
+template <int P>
+AZB_HD bool move_is_legal(const Game<P>& g, uint32_t action)
+{
+    if (action >= 180u) return false;
+    const uint32_t p = action / 30u, b = action - 30u * p, c = b / 6u;
+    const uint32_t src = (g.pl0 | g.pl1 | g.pl2 | spread5to6(g.misc & 31u)) & PLANE_MASK;
+    if (!((src >> b) & 1u)) return false;                    // azul.py:164-169: the source holds the colour
+    if (p == 0u) return true;                                // the floor takes anything
+    const int s = g.seat();
+    const uint32_t pat = g.sel(g.pat, s), wall = g.sel(g.wall, s);
+    const uint32_t r = p - 1u, cnt = (pat >> (6u * r + 3u)) & 7u, col = (pat >> (6u * r)) & 7u;
+    return (cnt == 0u || col == c) && !((wall >> (5u * r + c)) & 1u);      // azul.py:171-175
+}
+
 // position of the k-th (0-based) set bit of a 30-bit word; k < popc(m)
 AZB_HD uint32_t select_bit(uint32_t m, uint32_t k)
 {

@@ -57,6 +57,10 @@ def parse_args():
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-actions", default="random", choices=["random", "lowest"],
+                    help="--mode step: the caller-supplied action per game (a random or the lowest legal one)")
+    ap.add_argument("--presteps", type=int, default=203,
+                    help="--mode step: random-agent env steps before the timed step (0 = fresh games: no round can end)")
     return ap.parse_args()
 
 
@@ -230,15 +234,14 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def profiled_traffic(args):
+def profiled_traffic(args, key=None):
     """dram bytes per launch from the committed ncu capture of this configuration, if any."""
     p = os.path.join(REPO, "profiles", "rollout_traffic.json")
     if not os.path.exists(p):
         return None
     try:
         d = json.load(open(p))
-        key = "p%d_%s_g%d_k%d" % (args.players, args.pool, args.games, args.k_steps)
-        return d.get(key)
+        return d.get(key or "p%d_%s_g%d_k%d" % (args.players, args.pool, args.games, args.k_steps))
     except Exception:
         return None
 
@@ -466,16 +469,20 @@ def run_step(args):
     pool = 1 if args.pool == "lid" else 0
     G = args.games
     eng = BatchedAzul(G, args.players, pool, 0, seed=args.seed)
-    eng.rollout_random(17)
+    eng.rollout_random(args.presteps)
     mask = eng.legal_mask()
     done = torch.empty(G, dtype=torch.uint8, device=dev)
     status = torch.empty(G, dtype=torch.uint8, device=dev)
-    # a legal action per game: the lowest set bit of the first non-empty mask word (computed once, outside the timing)
-    m = (mask.to(torch.int64) & 0xFFFFFFFF)
-    word = (m != 0).to(torch.int64).argmax(dim=0)
-    w = m.gather(0, word[None, :]).squeeze(0)
-    low = (w & -w).to(torch.float64).log2().round().to(torch.int64)
-    action = (30 * word + low).to(torch.uint8)
+    # one legal action per game, computed once outside the timing: uniformly random among the legal ones (default: the
+    # share of games whose round ends in the timed step is then that of random play, ~1 in 10) or the lowest one
+    from azul_deep_reinforcement_learning_b200.engine import mask_to_bool
+    legal = mask_to_bool(mask)
+    if args.step_actions == "random":
+        gen = torch.Generator(device=dev).manual_seed(args.seed)
+        action = torch.multinomial(legal.float() + 1e-12, 1, generator=gen).squeeze(1).to(torch.uint8)
+    else:
+        action = legal.to(torch.uint8).argmax(dim=1).to(torch.uint8)
+    del legal
     snapshot = eng.state.clone()
     st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     p = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
@@ -492,19 +499,25 @@ def run_step(args):
         if i >= max(args.warmup, 3):
             ms.append(e0.elapsed_time(e1))
     assert int(status.max()) & 3 == 0
+    # MISC word: turn_counter [27:16] moves on new_round, end_of_game [12] when the scored round finished the game
+    round_ends = float((((eng.state[3] ^ snapshot[3]) & ((0xFFF << 16) | (1 << 12))) != 0).float().mean())
     b_alg = algorithmic_bytes_per_step(args.players) + 2
     t = statistics.median(ms) * 1e-3
     peak, src = hbm_peak()
     cfg = workload_config(args, 1)
     cfg["workload"] = "%d parallel %d-player games, ONE Azul.step + next legal mask per launch, caller-supplied actions" % (G, args.players)
     cfg["env_steps_per_game_per_launch"] = 1
+    cfg["actions"] = "%s legal action per game after %d random-agent steps; %.1f %% of the games end their round (score + refill) in the timed step" % (
+        args.step_actions, args.presteps, 100 * round_ends)
     cfg["l2"] = "working set %.0f MB per launch (state %d B + 28 B per game) exceeds the 126 MB L2" % (G * b_alg / 1e6, 4 * eng.W)
     print(json.dumps({
         "metric": METRIC, "value": G / t, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic", "config": cfg, "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": G * b_alg / t / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": G * b_alg / t / 1e9 / peak, "traffic": None, "peak_source": src,
+                     "frac": G * b_alg / t / 1e9 / peak,
+                     "traffic": profiled_traffic(args, "step_p%d_%s_g%d_%s" % (args.players, args.pool, G, args.step_actions)),
+                     "peak_source": src,
                      "algorithmic_bytes_per_env_step": b_alg, "kernel": "k_step<%d,%d>" % (args.players, pool)}}))
 
 

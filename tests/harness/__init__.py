@@ -37,6 +37,7 @@ def lib():
 
 OP_MOVE, OP_STEP, OP_NEXT, OP_SCORE, OP_NEW_ROUND, OP_RESET, OP_PREVIEW, OP_EOR, OP_EOG, OP_ROUNDTRIP = \
     0, 1, 2, 3, 5, 6, 7, 8, 9, 100
+OP_LEGAL_SINGLE = 10          # returns the number of action bytes where move_is_legal != mask bit
 
 
 def op(rec, players, pool, code, a=0, draws=None, seed=0, gid=0, first_rule=1, want_mask=False, want_preview=False):

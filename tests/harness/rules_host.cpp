@@ -29,6 +29,7 @@ static int run_op(int32_t* rec, int op, int a, const int8_t* draws, uint64_t see
         uint32_t m[6];
         if (g.ended()) { rc = -2; break; }
         legal_mask(g, m);
+        if (move_is_legal(g, (uint32_t)a) != action_is_legal(m, (uint32_t)a)) return -99;
         if (!action_is_legal(m, (uint32_t)a)) { rc = -1; break; }
         if (draws) advance<P, POOL>(g, (uint32_t)a, [&](Game<P>& gg) { new_round_injected<P, POOL>(gg, [&](int k) { return (int)draws[k]; }); });
         else advance<P, POOL>(g, (uint32_t)a, [&](Game<P>& gg) { new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL); });
@@ -41,6 +42,12 @@ static int run_op(int32_t* rec, int op, int a, const int8_t* draws, uint64_t see
     case 7: { Game<P> h = g; count_score<P, POOL>(h); for (int p = 0; p < P; p++) preview[p] = (int32_t)(h.scf[p] & 0xFFFFu); break; }
     case 8: rc = is_end_of_round(g); break;
     case 9: rc = is_end_of_game(g); break;
+    case 10: {  // single-action legality test against the full mask, all action bytes
+        uint32_t m[6];
+        legal_mask(g, m);
+        for (uint32_t b = 0; b < 256; b++) rc += move_is_legal(g, b) != action_is_legal(m, b);
+        break;
+    }
     case 100: break;   // round trip
     default: return -100;
     }

@@ -218,6 +218,63 @@ def test_step_philox_matches_oracle_and_illegal_leaves_state():
         assert np.array_equal(st & 3, np.where(expect == 0, 0, np.where(expect == -1, 1, 2))), t
 
 
+def _lowest_legal_action(mask):
+    """One legal action per game from the mask words (torch, on device)."""
+    m = mask.to(torch.int64) & 0xFFFFFFFF
+    word = (m != 0).to(torch.int64).argmax(dim=0)
+    w = m.gather(0, word[None, :]).squeeze(0)
+    low = torch.zeros_like(w)
+    for b in range(30):
+        low = torch.where(((w >> b) & 1).bool() & ((w & ((1 << b) - 1)) == 0), torch.full_like(w, b), low)
+    return (30 * word + low).to(torch.uint8)
+
+
+@pytest.mark.parametrize("players,pool,n", [(2, 1, 300001), (2, 0, 299972), (4, 1, 200000), (3, 1, 150002)])
+def test_step_many_rows_per_warp(players, pool, n):
+    """azb_step on batches where every persistent warp walks many rows (queue drains in the middle of the walk,
+    staged row tiles are recycled), with ragged / 16-byte-unaligned sizes, skipped, illegal and ended games:
+    identical to the same games stepped in small separate batches, and to the oracle on a sample."""
+    seed = 77
+    eng = engine(n, players, pool, 0, seed=seed)
+    eng.rollout_random(1 + (n % 13))
+    rng = torch.Generator(device="cpu").manual_seed(n)
+    for it in range(3):
+        action = _lowest_legal_action(eng.legal_mask())
+        r = torch.rand(n, generator=rng).to(eng.device)
+        action = torch.where(r < 0.05, torch.full_like(action, 255), action)            # skipped slots
+        action = torch.where((r >= 0.05) & (r < 0.08), torch.full_like(action, 199), action)   # out of range -> illegal
+        before = eng.state.clone()
+        out = eng.step(action, None, want_preview=(it == 1))
+        after = eng.state
+        for lo, m in ((0, 1000), (n - 999, 999), (n // 2 - 7, 4096)):
+            sub = engine(m, players, pool, 0, seed=seed, game_id_base=lo, reset=False)
+            sub.state.copy_(before[:, lo:lo + m])
+            o2 = sub.step(action[lo:lo + m], None, want_preview=(it == 1))
+            assert torch.equal(sub.state, after[:, lo:lo + m]), (it, lo)
+            for key in o2:
+                assert torch.equal(o2[key], out[key][..., lo:lo + m]), (it, lo, key)
+            if lo == 0 and it < 2:
+                recs = engine_records(before[:, :m], players, pool, seed)
+                got = sub.export_records().cpu().numpy()
+                st = o2["status"].cpu().numpy()
+                act = action[:m].cpu().numpy()
+                for i in range(m):
+                    if act[i] == 255:
+                        assert np.array_equal(got[i], recs[i]) and st[i] & 3 == 0
+                        continue
+                    g = O.Game(players, pool, record=recs[i])
+                    code = g.step(int(act[i]), None, seed, i)
+                    assert np.array_equal(got[i], g.rec), (it, i)
+                    assert (st[i] & 3) == (0 if code == 0 else 1 if code == -1 else 2), (it, i)
+        assert int((out["status"] & 1).sum()) > 0
+
+
+def engine_records(state, players, pool, seed):
+    e = engine(state.shape[1], players, pool, 0, seed=seed, reset=False)
+    e.state.copy_(state)
+    return e.export_records().cpu().numpy()
+
+
 def test_observe_matches_reference_layout():
     """GameRunner.get_state (game_runner.py:56-72) rebuilt with numpy from exported records."""
     for players in (2, 3, 4):

@@ -166,6 +166,8 @@ def test_packed_rules_random_boards():
             rec = fz[k + "_before"][i].astype(np.int32).copy()
             rc, m, _ = H.op(rec, players, pool, H.OP_ROUNDTRIP, want_mask=True)
             assert rc == 0 and np.array_equal(m, fz[k + "_mask"][i]), (k, i)
+            # the single-action legality test of the step kernel agrees with the mask for all 256 action bytes
+            assert H.op(rec.copy(), players, pool, H.OP_LEGAL_SINGLE)[0] == 0, (k, i)
             sc = rec.copy()
             assert H.op(sc, players, pool, H.OP_SCORE)[0] == 0
             assert np.array_equal(sc, fz[k + "_scored"][i].astype(np.int32)), (k, i)
