@@ -48,16 +48,21 @@ constexpr int W2_BYTES = K2_CHUNKS * N2_GROUPS * 128;        //  73,728
 constexpr int A_BYTES = K2_CHUNKS * M_GROUPS * 128;          //  49,152 (layer-2 A; layer-1 A aliases its start)
 constexpr int OFF_W1 = 0;
 constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
-constexpr int OFF_VEC = OFF_W2 + W2_BYTES;                    // fp32 vectors: b1[368] (actor 0..179, critic 180..359) w2c[192] b2a[192] b2c[1] pad[3]
-constexpr int VEC_FLOATS = N1 + 192 + N2 + 4;
+constexpr int OFF_VEC = OFF_W2 + W2_BYTES;                    // fp32 vectors: w2c[192] b2c[1] pad[3]
+constexpr int VEC_FLOATS = 192 + 4;
 constexpr int PACKED_BYTES = OFF_VEC + VEC_FLOATS * 4;        // what azb_policy_pack_weights produces
 constexpr int OFF_A = (PACKED_BYTES + 127) / 128 * 128;
 constexpr int OFF_BAR = OFF_A + A_BYTES;                      // 2 mbarriers + tmem base
 constexpr int SMEM_BYTES = OFF_BAR + 32;
 static_assert(SMEM_BYTES <= 232448, "policy kernel exceeds the 227 KB shared memory of an SM");
 
-constexpr int V_B1 = 0, V_W2C = N1, V_B2A = N1 + 192, V_B2C = N1 + 192 + N2;
-static_assert(OFF_VEC % 16 == 0 && (V_B1 + HID) % 4 == 0 && V_W2C % 4 == 0 && V_B2A % 4 == 0, "vectors must allow 128-bit loads");
+constexpr int V_W2C = 0, V_B2C = 192;
+static_assert(OFF_VEC % 16 == 0 && V_W2C % 4 == 0, "vectors must allow 128-bit loads");
+// The biases ride in the MMAs: the observation carries two constant-one inputs (columns OBS, OBS + 1 of the zero
+// padding) whose W1 rows hold the bf16 high and low halves of b1 (16 mantissa bits: error <= 2^-17 |b|), and the
+// hidden tile carries two constant-one units (columns HID, HID + 1) whose W2 rows hold the halves of b2_actor.
+constexpr int BIAS_K1 = OBS, BIAS_K2 = HID;
+static_assert(BIAS_K1 + 2 <= K1 && BIAS_K2 + 2 <= K2, "no padding column left for the bias inputs");
 
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -146,6 +151,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&p);
 }
+// 2^x on the SFU (flush-to-zero: no denormal fix-up code around it); exp(a - b) = ex2(fma(a, LOG2E, -b * LOG2E))
+__device__ __forceinline__ float ex2f(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+
 // exact float of a small non-negative integer without the conversion pipe
 __device__ __forceinline__ float small_int_to_float(uint32_t n) { return __uint_as_float(0x4B000000u | n) - 8388608.0f; }
 
@@ -179,6 +193,8 @@ __device__ __forceinline__ float obs_value(const Game<2>& g, uint32_t pat_me, ui
     } else if constexpr (IDX == 135) {                // next first player seen from this seat (game_runner.py:58-61)
         const int nf = (int)g.next_first_player();
         return nf > 0 ? small_int_to_float((uint32_t)(((nf - 1 - persp) & 1) + 1)) : 0.0f;
+    } else if constexpr (IDX == BIAS_K1 || IDX == BIAS_K1 + 1) {
+        return 1.0f;                                  // bias inputs (see BIAS_K1)
     } else {
         return 0.0f;
     }
@@ -318,7 +334,7 @@ __device__ __forceinline__ RowPart load_part(const float* parts, int slot)
     return rp;
 }
 
-template <int POOL>
+template <int POOL, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -354,6 +370,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches TMEM lanes 32*(warp%4)..+31
+    // The critic head reads 16-column chunks up to column HID + 191 = 371; layer 1 writes [0, 368).  Zero the tail once so
+    // that the (zero-weight) products of those columns are 0 and not NaN.
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(tmem_row + N1), "r"(0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
     const uint32_t w1_addr = smem_u32(smem + OFF_W1), w2_addr = smem_u32(smem + OFF_W2), a_addr = smem_u32(a_tile);
     const Philox rng{A.k0, A.k1};
@@ -404,9 +424,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         // ---- epilogue 1: actor hidden -> relu -> bf16 -> shared memory (layer-2 A operand, aliases the obs tile) ----
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
-            float v[16], bb[16];
-            tmem_ld16(tmem_row + c0, v);
-            ld16f(vec + V_B1 + c0, bb);
+            float v[16];
+            tmem_ld16(tmem_row + c0, v);                               // b1 is already in the accumulator (BIAS_K1)
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 uint4 o;
@@ -414,8 +433,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int j = c0 + 8 * q + 2 * e;                  // hidden unit (even, so j and j + 1 are both < or >= 180)
-                    ow[e] = j < HID ? pack_bf16(fmaxf(v[8 * q + 2 * e] + bb[8 * q + 2 * e], 0.0f),
-                                                fmaxf(v[8 * q + 2 * e + 1] + bb[8 * q + 2 * e + 1], 0.0f)) : 0u;
+                    ow[e] = j < HID ? pack_bf16(fmaxf(v[8 * q + 2 * e], 0.0f), fmaxf(v[8 * q + 2 * e + 1], 0.0f))
+                                    : (j == BIAS_K2 ? 0x3F803F80u : 0u);   // the two constant-one units that carry b2
                 }
                 *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = o;
             }
@@ -424,13 +443,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         float value_p = 0.0f;
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {      // critic hidden unit u lives in TMEM column 180 + u
-            float v[16], bb[16], ww[16];
+            float v[16], ww[16];
             tmem_ld16(tmem_row + HID + c0, v);
-            ld16f(vec + V_B1 + HID + c0, bb);
             ld16f(vec + V_W2C + c0, ww);
 #pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (c0 + i < HID) value_p = fmaf(fmaxf(v[i] + bb[i], 0.0f), ww[i], value_p);
+            for (int i = 0; i < 16; i++) value_p = fmaf(fmaxf(v[i], 0.0f), ww[i], value_p);   // w2c is zero beyond unit 179
         }
         fence_async_smem();
         tc_fence_before();
@@ -457,36 +474,42 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         linear_mask(m, lin);
         const uint64_t mybits = mask_window(lin, col0);
         // online softmax statistics over this part's legal logits, one 16-column chunk at a time and without
-        // per-column branches (32 different games share a warp): chunk maximum first, one rescale, then the sum
+        // per-column branches (32 different games share a warp): chunk maximum first, one rescale, then the sum.
+        // The chunk sums (relative to the running maximum at that chunk) are kept for the sampling step.
         float mx = -INFINITY, se = 0.0f, sl = 0.0f;
+        float cs[3], cms[3];
         int amax = 0;
-#pragma unroll 1
-        for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
-            float v[16], bb[16];
-            tmem_ld16(tmem_row + c0, v);
-            ld16f(vec + V_B2A + c0, bb);
-            const uint32_t bits = (uint32_t)(mybits >> (c0 - col0)) & 0xFFFFu;
+#pragma unroll
+        for (int c = 0; c < PART_COLS / 16; c++) {
+            const int c0 = col0 + 16 * c;
+            float v[16];
+            tmem_ld16(tmem_row + c0, v);                               // b2 is already in the accumulator (BIAS_K2)
+            const uint32_t bits = (uint32_t)(mybits >> (16 * c)) & 0xFFFFu;
             if (A.logits_out && valid) {
 #pragma unroll
                 for (int i = 0; i < 16; i++)
-                    if (c0 + i < ACT) A.logits_out[g * ACT + c0 + i] = v[i] + bb[i];
+                    if (c0 + i < ACT) A.logits_out[g * ACT + c0 + i] = v[i];
             }
             float cm = -INFINITY;
             int ci = 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const bool legal = (bits >> i) & 1u;
-                const float l = v[i] + bb[i];
+                const float l = v[i];
                 v[i] = legal ? l : -INFINITY;
                 sl += legal ? l : 0.0f;
-                if (v[i] > cm) { cm = v[i]; ci = i; }
+                if (MODE == 1) { if (v[i] > cm) { cm = v[i]; ci = i; } }      // argmax mode tracks the index
+                else cm = fmaxf(cm, v[i]);
             }
-            amax = cm > mx ? c0 + ci : amax;
+            if (MODE == 1) amax = cm > mx ? c0 + ci : amax;
             const float nm = fmaxf(mx, cm);
-            const float ms = nm == -INFINITY ? 0.0f : nm;          // no legal action so far: every term below is exp(-inf) = 0
-            se *= __expf(mx - ms);
+            const float ms = nm == -INFINITY ? 0.0f : nm;          // no legal action so far: every term below is 2^-inf = 0
+            const float ms2 = ms * LOG2E;
+            float sum = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 16; i++) se += __expf(v[i] - ms);
+            for (int i = 0; i < 16; i++) sum += ex2f(fmaf(v[i], LOG2E, -ms2));
+            se = se * ex2f(fmaf(mx, LOG2E, -ms2)) + sum;
+            cs[c] = sum; cms[c] = ms;
             mx = nm;
         }
         {
@@ -516,15 +539,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 #pragma unroll
         for (int q = 0; q < PARTS; q++) {
             const RowPart rp = load_part(parts, q * TILE_M + row);
-            wq[q] = rp.n > 0 ? rp.s * __expf(rp.m - gmx) : 0.0f;
+            wq[q] = rp.n > 0 ? rp.s * ex2f((rp.m - gmx) * LOG2E) : 0.0f;
             if (rp.n > 0) last_part = q;
             if (q < part) prefix += wq[q];
             gse += wq[q];
         }
         const float lse = gmx + __logf(gse);
-        if (A.mode == 0) {
-            // inverse-CDF sampling with one Philox word (agent.py:69 np.random.choice(p = policy)).  tcgen05.ld is
-            // warp-collective, so every lane runs the loop; only the owning part does arithmetic.
+        if (MODE == 0) {
+            // inverse-CDF sampling with one Philox word (agent.py:69 np.random.choice(p = policy)): the part that owns the
+            // target, then the 16-column chunk inside it (from the chunk sums), then a branch-free scan of that chunk only.
+            // tcgen05.ld is warp-collective and the chunk differs from lane to lane, so every lane loads its three chunks
+            // and keeps the one it needs by selects.
             uint32_t w[4];
             rng(A.gid0 + (uint32_t)gl, gm.steps >> 2, PURPOSE_POLICY, 0u, w);
             const uint32_t idx = gm.steps & 3u;
@@ -539,28 +564,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             }
             if (owner < 0) owner = last_part;
             const bool mine = owner == part && n_valid > 0;
-            float cum = prefix;
-            bool found = false;
-            int chosen = -1;
-            float chosen_l = 0.0f;
-#pragma unroll 1
-            for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
-                float v[16], bb[16];
-                tmem_ld16(tmem_row + c0, v);
-                ld16f(vec + V_B2A + c0, bb);
-                const uint32_t bits = (uint32_t)(mybits >> (c0 - col0)) & 0xFFFFu;
+            const float gm2 = (n_valid > 0 ? gmx : 0.0f) * LOG2E;
+            // chunk k: the first whose cumulative weight passes the target; `base` = weight before it (<= target)
+            float wc[3];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (mine && ((bits >> i) & 1u) && !found) {
-                        const float l = v[i] + bb[i];
-                        cum += __expf(l - gmx);
-                        chosen = c0 + i;                     // rounding may leave cum <= target: then the part's last legal action
-                        chosen_l = l;
-                        if (cum > target) found = true;
-                    }
-                }
+            for (int c = 0; c < 3; c++) wc[c] = cs[c] * ex2f(fmaf(cms[c], LOG2E, -gm2));
+            int k = -1;
+            float base = prefix, acc = prefix;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float nacc = acc + wc[c];
+                const bool hit = k < 0 && target < nacc;
+                base = hit ? acc : base;
+                k = hit ? c : k;
+                acc = nacc;
             }
-            if (mine) result[row] = make_int2(chosen, __float_as_int(chosen_l));
+            if (k < 0) {                                   // rounding left the target beyond the part: its last legal chunk
+                k = (mybits >> 32) ? 2 : ((mybits >> 16) & 0xFFFFull) ? 1 : 0;
+                base = prefix + (k > 0 ? wc[0] : 0.0f) + (k > 1 ? wc[1] : 0.0f);
+            }
+            float vs[16];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float v[16];
+                tmem_ld16(tmem_row + col0 + 16 * c, v);
+                const bool take = c == 0 || c == k;
+#pragma unroll
+                for (int i = 0; i < 16; i++) vs[i] = take ? v[i] : vs[i];
+            }
+            const uint32_t kb = (uint32_t)(mybits >> (16 * k)) & 0xFFFFu;
+            float cum = base, chosen_l = 0.0f;
+            int chosen = -1;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const bool legal = (kb >> i) & 1u;
+                const bool upd = legal && cum <= target;   // rounding may leave cum <= target to the end: then the chunk's last legal action
+                chosen = upd ? i : chosen;
+                chosen_l = upd ? vs[i] : chosen_l;
+                cum += ex2f(legal ? fmaf(vs[i], LOG2E, -gm2) : -INFINITY);      // 2^-inf = 0: no branch around the SFU op
+            }
+            if (mine && chosen >= 0) result[row] = make_int2(col0 + 16 * k + chosen, __float_as_int(chosen_l));
         }
         tc_fence_before();
         __syncthreads();
@@ -569,7 +612,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         if (part == 0) {
             uint32_t action = (uint32_t)gamax;
             float la = gmx;                             // argmax mode, and the fallback if rounding left no part a winner
-            if (A.mode == 0) {
+            if (MODE == 0) {
                 const int2 r = result[row];
                 if (r.x >= 0) { action = (uint32_t)r.x; la = __int_as_float(r.y); }
             }
@@ -713,29 +756,47 @@ __global__ void k_pack_weights(const float* __restrict__ w1a, const float* __res
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     // one thread per bf16 element of W1 / W2, then the fp32 vectors
+    // bias b as two bf16 inputs: hi = bf16(b), lo = bf16(b - hi)
+    auto split = [](float b, bool low) {
+        const float hi = __bfloat162float(__float2bfloat16_rn(b));
+        return low ? b - hi : b;
+    };
     if (i < N1 * K1) {
         const int n = i / K1, k = i % K1;
         float v = 0.0f;
         if (k < OBS) {
             if (n < HID) v = w1a[n * OBS + k];
             else if (n < 2 * HID) v = w1c[(n - HID) * OBS + k];
+        } else if (k == BIAS_K1 || k == BIAS_K1 + 1) {
+            if (n < HID) v = split(b1a[n], k != BIAS_K1);
+            else if (n < 2 * HID) v = split(b1c[n - HID], k != BIAS_K1);
         }
         __nv_bfloat16 b = __float2bfloat16_rn(v);
         *reinterpret_cast<__nv_bfloat16*>(out + OFF_W1 + ((k >> 3) * N1_GROUPS + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2) = b;
     } else if (i < N1 * K1 + N2 * K2) {
         const int j = i - N1 * K1, n = j / K2, k = j % K2;
-        const float v = (n < ACT && k < HID) ? w2a[n * HID + k] : 0.0f;
+        float v = 0.0f;
+        if (n < ACT) {
+            if (k < HID) v = w2a[n * HID + k];
+            else if (k == BIAS_K2 || k == BIAS_K2 + 1) v = split(b2a[n], k != BIAS_K2);
+        }
         __nv_bfloat16 b = __float2bfloat16_rn(v);
         *reinterpret_cast<__nv_bfloat16*>(out + OFF_W2 + ((k >> 3) * N2_GROUPS + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2) = b;
     } else if (i < N1 * K1 + N2 * K2 + VEC_FLOATS) {
         const int j = i - N1 * K1 - N2 * K2;
         float v = 0.0f;
-        if (j < V_W2C) { if (j < HID) v = b1a[j]; else if (j < 2 * HID) v = b1c[j - HID]; }
-        else if (j < V_B2A) { if (j - V_W2C < HID) v = w2c[j - V_W2C]; }
-        else if (j < V_B2C) { if (j - V_B2A < ACT) v = b2a[j - V_B2A]; }
+        if (j < V_B2C) { if (j - V_W2C < HID) v = w2c[j - V_W2C]; }
         else if (j == V_B2C) v = b2c[0];
         reinterpret_cast<float*>(out + OFF_VEC)[j] = v;
     }
+}
+
+template <int POOL, int MODE>
+static int launch_policy(const PolicyArgs& A, int grid, cudaStream_t stream)
+{
+    AZB_CUDA(cudaFuncSetAttribute(k_policy<POOL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    k_policy<POOL, MODE><<<grid, THREADS, SMEM_BYTES, stream>>>(A);
+    return 0;
 }
 
 }  // namespace pol
@@ -776,21 +837,18 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
     A.entropy_out = entropy_out; A.done_out = done_out; A.status_out = status_out; A.mask6_out = mask6_out;
     const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-    if (h->tile_pool == AZB_POOL_LID) {
-        AZB_CUDA(cudaFuncSetAttribute(pol::k_policy<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
-        pol::k_policy<1><<<grid, pol::THREADS, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
-    } else {
-        AZB_CUDA(cudaFuncSetAttribute(pol::k_policy<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
-        pol::k_policy<0><<<grid, pol::THREADS, pol::SMEM_BYTES, (cudaStream_t)stream>>>(A);
-    }
+    int rc = 0;
+    if (h->tile_pool == AZB_POOL_LID) rc = mode == 0 ? pol::launch_policy<1, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<1, 1>(A, grid, (cudaStream_t)stream);
+    else rc = mode == 0 ? pol::launch_policy<0, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<0, 1>(A, grid, (cudaStream_t)stream);
+    if (rc) return rc;
     CHECK_LAUNCH();
     if (apply_step) {
         pol::FinishArgs F;
         F.state = state; F.n = h->n_games; F.k0 = A.k0; F.k1 = A.k1; F.gid0 = A.gid0; F.first_rule = h->first_player;
         F.auto_reset = apply_step == 2; F.done_out = done_out; F.status_out = status_out; F.counters = counters;
         const int64_t rows = (h->n_games + 31) / 32;
-        // rows of 32 games per warp (tunable with AZB_FINISH_ROWS): more rows fill the queue better, fewer rows finish sooner
-        static const int rows_per_warp = [] { const char* e = getenv("AZB_FINISH_ROWS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+        // rows of 32 games per warp: more rows fill the queue better, fewer rows finish sooner (4 measured best)
+        constexpr int rows_per_warp = 4;
         int64_t blocks = (rows + STEP_WARPS * rows_per_warp - 1) / (STEP_WARPS * rows_per_warp);
         const int64_t resident = (int64_t)h->sm_count * 4;
         if (blocks > resident) blocks = resident;

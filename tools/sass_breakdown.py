@@ -44,9 +44,15 @@ def main():
             lines.append((curfile, cur))
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv"], text=True)
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr = rows[1]
+    # the page holds one section per profiled launch ("Kernel Name" row, header row, one row per instruction):
+    # take the first section of the wanted kernel
+    want = re.sub(r"I?L?i(\d+)E?", "", kname).split("I")[0].lstrip("_Z0123456789")
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    sec = next(((a, b) for a, b in zip(starts, starts[1:]) if want in rows[a][1] and b - a - 2 == len(lines)), None)
+    assert sec, ("no section of %d instructions for %s" % (len(lines), want), [(rows[a][1][:40], b - a - 2) for a, b in zip(starts, starts[1:])])
+    hdr = rows[sec[0] + 1]
     idx = {h: i for i, h in enumerate(hdr)}
-    data = rows[2:]
+    data = rows[sec[0] + 2:sec[1]]
     assert len(data) == len(lines), (len(data), len(lines), "rebuild the library at the profiled commit")
     src = {}
     for fn in os.listdir(CSRC):
@@ -62,16 +68,17 @@ def main():
                 name = m.group(1)
         return name
 
+    by_line = os.environ.get("BY_LINE")          # BY_LINE=azb_policy.cu: group that file's instructions by source line
     I, S, T = defaultdict(float), defaultdict(float), defaultdict(float)
     for (f, ln), r in zip(lines, data):
-        k = func_of(f, ln)
+        k = "%s:%d %s" % (f, ln, src[f][ln - 1].strip()[:60]) if by_line and f == by_line else func_of(f, ln)
         I[k] += float(r[idx["Instructions Executed"]] or 0)
         T[k] += float(r[idx["Thread Instructions Executed"]] or 0)
         S[k] += float(r[idx["Warp Stall Sampling (All Samples)"]] or 0)
     ti, ts = sum(I.values()), sum(S.values())
     print("%-28s %7s %7s %6s %10s" % ("function", "inst%", "stall%", "lanes", "inst/unit"))
-    for k in sorted(I, key=I.get, reverse=True)[:24]:
-        print("%-28s %6.1f%% %6.1f%% %6.1f %10.1f" % (k[:28], 100 * I[k] / ti, 100 * S[k] / ts, T[k] / max(I[k], 1), I[k] / units))
+    for k in sorted(I, key=I.get, reverse=True)[:60 if by_line else 24]:
+        print("%-28s %6.1f%% %6.1f%% %6.1f %10.1f" % (k if by_line else k[:28], 100 * I[k] / ti, 100 * S[k] / ts, T[k] / max(I[k], 1), I[k] / units))
     print("total instructions per unit: %.1f" % (ti / units))
 
 
