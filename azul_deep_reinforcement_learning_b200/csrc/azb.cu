@@ -5,6 +5,7 @@
 // 32 consecutive words per state word), and all rule arithmetic is SWAR on bit-planes
 // (azb_rules.cuh).  The path is integer work bounded by HBM traffic for the single-step entry
 // points and by the issue rate for the fused K-step rollout; there is nothing GEMM-shaped here.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -412,27 +413,34 @@ __global__ void k_export(const uint32_t* __restrict__ s, int32_t* __restrict__ r
 }
 
 // GameRunner.get_state (game_runner.py:56-72)
-template <int P>
-__global__ void k_observe(const uint32_t* __restrict__ s, int64_t n, int perspective, float* __restrict__ obs)
+__device__ __forceinline__ void obs_store(float* o, int i, float v) { o[i] = v; }
+__device__ __forceinline__ void obs_store(__nv_bfloat16* o, int i, float v) { o[i] = __float2bfloat16_rn(v); }
+
+// One warp per block and 32 games per warp: every thread builds its game's row in shared memory ([game][D + 1]), then the
+// warp copies the 32 rows -- contiguous in the output -- with coalesced stores (a thread writing its own row directly
+// touches 32 different sectors per store instruction).
+template <int P, typename T>
+__global__ void __launch_bounds__(32) k_observe(const uint32_t* __restrict__ s, int64_t n, int perspective, T* __restrict__ obs_out)
 {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= n) return;
     constexpr int D = 32 + 52 * P;
+    __shared__ T tile[32 * (D + 1)];
+    const int lane = threadIdx.x;
+    const int64_t g0 = (int64_t)blockIdx.x * 32, g = g0 + lane;
     Game<P> gm;
-    gm.load(s, n, g);
-    float* o = obs + g * D;
+    gm.load(s, n, g < n ? g : n - 1);
+    T* o = tile + lane * (D + 1);
     const int persp = perspective >= 0 ? perspective : gm.seat();
     for (int i = 0; i < 5; i++)
         for (int c = 0; c < 5; c++) {
             const uint32_t b = (uint32_t)(i + 1 + 6 * c);
-            o[i * 5 + c] = (float)(((gm.pl0 >> b) & 1u) | (((gm.pl1 >> b) & 1u) << 1) | (((gm.pl2 >> b) & 1u) << 2));
+            obs_store(o, i * 5 + c, (float)(((gm.pl0 >> b) & 1u) | (((gm.pl1 >> b) & 1u) << 1) | (((gm.pl2 >> b) & 1u) << 2)));
         }
     for (int c = 0; c < 5; c++) {
         const uint32_t b = (uint32_t)(6 * c);
-        o[25 + c] = (float)(((gm.pl0 >> b) & 1u) | (((gm.pl1 >> b) & 1u) << 1) | (((gm.pl2 >> b) & 1u) << 2) |
-                            (((gm.misc >> c) & 1u) << 3));
+        obs_store(o, 25 + c, (float)(((gm.pl0 >> b) & 1u) | (((gm.pl1 >> b) & 1u) << 1) | (((gm.pl2 >> b) & 1u) << 2) |
+                            (((gm.misc >> c) & 1u) << 3)));
     }
-    o[30] = (float)((gm.misc >> 5) & 1u);
+    obs_store(o, 30, (float)((gm.misc >> 5) & 1u));
     // order = [perspective] + ascending others (game_runner.py:57)
 #pragma unroll
     for (int slot = 0; slot < P; slot++) {
@@ -441,15 +449,24 @@ __global__ void k_observe(const uint32_t* __restrict__ s, int64_t n, int perspec
         for (int r = 0; r < 5; r++) {
             const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, col = (pat >> (6 * r)) & 7u;
             for (int c = 0; c < 5; c++) {
-                o[31 + 25 * slot + 5 * r + c] = (float)((cnt && col == (uint32_t)c) ? cnt : 0u);
-                o[31 + 25 * P + 25 * slot + 5 * r + c] = (float)((wall >> (5 * r + c)) & 1u);
+                obs_store(o, 31 + 25 * slot + 5 * r + c, (float)((cnt && col == (uint32_t)c) ? cnt : 0u));
+                obs_store(o, 31 + 25 * P + 25 * slot + 5 * r + c, (float)((wall >> (5 * r + c)) & 1u));
             }
         }
-        o[31 + 50 * P + slot] = (float)((scf >> 16) & 7u);
-        o[31 + 51 * P + slot] = (float)(scf & 0xFFFFu);
+        obs_store(o, 31 + 50 * P + slot, (float)((scf >> 16) & 7u));
+        obs_store(o, 31 + 51 * P + slot, (float)(scf & 0xFFFFu));
     }
     const int nf = (int)gm.next_first_player();
-    o[31 + 52 * P] = nf > 0 ? (float)(((nf - 1 - persp) % P + P) % P + 1) : 0.0f;     // game_runner.py:58-61
+    obs_store(o, 31 + 52 * P, nf > 0 ? (float)(((nf - 1 - persp) % P + P) % P + 1) : 0.0f);     // game_runner.py:58-61
+    __syncwarp();
+    const int64_t rows = n - g0 < 32 ? n - g0 : 32;
+    T* out = obs_out + g0 * D;
+    int row = 0, col = lane;
+    for (int64_t idx = lane; idx < rows * D; idx += 32) {
+        out[idx] = tile[row * (D + 1) + col];
+        col += 32;
+        if (col >= D) { col -= D; row++; }
+    }
 }
 
 // Azul.get_statistics raw integers (azul.py:314-315)
@@ -738,7 +755,18 @@ int azb_observe(azb_t* h, const uint32_t* state, int perspective, float* obs, vo
     CHECK_HANDLE(h);
     if (!state || !obs) return azb_fail(AZB_E_INVALID, "null buffer%s");
     if (perspective < -1 || perspective >= h->players) return azb_fail(AZB_E_INVALID, "perspective out of range%s");
-    DISPATCH_P(h, (k_observe<P><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(state, h->n_games, perspective, obs)));
+    DISPATCH_P(h, (k_observe<P, float><<<dim3((unsigned)((h->n_games + 31) / 32)), 32, 0, (cudaStream_t)stream>>>(state, h->n_games, perspective, obs)));
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_observe_bf16(azb_t* h, const uint32_t* state, int perspective, void* obs_bf16, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !obs_bf16) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    if (perspective < -1 || perspective >= h->players) return azb_fail(AZB_E_INVALID, "perspective out of range%s");
+    DISPATCH_P(h, (k_observe<P, __nv_bfloat16><<<dim3((unsigned)((h->n_games + 31) / 32)), 32, 0, (cudaStream_t)stream>>>(
+                      state, h->n_games, perspective, (__nv_bfloat16*)obs_bf16)));
     CHECK_LAUNCH();
     return 0;
 }

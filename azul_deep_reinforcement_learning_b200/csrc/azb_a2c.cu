@@ -1,0 +1,139 @@
+// azb_a2c.cu -- the loss of Agent.update (reference azulnet/agent.py:45-56 with the per-decision terms of
+// nn_runner.py:32-40) and its gradient with respect to the network outputs, for a batch of recorded decisions.
+//
+//   log_prob = log_softmax(masked logits)[action]            nn_runner.py:32, model.py:37-40
+//   entropy  = -mean(log_softmax over the legal actions)     nn_runner.py:36-40 (the reference's "entropy")
+//   advantage = q - value                                    agent.py:45 (NOT detached in the actor term)
+//   loss = sum_n [ actor_c * (-log_prob * advantage) + critic_c * advantage^2 + entropy_c * entropy ] * scale
+//
+// One warp per decision: the 180 logits are read once (coalesced), max / sum-exp / legal-sum are warp
+// reductions, the gradient row is written once.  HBM-bound: 2 x 720 B per decision.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "azb_internal.h"
+
+namespace a2c {
+
+constexpr int ACT = 180, PER_LANE = 6;      // columns lane, lane + 32, ...: 6 * 32 = 192 >= 180
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+struct Args {
+    int64_t n;
+    const float* __restrict__ logits;       // [n][180] raw (unmasked) actor outputs
+    const float* __restrict__ value;        // [n]
+    const uint32_t* __restrict__ mask_rows; // [n][6] legal-mask words of the decision (word p bit b <=> action 30p + b)
+    const int64_t* __restrict__ action;     // [n]
+    const float* __restrict__ qval;         // [n] discounted return
+    float scale, actor_c, critic_c, entropy_c;
+    float* __restrict__ dlogits;            // [n][180] d loss / d logits
+    float* __restrict__ dvalue;             // [n]      d loss / d value
+    double* __restrict__ sums;              // [3] += sum of (-log_prob * advantage), advantage^2, entropy (unscaled)
+};
+
+__global__ void __launch_bounds__(256) k_a2c_loss_grad(Args A)
+{
+    __shared__ double part[3][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    double acc_a = 0.0, acc_c = 0.0, acc_e = 0.0;           // lane 0 accumulates this warp's rows
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; row < A.n; row += warps_total) {
+        const float* lr = A.logits + row * ACT;
+        const uint32_t mw = lane < 6 ? A.mask_rows[row * 6 + lane] : 0u;
+        float l[PER_LANE];
+        bool legal[PER_LANE];
+        float mx = -INFINITY, sl = 0.0f;
+        int k = 0;
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) {
+            const int a = lane + 32 * j;
+            const int p = a / 30, b = a - 30 * p;
+            const uint32_t w = __shfl_sync(0xFFFFFFFFu, mw, p < 6 ? p : 0);
+            legal[j] = a < ACT && ((w >> b) & 1u);
+            l[j] = a < ACT ? lr[a] : 0.0f;
+            if (legal[j]) { mx = fmaxf(mx, l[j]); sl += l[j]; k++; }
+        }
+        mx = warp_max(mx);
+        float se = 0.0f;
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) se += legal[j] ? expf(l[j] - mx) : 0.0f;
+        se = warp_sum(se);
+        sl = warp_sum(sl);
+        k = (int)warp_sum((float)k);
+        const int act = (int)A.action[row];
+        const float v = A.value[row], q = A.qval[row];
+        float* dr = A.dlogits + row * ACT;
+        if (k == 0 || act < 0 || act >= ACT) {              // model.py:33-34 IllegalMask: such rows are never recorded
+#pragma unroll
+            for (int j = 0; j < PER_LANE; j++)
+                if (lane + 32 * j < ACT) dr[lane + 32 * j] = 0.0f;
+            if (lane == 0) A.dvalue[row] = 0.0f;
+            continue;
+        }
+        const float lse = mx + logf(se);
+        float la = 0.0f;                                    // logit of the taken action, from the lane that holds it
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) la += (lane + 32 * j == act) ? l[j] : 0.0f;
+        la = warp_sum(la);
+        const float log_prob = la - lse;
+        const float adv = q - v;
+        const float inv_k = 1.0f / (float)k;
+        const float entropy = -(sl * inv_k - lse);
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) {
+            const int a = lane + 32 * j;
+            if (a < ACT) {
+                float gj = 0.0f;
+                if (legal[j]) {
+                    const float pj = expf(l[j] - lse);
+                    // d(-log_prob * adv)/dl_j = -adv * (delta_ja - p_j);  d entropy / dl_j = p_j - 1/k
+                    gj = A.actor_c * (-adv) * ((a == act ? 1.0f : 0.0f) - pj) + A.entropy_c * (pj - inv_k);
+                }
+                dr[a] = gj * A.scale;
+            }
+        }
+        if (lane == 0) {
+            // value enters through advantage = q - value in the actor AND the critic term (agent.py:45-50)
+            A.dvalue[row] = (A.actor_c * log_prob - 2.0f * A.critic_c * adv) * A.scale;
+            acc_a += (double)(-log_prob * adv); acc_c += (double)(adv * adv); acc_e += (double)entropy;
+        }
+    }
+    if (lane == 0) { part[0][warp] = acc_a; part[1][warp] = acc_c; part[2][warp] = acc_e; }
+    __syncthreads();
+    if (threadIdx.x < 3 && A.sums) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += part[threadIdx.x][w];
+        atomicAdd(&A.sums[threadIdx.x], t);
+    }
+}
+
+}  // namespace a2c
+
+extern "C" int azb_a2c_loss_grad(azb_t* h, int64_t n, const float* logits, const float* value, const uint32_t* mask_rows,
+                                 const int64_t* action, const float* qval, float scale, float actor_coeff,
+                                 float critic_coeff, float entropy_coeff, float* dlogits, float* dvalue, double* sums,
+                                 void* stream)
+{
+    CHECK_HANDLE(h);
+    if (n < 0) return azb_fail(AZB_E_INVALID, "n < 0%s");
+    if (n == 0) return 0;
+    if (!logits || !value || !mask_rows || !action || !qval || !dlogits || !dvalue) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    a2c::Args A{n, logits, value, mask_rows, action, qval, scale, actor_coeff, critic_coeff, entropy_coeff, dlogits, dvalue, sums};
+    const int64_t blocks_needed = (n + 7) / 8;
+    const int64_t cap = (int64_t)h->sm_count * 8;
+    a2c::k_a2c_loss_grad<<<(unsigned)(blocks_needed < cap ? blocks_needed : cap), 256, 0, (cudaStream_t)stream>>>(A);
+    CHECK_LAUNCH();
+    return 0;
+}

@@ -187,6 +187,28 @@ class BatchedAzul:
         _lib.check(self.lib.azb_observe(self._h, _ptr(self.state), int(perspective), _ptr(obs), self._stream()))
         return obs
 
+    def observe_bf16(self, perspective=-1):
+        """:meth:`observe` in bfloat16 (what the policy kernel feeds its first layer; what training records)."""
+        obs = self._new((self.n_games, 32 + 52 * self.players), torch.bfloat16)
+        _lib.check(self.lib.azb_observe_bf16(self._h, _ptr(self.state), int(perspective), _ptr(obs), self._stream()))
+        return obs
+
+    def a2c_loss_grad(self, logits, value, mask_rows, action, qval, scale, coeffs, sums=None):
+        """The loss of ``Agent.update`` (agent.py:45-56) at the network outputs, and its gradient, in one kernel.
+
+        logits float32 [N,180] (raw), value float32 [N], mask_rows int32 [N,6], action int64 [N], qval float32 [N];
+        ``coeffs`` = (actor, critic, entropy).  Returns (dlogits [N,180], dvalue [N]); ``sums`` (float64 [3], optional)
+        accumulates the unscaled sums of the three loss terms."""
+        n = logits.shape[0]
+        for t, dt in ((logits, torch.float32), (value, torch.float32), (mask_rows, torch.int32), (action, torch.int64), (qval, torch.float32)):
+            assert t.dtype == dt and t.is_contiguous() and t.device == self.device and t.shape[0] == n, (t.dtype, t.shape)
+        assert logits.shape == (n, N_ACTIONS) and mask_rows.shape == (n, MASK_WORDS)
+        dlogits, dvalue = torch.empty_like(logits), torch.empty_like(value)
+        _lib.check(self.lib.azb_a2c_loss_grad(self._h, n, _ptr(logits), _ptr(value), _ptr(mask_rows), _ptr(action), _ptr(qval),
+                                              float(scale), float(coeffs[0]), float(coeffs[1]), float(coeffs[2]),
+                                              _ptr(dlogits), _ptr(dvalue), _ptr(sums), self._stream()))
+        return dlogits, dvalue
+
     def stats(self):
         out = self._new((self.n_games, 10), torch.int32)
         _lib.check(self.lib.azb_stats(self._h, _ptr(self.state), _ptr(out), self._stream()))
@@ -277,3 +299,10 @@ def mask_to_bool(mask6):
     m = mask6.to(torch.int64) & 0xFFFFFFFF
     bits = (m.unsqueeze(-1) >> torch.arange(30, device=m.device)) & 1      # [6, G, 30]
     return bits.permute(1, 0, 2).reshape(m.shape[1], N_ACTIONS).bool()
+
+
+def mask_rows_to_bool(rows):
+    """int32 ``[N, 6]`` mask words (one row per decision) -> bool ``[N, 180]``; 32-bit arithmetic only (the 30 mask
+    bits never reach the sign bit)."""
+    shifts = torch.arange(30, device=rows.device, dtype=torch.int32)
+    return ((rows.unsqueeze(-1) >> shifts) & 1).reshape(rows.shape[0], N_ACTIONS).bool()

@@ -101,7 +101,7 @@ def run_episodes(runner, packed, max_decisions=160, check_every=8, record_obs=Tr
 def _one_decision(runner, packed, rec, alive, record_obs):
     """One agent decision for every game: record what ``NNRunner.run_episode`` records (nn_runner.py:27-45)."""
     if record_obs:
-        rec["obs"].append(runner.get_state().to(torch.bfloat16))
+        rec["obs"].append(runner.engine.observe_bf16(0))
     rec["mask"].append(runner.mask.clone())
     out = runner.step_policy(packed)
     acted = alive & ((out["policy_status"] & 6) == 0)         # a decision was actually taken for this game
@@ -115,33 +115,47 @@ def _one_decision(runner, packed, rec, alive, record_obs):
 
 
 class GraphedEpisodes:
-    """``run_episodes`` with its launch-bound inner loop captured once in a CUDA graph.
+    """``run_episodes`` with its launch-bound inner loop captured in CUDA graphs.
 
-    One agent decision is three small kernels plus a handful of bookkeeping ops; at 1,024 games per batch the
-    loop is bound by launch latency, not by the GPU.  The first ``decisions`` decisions of an episode batch
-    (reset included) are therefore recorded into one CUDA graph and replayed per batch; batches in which some
-    game needs more decisions continue eagerly.  Results are identical to :func:`run_episodes`."""
+    One agent decision is three small kernels plus a handful of bookkeeping ops; the loop is bound by launch
+    latency, not by the GPU.  The first ``decisions`` decisions of an episode batch (reset included) are recorded
+    into one CUDA graph, and a second graph holds ``more`` further decisions; batches in which some game is still
+    running replay the second graph until all are done (its outputs are copied out after every replay).  Results
+    are identical to :func:`run_episodes`."""
 
-    def __init__(self, runner, packed, decisions=48, record_obs=True):
-        self.runner, self.packed, self.decisions, self.record_obs = runner, packed, decisions, record_obs
+    KEYS = ("reward", "value", "logp", "entropy", "action", "active", "mask", "obs")
+
+    def __init__(self, runner, packed, decisions=48, record_obs=True, more=8):
+        self.runner, self.packed, self.decisions, self.record_obs, self.more = runner, packed, decisions, record_obs, more
         dev = runner.device
         # warm-up on a side stream (lazy CUDA initialisation must not happen during capture)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self._body(2)
+            self._body(2, None)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.rec, self.alive = self._body(decisions)
+            self.rec, self.alive = self._body(decisions, None)
+            self.mask_out = runner.mask
+        # continuation: starts from the engine's current state, the `alive` flags in self.alive_in and the legal mask
+        # in self.mask_in (both copied in before a replay: a graph reads fixed addresses)
+        self.alive_in = torch.zeros_like(self.alive)
+        self.mask_in = torch.zeros_like(self.mask_out)
+        self.graph_more = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_more, pool=self.graph.pool()):
+            runner.mask = self.mask_in
+            self.rec_more, self.alive_more = self._body(more, self.alive_in)
+            self.mask_more = runner.mask
 
-    def _body(self, decisions):
+    def _body(self, decisions, alive):
         runner = self.runner
         G, dev = runner.n_games, runner.device
-        runner.reset()
-        alive = torch.ones(G, dtype=torch.bool, device=dev)
-        rec = {k: [] for k in ("reward", "value", "logp", "entropy", "action", "active", "mask", "obs")}
+        if alive is None:
+            runner.reset()
+            alive = torch.ones(G, dtype=torch.bool, device=dev)
+        rec = {k: [] for k in self.KEYS}
         for _ in range(decisions):
             alive = _one_decision(runner, self.packed, rec, alive, self.record_obs)
         return rec, alive
@@ -149,12 +163,17 @@ class GraphedEpisodes:
     def run(self, max_decisions=160, check_every=8):
         self.graph.replay()
         rec = {k: list(v) for k, v in self.rec.items()}
-        alive = self.alive
+        alive, mask = self.alive, self.mask_out
         t = self.decisions
         while t < max_decisions and bool(alive.any()):
-            for _ in range(check_every):
-                alive = _one_decision(self.runner, self.packed, rec, alive, self.record_obs)
-            t += check_every
+            self.alive_in.copy_(alive)
+            self.mask_in.copy_(mask)
+            self.graph_more.replay()
+            for k, v in self.rec_more.items():
+                rec[k].extend(x.clone() for x in v)
+            alive, mask = self.alive_more.clone(), self.mask_more
+            t += self.more
+        self.runner.mask = mask
         out = {k: torch.stack(v) for k, v in rec.items() if v}
         out["unfinished"] = int(alive.sum())
         return out

@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from . import parallel
 from .azulnet.model import ActorCritic
-from .engine import PackedPolicy, mask_to_bool
+from .engine import PackedPolicy
 from .selfplay import BatchedGameRunner, GraphedEpisodes, discounted_returns, run_episodes
 
 ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF = 1.0, 0.5, 0.1          # agent.py:47-49
@@ -63,8 +63,9 @@ def global_count(n_local, device):
 
 class SelfPlayTrainer:
     def __init__(self, games_per_rank=1024, learning_rate=3e-4, gamma=0.99, seed=0, device=0, rank=0, world=1,
-                 rules=None, max_decisions=160, use_cuda_graph=True):
+                 rules=None, max_decisions=160, use_cuda_graph=True, tf32_update=True):
         self.rank, self.world, self.gamma, self.max_decisions = rank, world, gamma, max_decisions
+        self.tf32_update = tf32_update
         self.device = torch.device("cuda", device)
         torch.manual_seed(seed)                              # identical initial weights on every rank
         self.net = ActorCritic(136, 180).to(self.device)
@@ -103,13 +104,24 @@ class SelfPlayTrainer:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         sums = torch.zeros(3, dtype=torch.float64, device=self.device)
-        for lo in range(0, n_local, chunk):
-            idx = sel[lo:lo + chunk]
-            m = mask_to_bool(masks[idx].t().contiguous())
-            a, c, e = a2c_loss_terms(self.net, obs[idx].float(), m, action[idx], qval[idx])
-            loss = (ACTOR_COEFF * a + CRITIC_COEFF * c + ENTROPY_COEFF * e) / n_global
-            loss.backward()
-            sums += torch.stack([a.detach(), c.detach(), e.detach()]).double()
+        # The dense layers run on the tensor cores through cuBLAS (TF32: fp32 storage and accumulation, 10-bit operand
+        # mantissas -- finer than the bf16 operands the rollout's decisions were taken with); everything between the
+        # network outputs and the loss -- masked log-softmax, the three terms, their gradient -- is one kernel
+        # (azb_a2c_loss_grad), back-propagated through the layers by autograd.
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32_update
+        try:
+            for lo in range(0, n_local, chunk):
+                idx = sel[lo:lo + chunk]
+                x = obs[idx].float()
+                logits = self.net.actor_linear2(torch.relu(self.net.actor_linear1(x)))
+                value = self.net.forward_critic(x).squeeze(1)
+                dlogits, dvalue = self.runner.engine.a2c_loss_grad(
+                    logits.detach(), value.detach().contiguous(), masks[idx].contiguous(), action[idx], qval[idx],
+                    1.0 / n_global, (ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF), sums)
+                torch.autograd.backward([logits, value], [dlogits, dvalue])
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
         t0 = time.perf_counter()
         allreduce_gradients(self.params)
         self.opt.step()

@@ -580,7 +580,7 @@ def run_train(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 rollout MLP / fp32 update / u32 rules", "data": "synthetic", "config": cfg,
+            "vs_baseline": None, "dtype": "bf16 rollout MLP / tf32 update (fp32 storage) / u32 rules", "data": "synthetic", "config": cfg,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 32,
                     "note": "a training batch is end to end by construction: statistics are read back to the host every batch"},
             "gpu_launches": None, "clocks": clocks,

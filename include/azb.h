@@ -121,6 +121,10 @@ int azb_observe(azb_t* h, const uint32_t* state, int perspective, float* obs, vo
  * completed columns, completed colours (seat 0). */
 int azb_stats(azb_t* h, const uint32_t* state, int32_t* stats10, void* stream);
 
+/* azb_observe with bfloat16 output (uint16 bit patterns, [G][32 + 52P]): what the policy kernel feeds its first
+ * layer and what the training loop records per decision.  Counts <= 256 are exact in bf16. */
+int azb_observe_bf16(azb_t* h, const uint32_t* state, int perspective, void* obs_bf16, void* stream);
+
 /* The reference's public per-function entry points, batched (used by the azulnet façade):
  *   azb_move         Azul.move            azul.py:118-161 (no legality check, like the reference)
  *   azb_next_player  Azul.next_player     azul.py:177-181
@@ -168,6 +172,22 @@ int azb_policy_pack_weights(azb_t* h, const float* w1a, const float* b1a, const 
 int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int apply_step, uint8_t* action_out,
                     float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
                     uint8_t* status_out, float* logits_out, unsigned long long* counters, int act_filter, void* stream);
+
+/* ---- a19: the loss of Agent.update and its gradient at the network outputs --------------------
+ * For n recorded agent decisions (device arrays): logits float [n][180] (raw actor outputs), value float [n],
+ * mask_rows uint32 [n][6] (the legal-mask words of each decision), action int64 [n], qval float [n]
+ * (discounted returns, nn_runner.py:72-75).  Per decision, exactly as the reference:
+ *   log_prob  = log_softmax(logits with illegal = -inf)[action]          nn_runner.py:32, model.py:37-40
+ *   entropy   = -mean(log_softmax over the legal actions)                nn_runner.py:36-40
+ *   advantage = qval - value (not detached in the actor term)            agent.py:45
+ *   loss      = scale * sum(actor_coeff * -log_prob * advantage + critic_coeff * advantage^2
+ *                           + entropy_coeff * entropy)                   agent.py:47-56 (means: scale = 1/N)
+ * Writes dlogits float [n][180] = d loss / d logits, dvalue float [n] = d loss / d value, and ADDS the unscaled sums
+ * of the three terms to sums double [3] (optional).  The caller back-propagates (dlogits, dvalue) through the
+ * network (torch.autograd.backward) -- the dense layers stay in the caller's framework. */
+int azb_a2c_loss_grad(azb_t* h, int64_t n, const float* logits, const float* value, const uint32_t* mask_rows,
+                      const int64_t* action, const float* qval, float scale, float actor_coeff, float critic_coeff,
+                      float entropy_coeff, float* dlogits, float* dvalue, double* sums, void* stream);
 
 #ifdef __cplusplus
 }

@@ -134,3 +134,52 @@ def test_cuda_graph_rollout_equals_eager():
         for k in ("reward", "action", "logp", "value", "entropy"):
             assert torch.equal(eager[k][:T][act], g[k][:T][act]), (rep, k)
         assert torch.equal(a.engine.state, b.engine.state)
+
+
+def test_fused_a2c_loss_gradient_matches_autograd():
+    """azb_a2c_loss_grad (one kernel: masked log-softmax, the three terms of Agent.update, their gradient) against PyTorch
+    autograd of train.a2c_loss_terms -- the formula test_train_cpu pins to the reference's Agent.update -- on recorded
+    decisions of a real rollout.  fp32 both sides; tolerance 2e-5 of the gradient scale."""
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import PackedPolicy, mask_rows_to_bool
+    from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner, discounted_returns, run_episodes
+    from azul_deep_reinforcement_learning_b200.train import ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF, a2c_loss_terms
+    torch.manual_seed(3)
+    net = ActorCritic(136, 180).cuda()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(2.5)
+    gr = BatchedGameRunner(300, seed=8)
+    batch = run_episodes(gr, PackedPolicy(gr.engine, net))
+    act = batch["active"]
+    T, G = act.shape
+    sel = act.reshape(-1).nonzero(as_tuple=True)[0]
+    obs = batch["obs"].reshape(T * G, -1)[sel].float()
+    assert obs.dtype == torch.float32 and batch["obs"].dtype == torch.bfloat16
+    rows = batch["mask"].permute(0, 2, 1).reshape(T * G, 6)[sel].contiguous()
+    action = batch["action"].reshape(-1)[sel]
+    qval = discounted_returns(batch["reward"], act, 0.99).reshape(-1)[sel]
+    n = int(sel.numel())
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        # reference: autograd through the torch formula
+        a, c, e = a2c_loss_terms(net, obs, mask_rows_to_bool(rows), action, qval)
+        ((ACTOR_COEFF * a + CRITIC_COEFF * c + ENTROPY_COEFF * e) / n).backward()
+        want = [p.grad.clone() for p in net.parameters()]
+        net.zero_grad()
+        # fused kernel at the network outputs, autograd through the layers
+        logits = net.actor_linear2(torch.relu(net.actor_linear1(obs)))
+        value = net.forward_critic(obs).squeeze(1)
+        sums = torch.zeros(3, dtype=torch.float64, device="cuda")
+        dl, dv = gr.engine.a2c_loss_grad(logits.detach(), value.detach().contiguous(), rows, action, qval, 1.0 / n,
+                                         (ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF), sums)
+        torch.autograd.backward([logits, value], [dl, dv])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    legal = mask_rows_to_bool(rows)
+    assert float(dl[~legal].abs().max()) == 0.0                      # no gradient into illegal actions
+    for p, w in zip(net.parameters(), want):
+        assert float((p.grad - w).abs().max()) <= 2e-5 * max(1.0, float(w.abs().max())), p.shape
+    ref = torch.stack([a, c, e]).double()
+    assert float(((sums - ref).abs() / ref.abs().clamp_min(1.0)).max()) < 1e-5
