@@ -78,6 +78,51 @@ class BatchedGameRunner:
         return out
 
 
+RAW_KEYS = ("obs", "mask", "reward", "value", "logp", "entropy", "action", "status", "done")
+
+
+def _one_decision(runner, packed, rec, record_obs):
+    """One agent decision for every game; appends the raw outputs of the kernels (what ``NNRunner.run_episode``
+    records, nn_runner.py:27-45) without any per-decision bookkeeping -- see :func:`_alive_chain`."""
+    if record_obs:
+        rec["obs"].append(runner.engine.observe_bf16(0))
+    rec["mask"].append(runner.mask)          # every opponent_random call returns a new tensor: no copy needed
+    out = runner.step_policy(packed)
+    rec["reward"].append(out["reward"])
+    rec["value"].append(out["value"])
+    rec["logp"].append(out["logp"])
+    rec["entropy"].append(out["entropy"])
+    rec["action"].append(out["action"])
+    rec["status"].append(out["policy_status"])
+    rec["done"].append(out["done"])
+
+
+def _alive_chain(status, done, alive0):
+    """``active[t]`` = the game was still running when decision t was taken and a decision was taken
+    (policy status without ENDED / STUCK); a game stays alive while it acts and is not done.  Vectorised over the
+    decisions of a chunk: status, done uint8 [C, G]; alive0 bool [G].  Returns (active bool [C, G], alive bool [G])."""
+    ok = (status & 6) == 0
+    live = (ok & (done == 0)).to(torch.uint8)
+    chain = torch.cummin(live, dim=0).values.bool()                       # alive after decision t (given alive0)
+    before = torch.cat([torch.ones_like(chain[:1]), chain[:-1]])
+    return before & ok & alive0, chain[-1] & alive0
+
+
+def _finish_batch(chunks, alive):
+    out = {k: torch.cat([c[k] for c in chunks]) for k in chunks[0]}
+    out["reward"] = out["reward"].to(torch.float32)
+    out["action"] = out["action"].to(torch.int64)
+    del out["status"], out["done"]
+    out["unfinished"] = int(alive.sum())
+    return out
+
+
+def _stack_chunk(rec, alive):
+    chunk = {k: torch.stack(v) for k, v in rec.items() if v}
+    chunk["active"], alive = _alive_chain(chunk["status"], chunk["done"], alive)
+    return chunk, alive
+
+
 def run_episodes(runner, packed, max_decisions=160, check_every=8, record_obs=True):
     """``NNRunner.run_episode`` for every game of ``runner`` at once (nn_runner.py:17-47).
 
@@ -88,42 +133,28 @@ def run_episodes(runner, packed, max_decisions=160, check_every=8, record_obs=Tr
     G, dev = runner.n_games, runner.device
     runner.reset()
     alive = torch.ones(G, dtype=torch.bool, device=dev)
-    rec = {k: [] for k in ("reward", "value", "logp", "entropy", "action", "active", "mask", "obs")}
-    for t in range(max_decisions):
-        alive = _one_decision(runner, packed, rec, alive, record_obs)
-        if (t + 1) % check_every == 0 and not bool(alive.any()):
+    chunks, t = [], 0
+    while t < max_decisions:
+        rec = {k: [] for k in RAW_KEYS}
+        for _ in range(min(check_every, max_decisions - t)):
+            _one_decision(runner, packed, rec, record_obs)
+        t += check_every
+        chunk, alive = _stack_chunk(rec, alive)
+        chunks.append(chunk)
+        if not bool(alive.any()):
             break
-    out = {k: torch.stack(v) for k, v in rec.items() if v}
-    out["unfinished"] = int(alive.sum())
-    return out
-
-
-def _one_decision(runner, packed, rec, alive, record_obs):
-    """One agent decision for every game: record what ``NNRunner.run_episode`` records (nn_runner.py:27-45)."""
-    if record_obs:
-        rec["obs"].append(runner.engine.observe_bf16(0))
-    rec["mask"].append(runner.mask.clone())
-    out = runner.step_policy(packed)
-    acted = alive & ((out["policy_status"] & 6) == 0)         # a decision was actually taken for this game
-    rec["active"].append(acted)
-    rec["reward"].append(out["reward"].to(torch.float32))
-    rec["value"].append(out["value"])
-    rec["logp"].append(out["logp"])
-    rec["entropy"].append(out["entropy"])
-    rec["action"].append(out["action"].to(torch.int64))
-    return acted & ~out["done"].bool()
+    return _finish_batch(chunks, alive)
 
 
 class GraphedEpisodes:
     """``run_episodes`` with its launch-bound inner loop captured in CUDA graphs.
 
-    One agent decision is three small kernels plus a handful of bookkeeping ops; the loop is bound by launch
+    One agent decision is five small kernels (observation record, policy, round finisher, opponent loop + reward,
+    and nothing else: the bookkeeping is vectorised over the decisions afterwards); the loop is bound by launch
     latency, not by the GPU.  The first ``decisions`` decisions of an episode batch (reset included) are recorded
     into one CUDA graph, and a second graph holds ``more`` further decisions; batches in which some game is still
     running replay the second graph until all are done (its outputs are copied out after every replay).  Results
     are identical to :func:`run_episodes`."""
-
-    KEYS = ("reward", "value", "logp", "entropy", "action", "active", "mask", "obs")
 
     def __init__(self, runner, packed, decisions=48, record_obs=True, more=8):
         self.runner, self.packed, self.decisions, self.record_obs, self.more = runner, packed, decisions, record_obs, more
@@ -132,51 +163,46 @@ class GraphedEpisodes:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self._body(2, None)
+            runner.reset()
+            self._body(2)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.rec, self.alive = self._body(decisions, None)
+            runner.reset()
+            self.rec = self._body(decisions)
             self.mask_out = runner.mask
-        # continuation: starts from the engine's current state, the `alive` flags in self.alive_in and the legal mask
-        # in self.mask_in (both copied in before a replay: a graph reads fixed addresses)
-        self.alive_in = torch.zeros_like(self.alive)
+        # continuation: starts from the engine's current state and the legal mask in self.mask_in (copied in before a
+        # replay: a graph reads fixed addresses)
         self.mask_in = torch.zeros_like(self.mask_out)
         self.graph_more = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_more, pool=self.graph.pool()):
             runner.mask = self.mask_in
-            self.rec_more, self.alive_more = self._body(more, self.alive_in)
+            self.rec_more = self._body(more)
             self.mask_more = runner.mask
 
-    def _body(self, decisions, alive):
-        runner = self.runner
-        G, dev = runner.n_games, runner.device
-        if alive is None:
-            runner.reset()
-            alive = torch.ones(G, dtype=torch.bool, device=dev)
-        rec = {k: [] for k in self.KEYS}
+    def _body(self, decisions):
+        rec = {k: [] for k in RAW_KEYS}
         for _ in range(decisions):
-            alive = _one_decision(runner, self.packed, rec, alive, self.record_obs)
-        return rec, alive
+            _one_decision(self.runner, self.packed, rec, self.record_obs)
+        return {k: torch.stack(v) for k, v in rec.items() if v}
 
     def run(self, max_decisions=160, check_every=8):
+        G, dev = self.runner.n_games, self.runner.device
         self.graph.replay()
-        rec = {k: list(v) for k, v in self.rec.items()}
-        alive, mask = self.alive, self.mask_out
-        t = self.decisions
+        chunk = dict(self.rec)
+        chunk["active"], alive = _alive_chain(chunk["status"], chunk["done"], torch.ones(G, dtype=torch.bool, device=dev))
+        chunks, mask, t = [chunk], self.mask_out, self.decisions
         while t < max_decisions and bool(alive.any()):
-            self.alive_in.copy_(alive)
             self.mask_in.copy_(mask)
             self.graph_more.replay()
-            for k, v in self.rec_more.items():
-                rec[k].extend(x.clone() for x in v)
-            alive, mask = self.alive_more.clone(), self.mask_more
+            chunk = {k: v.clone() for k, v in self.rec_more.items()}
+            chunk["active"], alive = _alive_chain(chunk["status"], chunk["done"], alive)
+            chunks.append(chunk)
+            mask = self.mask_more
             t += self.more
         self.runner.mask = mask
-        out = {k: torch.stack(v) for k, v in rec.items() if v}
-        out["unfinished"] = int(alive.sum())
-        return out
+        return _finish_batch(chunks, alive)
 
 
 def discounted_returns(reward, active, gamma):

@@ -54,6 +54,20 @@ def allreduce_gradients(params):
         off += n
 
 
+def allreduce_gradients_and_stats(params, stats):
+    """C1 + C2 in ONE collective: every gradient (sums over the local decisions, not yet divided by a count) and the
+    statistics vector travel as one float64 buffer; returns the reduced statistics.  No host synchronisation."""
+    flat = torch.cat([p.grad.reshape(-1).double() for p in params] + [stats.double().reshape(-1)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat[off:]
+
+
 def global_count(n_local, device):
     t = torch.tensor([float(n_local)], dtype=torch.float64, device=device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -89,12 +103,16 @@ class SelfPlayTrainer:
         return batch
 
     def update(self, batch, chunk=1 << 18):
-        """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch."""
+        """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch.
+
+        Gradients are accumulated as SUMS over the local decisions; one all-reduce carries them together with the
+        decision count and the batch statistics, then every rank divides by the global count (the means of
+        agent.py:47-56 over the global batch) and takes the same Adam step.  The host is not synchronised before
+        the statistics are read at the end."""
         act = batch["active"]
         T, G = act.shape
         sel = act.reshape(-1).nonzero(as_tuple=True)[0]
         n_local = int(sel.numel())
-        n_global = global_count(n_local, self.device)
         obs = batch["obs"].reshape(T * G, -1)
         masks = batch["mask"].permute(0, 2, 1).reshape(T * G, 6)
         action = batch["action"].reshape(-1)
@@ -118,30 +136,30 @@ class SelfPlayTrainer:
                 value = self.net.forward_critic(x).squeeze(1)
                 dlogits, dvalue = self.runner.engine.a2c_loss_grad(
                     logits.detach(), value.detach().contiguous(), masks[idx].contiguous(), action[idx], qval[idx],
-                    1.0 / n_global, (ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF), sums)
+                    1.0, (ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF), sums)
                 torch.autograd.backward([logits, value], [dlogits, dvalue])
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
         t0 = time.perf_counter()
-        allreduce_gradients(self.params)
+        one = torch.ones(1, dtype=torch.float64, device=self.device)
+        wins = (batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum().reshape(1)
+        stats = torch.cat([one * n_local, sums, batch["reward"].double().mul(act).sum().reshape(1), one * G,
+                           batch["stats"].sum(dim=0), wins])
+        stats = allreduce_gradients_and_stats(self.params, stats)
+        inv = (1.0 / stats[0].clamp_min(1.0)).float()
+        for p in self.params:
+            p.grad.mul_(inv)
         self.opt.step()
-        stats = torch.cat([sums, batch["reward"].double().mul(act).sum().reshape(1),
-                           torch.tensor([float(G)], dtype=torch.float64, device=self.device),
-                           batch["stats"].sum(dim=0)])
-        parallel.reduce_counters(stats)
         s = stats.cpu().tolist()
-        games = s[4]
-        out = {"transitions": n_global, "games": games, "actor_loss": s[0] / n_global, "critic_loss": s[1] / n_global,
-               "entropy_loss": s[2] / n_global, "reward": s[3] / games, "update_sync_s": time.perf_counter() - t0}
+        n_global, games = max(s[0], 1.0), s[5]
+        out = {"transitions": s[0], "games": games, "actor_loss": s[1] / n_global, "critic_loss": s[2] / n_global,
+               "entropy_loss": s[3] / n_global, "reward": s[4] / games, "update_sync_s": time.perf_counter() - t0}
         out["ac_loss"] = ACTOR_COEFF * out["actor_loss"] + CRITIC_COEFF * out["critic_loss"] + ENTROPY_COEFF * out["entropy_loss"]
-        g = [x / games for x in s[5:15]]
+        g = [x / games for x in s[6:16]]
         out.update(player_score=g[0], opponent_score=g[1], rounds=g[2],
-                   percent_first_player=100.0 * s[8] / max(s[9], 1.0), floor_penalty=g[5], max_combo=g[6],
+                   percent_first_player=100.0 * s[9] / max(s[10], 1.0), floor_penalty=g[5], max_combo=g[6],
                    completed_rows=g[7], completed_columns=g[8], completed_colors=g[9])
-        win = float((batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum())
-        w = torch.tensor([win], dtype=torch.float64, device=self.device)
-        parallel.reduce_counters(w)
-        out["win_percent"] = float(w.item()) / games
+        out["win_percent"] = s[16] / games
         return out
 
     def train(self, batches=1000, net_name=None, log=print):

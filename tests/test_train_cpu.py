@@ -47,6 +47,24 @@ def test_batched_loss_equals_agent_update_formula():
         assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-5)
 
 
+def test_alive_chain_equals_the_sequential_bookkeeping():
+    """The vectorised `active` / `alive` flags of a chunk of decisions equal the per-decision recurrence
+    acted = alive & ok; alive = acted & ~done (what NNRunner.run_episode's while-loop does per game)."""
+    from azul_deep_reinforcement_learning_b200.selfplay import _alive_chain
+    g = torch.Generator().manual_seed(4)
+    C, G = 13, 257
+    status = (torch.rand(C, G, generator=g) < 0.08).to(torch.uint8) * 2 + (torch.rand(C, G, generator=g) < 0.05).to(torch.uint8) * 4
+    done = (torch.rand(C, G, generator=g) < 0.1).to(torch.uint8)
+    alive0 = torch.rand(G, generator=g) < 0.8
+    active, alive = _alive_chain(status, done, alive0)
+    a = alive0.clone()
+    for t in range(C):
+        acted = a & ((status[t] & 6) == 0)
+        assert torch.equal(active[t], acted), t
+        a = acted & ~done[t].bool()
+    assert torch.equal(alive, a)
+
+
 def test_discounted_returns():
     from azul_deep_reinforcement_learning_b200.selfplay import discounted_returns
     r = torch.tensor([[1.0, 2.0], [0.0, -1.0], [3.0, 5.0]])
@@ -61,7 +79,8 @@ def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     from azul_deep_reinforcement_learning_b200 import parallel
     from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
-    from azul_deep_reinforcement_learning_b200.train import a2c_loss_terms, allreduce_gradients, global_count
+    from azul_deep_reinforcement_learning_b200.train import (a2c_loss_terms, allreduce_gradients, allreduce_gradients_and_stats,
+                                                             global_count)
     parallel.init("gloo")
     torch.manual_seed(0)
     net = ActorCritic(136, 180)
@@ -73,6 +92,13 @@ def _worker(rank, world, port, out_dir):
     params = list(net.parameters())
     allreduce_gradients(params)
     torch.save([p.grad.clone() for p in params], os.path.join(out_dir, "grads%d.pt" % rank))
+    # the trainer's form: unscaled gradient sums + the count in ONE collective, divided afterwards
+    net.zero_grad()
+    a, c, e = a2c_loss_terms(net, obs, mask, action, qval)
+    (a + 0.5 * c + 0.1 * e).backward()
+    stats = allreduce_gradients_and_stats(params, torch.tensor([float(n), 7.0 + rank]))
+    assert stats.tolist() == [105.0, 15.0]
+    torch.save([p.grad / stats[0].float() for p in params], os.path.join(out_dir, "grads_one%d.pt" % rank))
     torch.distributed.destroy_process_group()
 
 
@@ -87,6 +113,7 @@ def test_two_rank_gradient_allreduce_matches_global_batch(tmp_path):
     a, c, e = a2c_loss_terms(net, obs, mask, action, qval)
     ref = torch.autograd.grad((a + 0.5 * c + 0.1 * e) / 105, list(net.parameters()))
     for r in range(2):
-        got = torch.load(tmp_path / ("grads%d.pt" % r))
-        for g1, g2 in zip(got, ref):
-            assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-6)
+        for name in ("grads%d.pt", "grads_one%d.pt"):
+            got = torch.load(tmp_path / (name % r))
+            for g1, g2 in zip(got, ref):
+                assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-6), name
