@@ -52,7 +52,8 @@ constexpr int OFF_VEC = OFF_W2 + W2_BYTES;                    // fp32 vectors: w
 constexpr int VEC_FLOATS = 192 + 4;
 constexpr int PACKED_BYTES = OFF_VEC + VEC_FLOATS * 4;        // what azb_policy_pack_weights produces
 constexpr int OFF_A = (PACKED_BYTES + 127) / 128 * 128;
-constexpr int OFF_BAR = OFF_A + A_BYTES;                      // 2 mbarriers + tmem base
+constexpr int OFF_BAR = OFF_A + A_BYTES;                      // 2 MMA mbarriers, tmem base (+16), weight-copy mbarrier (+24)
+static_assert(PACKED_BYTES % 16 == 0, "the weight image is moved with 16-byte-granular bulk copies");
 constexpr int SMEM_BYTES = OFF_BAR + 32;
 static_assert(SMEM_BYTES <= 232448, "policy kernel exceeds the 227 KB shared memory of an SM");
 
@@ -349,16 +350,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     if (tid < AZB_N_COUNTERS) cnt[tid] = 0ull;
     SmemSink sink{cnt};
 
-    // one-time: weights image -> shared memory, barriers, tensor memory
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(A.packed);
-        uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < PACKED_BYTES / 16; i += THREADS) dst[i] = src[i];
-    }
+    // one-time: barriers, tensor memory, and the weight image -> shared memory as bulk async copies (TMA, no registers
+    // and no thread time: the first observation tile is built while the 180 KB arrive)
+    const uint32_t bar_w = bar1 + 24;
     if (tid == 0) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"((uint32_t)PACKED_BYTES) : "memory");
+        constexpr uint32_t CHUNK = 32768;
+        for (uint32_t off = 0; off < (uint32_t)PACKED_BYTES; off += CHUNK) {
+            const uint32_t bytes = (uint32_t)PACKED_BYTES - off < CHUNK ? (uint32_t)PACKED_BYTES - off : CHUNK;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem) + off), "l"(A.packed + off), "r"(bytes), "r"(bar_w) : "memory");
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -389,6 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         nxt.load(A.state_in, A.n, g0 < A.n ? g0 : A.n - 1);
         build_obs_tile(nxt, a_tile, row, part);
     }
+    mbar_wait(bar_w, 0);                                  // weights and vectors have landed (every thread reads the vectors)
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t g = tile * TILE_M + row;
         const bool valid = g < A.n;

@@ -1,3 +1,4 @@
+"""torch.profiler tables of one training update and one rollout (16,384 episodes): python tools/profile_train.py"""
 import sys, os; sys.path.insert(0, os.getcwd())
 import torch, time
 from torch.profiler import profile, ProfilerActivity
