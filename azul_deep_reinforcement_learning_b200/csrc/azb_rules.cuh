@@ -292,11 +292,18 @@ AZB_HD void score_player(Game<P>& g, const int pl)
         wc |= (((row << r) | (row >> (5 - r))) & 31u) << (5 * r);
     }
     uint32_t combo = sta >> 28;
+    // the full lines (:216, count == row + 1), ascending: a warp walks max-over-lanes(#full lines) iterations instead
+    // of all five rows (nearly every row is full in SOME of a warp's 32 games)
+    uint32_t full = 0;
+#pragma unroll
+    for (int r = 0; r < 5; r++) full |= (((pat >> (6 * r + 3)) & 7u) == (uint32_t)(r + 1) ? 1u : 0u) << r;
     AZB_ROLLED
-    for (uint32_t r = 0; r < 5u; r++) {
+    while (full) {
+        const uint32_t r = (uint32_t)ctz(full);
+        full &= full - 1u;
         const uint32_t sh6 = 6u * r, sh5 = 5u * r;
-        const uint32_t cnt = (pat >> (sh6 + 3u)) & 7u, c = (pat >> sh6) & 7u;
-        if (cnt == r + 1u) {                                      // :216 line is full
+        const uint32_t c = (pat >> sh6) & 7u;
+        {
             pat &= ~(63u << sh6);                                 // :218
             wall |= 1u << (sh5 + c);                              // :219
             if (POOL == POOL_LID) g.lid += r << (6u * c);         // :220-222
@@ -711,10 +718,12 @@ struct InlineWords {
 // Warp-vote policies for rollout_steps: the kernels vote across the 32 games of a warp, the host
 // harness (one game at a time) votes with itself.
 struct SingleLane {
+    static constexpr int LANES = 1;
     AZB_M int count(bool p) const { return p ? 1 : 0; }
 };
 #if defined(__CUDACC__)
 struct WarpLanes {
+    static constexpr int LANES = 32;
     __device__ __forceinline__ int count(bool p) const { return __popc(__ballot_sync(0xFFFFFFFFu, p)); }
 };
 #endif
@@ -750,8 +759,9 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 else next_player(g);                                  // azul.py:313
             }
         }
-        const int n_waiting = vote.count(phase != 0);
         const int n_movable = vote.count(remaining > 0 && phase == 0);
+        // with defer = all lanes (the default) a pass can only be due when nothing can move: one vote per light step
+        const int n_waiting = (n_movable == 0 || defer < Vote::LANES) ? vote.count(phase != 0) : 0;
         if (n_waiting > 0 && (n_waiting >= defer || n_movable == 0)) {
             if (phase != 0) {
                 bool fresh = phase == 2;
