@@ -552,9 +552,15 @@ AZB_HD uint32_t random_action(const uint32_t m[6], uint32_t word)
     const uint32_t r = mulhi(word, total);
     const bool heavy = r < 100u * n_hi;
     const uint32_t kh = r / 100u;                        // rank among the heavy actions
-    const uint32_t i = (uint32_t)(kh >= e1) + (uint32_t)(kh >= e2) + (uint32_t)(kh >= e3) + (uint32_t)(kh >= e4);
-    const uint32_t before = i == 0u ? 0u : i == 1u ? e1 : i == 2u ? e2 : i == 3u ? e3 : e4;
-    const uint32_t wh = i == 0u ? m[1] : i == 1u ? m[2] : i == 2u ? m[3] : i == 3u ? m[4] : m[5];
+    // word i + 1 holds the kh-th heavy action: the thresholds are monotone, so four predicated overwrites pick the
+    // word and the rank before it (an `i == k ? ... :` chain compiles to a divergent switch)
+    const bool g1 = kh >= e1, g2 = kh >= e2, g3 = kh >= e3, g4 = kh >= e4;
+    const uint32_t i = (uint32_t)g1 + (uint32_t)g2 + (uint32_t)g3 + (uint32_t)g4;
+    uint32_t before = 0u, wh = m[1];
+    before = g1 ? e1 : before; wh = g1 ? m[2] : wh;
+    before = g2 ? e2 : before; wh = g2 ? m[3] : wh;
+    before = g3 ? e3 : before; wh = g3 ? m[4] : wh;
+    before = g4 ? e4 : before; wh = g4 ? m[5] : wh;
     const uint32_t w = heavy ? wh : m[0];
     const uint32_t k = heavy ? kh - before : r - 100u * n_hi;
     const uint32_t base = heavy ? 30u * (i + 1u) : 0u;
