@@ -517,15 +517,16 @@ AZB_HD bool action_is_legal(const uint32_t m[6], uint32_t action)
 template <int P>
 AZB_HD bool move_is_legal(const Game<P>& g, uint32_t action)
 {
-    if (action >= 180u) return false;
-    const uint32_t p = action / 30u, b = action - 30u * p, c = b / 6u;
+    // branch-free: a warp tests 32 different games
+    const uint32_t a = action < 180u ? action : 0u;
+    const uint32_t p = a / 30u, b = a - 30u * p, c = b / 6u;
     const uint32_t src = (g.pl0 | g.pl1 | g.pl2 | spread5to6(g.misc & 31u)) & PLANE_MASK;
-    if (!((src >> b) & 1u)) return false;                    // azul.py:164-169: the source holds the colour
-    if (p == 0u) return true;                                // the floor takes anything
     const int s = g.seat();
     const uint32_t pat = g.sel(g.pat, s), wall = g.sel(g.wall, s);
-    const uint32_t r = p - 1u, cnt = (pat >> (6u * r + 3u)) & 7u, col = (pat >> (6u * r)) & 7u;
-    return (cnt == 0u || col == c) && !((wall >> (5u * r + c)) & 1u);      // azul.py:171-175
+    const uint32_t r = p ? p - 1u : 0u, cnt = (pat >> (6u * r + 3u)) & 7u, col = (pat >> (6u * r)) & 7u;
+    const bool source_ok = (src >> b) & 1u;                                           // azul.py:164-169
+    const bool row_ok = ((cnt == 0u) | (col == c)) & !((wall >> (5u * r + c)) & 1u);   // azul.py:171-175
+    return (action < 180u) & source_ok & ((p == 0u) | row_ok);                        // the floor takes anything
 }
 
 // position of the k-th (0-based) set bit of a 30-bit word; k < popc(m)
