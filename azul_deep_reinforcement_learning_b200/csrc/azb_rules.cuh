@@ -364,15 +364,16 @@ AZB_HD void new_round_header(Game<P>& g)
     g.pl0 = g.pl1 = g.pl2 = 0u;                                   // :73
 }
 
-// Lid pool: the five box counts unpacked into registers for the duration of a refill
+// Lid pool: the box for the duration of a refill, held as the four cumulative counts the draw compares against
+// (e0 = box[0], e1 = box[0] + box[1], ...) and the total, so a draw updates its thresholds in place.
 struct BoxRegs {
-    uint32_t b0, b1, b2, b3, b4, total;
+    uint32_t e0, e1, e2, e3, total;
     AZB_M void unpack(uint32_t w)
     {
-        b0 = w & 63u; b1 = (w >> 6) & 63u; b2 = (w >> 12) & 63u; b3 = (w >> 18) & 63u; b4 = (w >> 24) & 63u;
-        total = b0 + b1 + b2 + b3 + b4;
+        e0 = w & 63u; e1 = e0 + ((w >> 6) & 63u); e2 = e1 + ((w >> 12) & 63u); e3 = e2 + ((w >> 18) & 63u);
+        total = e3 + ((w >> 24) & 63u);
     }
-    AZB_M uint32_t pack() const { return b0 | (b1 << 6) | (b2 << 12) | (b3 << 18) | (b4 << 24); }
+    AZB_M uint32_t pack() const { return e0 | ((e1 - e0) << 6) | ((e2 - e1) << 12) | ((e3 - e2) << 18) | ((total - e3) << 24); }
 };
 
 // Lid pool, one draw (azul.py:79-89): pour the lid into an empty box, pick colour c when the
@@ -387,12 +388,11 @@ AZB_HD int lid_draw(Game<P>& g, BoxRegs& B, uint32_t& x)
     }
     const uint32_t r = mulhi(x, B.total);
     x *= B.total;
-    const uint32_t e1 = B.b0 + B.b1, e2 = e1 + B.b2, e3 = e2 + B.b3;
-    const int c = (int)(r >= B.b0) + (int)(r >= e1) + (int)(r >= e2) + (int)(r >= e3);
-    B.b0 -= c == 0 ? 1u : 0u; B.b1 -= c == 1 ? 1u : 0u; B.b2 -= c == 2 ? 1u : 0u;
-    B.b3 -= c == 3 ? 1u : 0u; B.b4 -= c == 4 ? 1u : 0u;           // :89
+    // colour c <=> e(c-1) <= r < e(c); taking one tile of c lowers every threshold from e(c) on (:89)
+    const uint32_t g0 = r >= B.e0 ? 1u : 0u, g1 = r >= B.e1 ? 1u : 0u, g2 = r >= B.e2 ? 1u : 0u, g3 = r >= B.e3 ? 1u : 0u;
+    B.e0 += g0 - 1u; B.e1 += g1 - 1u; B.e2 += g2 - 1u; B.e3 += g3 - 1u;
     B.total -= 1u;
-    return c;
+    return (int)(g0 + g1 + g2 + g3);
 }
 
 // azul.py:64-89 with the Philox draw schedule (DESIGN.md "RNG schedule"): call j of
