@@ -84,17 +84,40 @@ struct StepOut {
     uint8_t* __restrict__ status;
 };
 
-// state (when the game moved) and the per-game outputs of azb_step
-template <int P, int POOL>
-__device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, Game<P>& gm, int64_t g, uint32_t status, bool moved)
+__device__ __forceinline__ void st_global_hint(uint32_t* dst, uint32_t v, uint64_t policy)
 {
-    if (moved) gm.store(L.state, L.n, g);
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(dst), "r"(v), "l"(policy) : "memory");
+}
+
+// state (when the game moved) and the per-game outputs of azb_step; `policy` != 0: L2 cache hint for the state and mask
+// words (the queue drain's patches are the last writes to their lines: evict first)
+template <int P, int POOL>
+__device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, Game<P>& gm, int64_t g, uint32_t status, bool moved,
+                                            uint64_t policy = 0)
+{
+    if (moved) {
+        if (policy) {
+            uint32_t w[Game<P>::WORDS];
+            gm.store(w, 1, 0);
+#pragma unroll
+            for (int i = 0; i < Game<P>::WORDS; i++) st_global_hint(L.state + i * L.n + g, w[i], policy);
+        } else {
+            gm.store(L.state, L.n, g);
+        }
+    }
     if (O.mask6 || O.status) {
         uint32_t m[6];
         legal_mask(gm, m);
         if (!gm.ended() && (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u && gm.current_player() != 0u)
             status |= ST_STUCK;
-        if (O.mask6) store_mask(O.mask6, L.n, g, m);
+        if (O.mask6) {
+            if (policy) {
+#pragma unroll
+                for (int p = 0; p < 6; p++) st_global_hint(O.mask6 + p * L.n + g, m[p], policy);
+            } else {
+                store_mask(O.mask6, L.n, g, m);
+            }
+        }
     }
     if (O.preview) {
         Game<P> cp = gm;
@@ -112,6 +135,9 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 // (no registers are held by loads in flight), read from the tile with conflict-free 4-byte shared loads, and --
 // on the aligned path -- written back through the tile with 16-byte global stores, so that a row costs
 // ceil(W/4) + 2 global store instructions instead of W + 6 and every 128-byte line is written whole.
+// games waiting in a warp's queue that trigger a pass: fuller passes cost fewer instructions, earlier passes patch lines that
+// are still in L2 (measured 16 / 20 / 24 / 28 / 32: 201 / 191 / 183 / 186 / 196 us for 4.2 M two-player games)
+constexpr int STEP_DRAIN_AT = 24;
 constexpr int STEP5_QCAP = 48;           // a row that would overflow the queue drains it first
 constexpr int STEP5_WARPS = 2;           // warps per block (fine-grained shared-memory occupancy)
 
@@ -129,6 +155,29 @@ __device__ __forceinline__ void cp_async16(uint32_t* smem_dst, const uint32_t* g
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+// L2 residency hints: a row's lines are read once, rewritten whole a few rows later and -- for the games whose round
+// ended -- patched once more when their warp's queue drains; keeping the rewritten lines in L2 until then avoids
+// partial-sector writes to lines that already left for DRAM.
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t* smem_dst, const uint32_t* gsrc, uint64_t policy)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_global_v4_hint(uint32_t* dst, const uint4& v, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -144,14 +193,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // lane are 4 words apart: `lane_off` = (l >> 3) * n + 4 * (l & 7) is fixed per thread and `n4` = 4 * n steps to the next.
 template <int LINES>
 __device__ __forceinline__ void row_fetch(uint32_t* tile, const uint32_t* __restrict__ s, const uint8_t* __restrict__ action,
-                                          int64_t n, int64_t g0, int lane, bool fast, int64_t lane_off, int64_t n4)
+                                          int64_t n, int64_t g0, int lane, bool fast, int64_t lane_off, int64_t n4, uint64_t policy)
 {
     if (fast) {
         const uint32_t* src = s + lane_off + g0;
         uint32_t* dst = tile + 4 * lane;
 #pragma unroll
         for (int k = 0; k < (LINES * 8 + 31) / 32; k++, src += n4, dst += 128)
-            if (32 * k + 32 <= LINES * 8 || lane < LINES * 8 - 32 * k) cp_async16(dst, src);
+            if (32 * k + 32 <= LINES * 8 || lane < LINES * 8 - 32 * k) cp_async16_hint(dst, src, policy);
         if (lane < 2) cp_async16(tile + LINES * 32 + 4 * lane, reinterpret_cast<const uint32_t*>(action + g0) + 4 * lane);
     } else if (g0 + lane < n) {
 #pragma unroll
@@ -160,13 +209,13 @@ __device__ __forceinline__ void row_fetch(uint32_t* tile, const uint32_t* __rest
 }
 // tile [word][32] -> global [word][n], 16 bytes per lane (aligned, full rows only)
 template <int LINES>
-__device__ __forceinline__ void row_flush(const uint32_t* tile, uint32_t* __restrict__ s, int64_t g0, int lane, int64_t lane_off, int64_t n4)
+__device__ __forceinline__ void row_flush(const uint32_t* tile, uint32_t* __restrict__ s, int64_t g0, int lane, int64_t lane_off, int64_t n4, uint64_t policy)
 {
     uint32_t* dst = s + lane_off + g0;
     const uint32_t* src = tile + 4 * lane;
 #pragma unroll
     for (int k = 0; k < (LINES * 8 + 31) / 32; k++, dst += n4, src += 128)
-        if (32 * k + 32 <= LINES * 8 || lane < LINES * 8 - 32 * k) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        if (32 * k + 32 <= LINES * 8 || lane < LINES * 8 - 32 * k) st_global_v4_hint(dst, *reinterpret_cast<const uint4*>(src), policy);
 }
 
 template <int P, int POOL, int STAGES>
@@ -184,6 +233,7 @@ __global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const ui
     const int64_t warps_total = (int64_t)gridDim.x * STEP5_WARPS;
     const Philox rng{L.k0, L.k1};
     int waiting = 0;                                        // warp-uniform: entries in this warp's queue
+    const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
 
     auto drain = [&](int count) {                           // finish `count` (<= 32) games from the tail of the queue
         if (lane < count) {
@@ -199,7 +249,7 @@ __global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const ui
             } else {
                 new_round_philox<P, POOL>(h, rng, L.gid0 + gidx, PURPOSE_REFILL);
             }
-            step_finish<P, POOL>(L, O, h, (int64_t)gidx, st, true);
+            step_finish<P, POOL>(L, O, h, (int64_t)gidx, st, true, pol_first);
         }
         waiting -= count;
         __syncwarp();
@@ -212,7 +262,7 @@ __global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const ui
 #pragma unroll
     for (int k = 0; k < STAGES - 1; k++) {
         const int64_t r = row0 + k * warps_total;
-        if (r < n_rows) row_fetch<W>(tiles + k * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4);
+        if (r < n_rows) row_fetch<W>(tiles + k * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4, pol_first);
         cp_async_commit();
     }
     int stage = 0;
@@ -225,7 +275,7 @@ __global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const ui
             __syncwarp();
             const int64_t r = row + (STAGES - 1) * warps_total;
             const int st_fill = stage == 0 ? STAGES - 1 : stage - 1;
-            if (r < n_rows) row_fetch<W>(tiles + st_fill * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4);
+            if (r < n_rows) row_fetch<W>(tiles + st_fill * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4, pol_first);
             cp_async_commit();
         }
         cp_async_wait<STAGES - 1>();
@@ -267,8 +317,8 @@ __global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const ui
                 for (int p = 0; p < 6; p++) mask_tile[32 * p + lane] = m[p];
             }
             __syncwarp();
-            if (any_moved) row_flush<W>(tile, L.state, row * 32, lane, lane_off, n4);
-            if (O.mask6) row_flush<6>(mask_tile, O.mask6, row * 32, lane, lane_off, n4);
+            if (any_moved) row_flush<W>(tile, L.state, row * 32, lane, lane_off, n4, pol_last);
+            if (O.mask6) row_flush<6>(mask_tile, O.mask6, row * 32, lane, lane_off, n4, pol_last);
             if (!round_over) {
                 if (O.preview) {
                     Game<P> cp = gm;
@@ -288,7 +338,7 @@ __global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const ui
             if (round_over) queue_put<P, QCAP>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
             waiting += __popc(over);
             __syncwarp();
-            if (waiting >= 32) drain(32);
+            if (waiting >= STEP_DRAIN_AT) drain(waiting < 32 ? waiting : 32);
         }
         stage = stage + 1 == STAGES ? 0 : stage + 1;
     }
@@ -576,7 +626,7 @@ template <int P, int POOL>
 static int launch_step(const azb_t* h, const Launch& L, const uint8_t* action, const int8_t* draws, const StepOut& O,
                        int aligned, cudaStream_t stream)
 {
-    constexpr int STAGES = P == 2 ? 4 : 3;       // measured: 2 / 3 / 4 stages = 244 / 240 / 229 us for 4.2 M two-player games
+    constexpr int STAGES = P == 2 ? 4 : 3;       // 2 / 3 / 4 / 5 stages: 183 / 192 / 183 / 198 us for 4.2 M two-player games       // measured: 2 / 3 / 4 stages = 244 / 240 / 229 us for 4.2 M two-player games
     auto kern = k_step<P, POOL, STAGES>;
     const size_t smem = StepSmem<P, STAGES>::bytes(STEP5_WARPS);
     static thread_local int per_sm_cached[64] = {0};      // function attributes are per device
