@@ -626,7 +626,7 @@ template <int P, int POOL>
 static int launch_step(const azb_t* h, const Launch& L, const uint8_t* action, const int8_t* draws, const StepOut& O,
                        int aligned, cudaStream_t stream)
 {
-    constexpr int STAGES = P == 2 ? 4 : 3;       // 2 / 3 / 4 / 5 stages: 183 / 192 / 183 / 198 us for 4.2 M two-player games       // measured: 2 / 3 / 4 stages = 244 / 240 / 229 us for 4.2 M two-player games
+    constexpr int STAGES = P == 2 ? 4 : 3;       // 2 / 3 / 4 / 5 stages: 183 / 192 / 183 / 198 us for 4.2 M two-player games
     auto kern = k_step<P, POOL, STAGES>;
     const size_t smem = StepSmem<P, STAGES>::bytes(STEP5_WARPS);
     static thread_local int per_sm_cached[64] = {0};      // function attributes are per device
