@@ -471,15 +471,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             }
             umma_commit(bar2);
         }
+        // while the layer-2 MMAs run: everything the epilogue needs that does not depend on the logits -- the legal
+        // mask of the game, this part's 48-bit window of it, and the Philox word of the sampling step
+        uint32_t m[6], lin[6];
+        legal_mask(gm, m);
+        linear_mask(m, lin);
+        const uint64_t mybits = mask_window(lin, col0);
+        uint32_t sample_word = 0u;
+        if (MODE == 0) {
+            uint32_t w[4];
+            rng(A.gid0 + (uint32_t)gl, gm.steps >> 2, PURPOSE_POLICY, 0u, w);
+            const uint32_t idx = gm.steps & 3u;
+            sample_word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
+        }
         mbar_wait(bar2, phase);
         tc_fence_after();
         phase ^= 1;
 
         // ---- epilogue 2a: per part -- critic partial sum and online softmax over its 48 columns ----
-        uint32_t m[6], lin[6];
-        legal_mask(gm, m);
-        linear_mask(m, lin);
-        const uint64_t mybits = mask_window(lin, col0);
         // online softmax statistics over this part's legal logits, one 16-column chunk at a time and without
         // per-column branches (32 different games share a warp): chunk maximum first, one rescale, then the sum.
         // The chunk sums (relative to the running maximum at that chunk) are kept for the sampling step.
@@ -557,11 +566,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             // target, then the 16-column chunk inside it (from the chunk sums), then a branch-free scan of that chunk only.
             // tcgen05.ld is warp-collective and the chunk differs from lane to lane, so every lane loads its three chunks
             // and keeps the one it needs by selects.
-            uint32_t w[4];
-            rng(A.gid0 + (uint32_t)gl, gm.steps >> 2, PURPOSE_POLICY, 0u, w);
-            const uint32_t idx = gm.steps & 3u;
-            const uint32_t word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
-            const float target = (float)(word >> 8) * (1.0f / 16777216.0f) * gse;
+            const float target = (float)(sample_word >> 8) * (1.0f / 16777216.0f) * gse;
             int owner = -1;
             float run = 0.0f;
 #pragma unroll
@@ -608,7 +613,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 const bool upd = legal && cum <= target;   // rounding may leave cum <= target to the end: then the chunk's last legal action
                 chosen = upd ? i : chosen;
                 chosen_l = upd ? vs[i] : chosen_l;
-                cum += ex2f(legal ? fmaf(vs[i], LOG2E, -gm2) : -INFINITY);      // 2^-inf = 0: no branch around the SFU op
+                // the weight of an illegal column is masked to +0.0 with integer logic: a `legal ? ... : ...` around the SFU op
+                // is compiled to a branch per column (half the lanes idle)
+                const uint32_t keep = 0u - ((kb >> i) & 1u);
+                cum += __uint_as_float(__float_as_uint(ex2f(fmaf(vs[i], LOG2E, -gm2))) & keep);
             }
             if (mine && chosen >= 0) result[row] = make_int2(col0 + 16 * k + chosen, __float_as_int(chosen_l));
         }
