@@ -22,7 +22,6 @@
 
 #include "azb_internal.h"
 #include "azb_rules.cuh"
-#include "azb_queue.cuh"
 
 using namespace azb;
 
@@ -296,7 +295,7 @@ struct PolicyArgs {
 };
 
 constexpr uint32_t PURPOSE_POLICY = 4;
-// transient MISC bits between k_policy and k_finish_rounds (never visible outside azb_policy_step)
+// transient MISC bits between k_policy's tile loop and its finishing phase (never visible outside azb_policy_step)
 constexpr uint32_t FLAG_ROUND_OVER = 1u << 28, FLAG_FRESH_GAME = 1u << 29;
 
 struct SmemSink {
@@ -307,6 +306,33 @@ struct SmemSink {
     }
     __device__ __forceinline__ void add_group(int i, uint32_t v) { add(i, v); }
 };
+
+// Completes the step of one game whose move k_policy applied: count_score, game-over test and new_round (azul.py:307-311)
+// when its round ended, a fresh game for a finished / stuck slot in self-play mode; finalises done / status.
+template <int POOL>
+__device__ __forceinline__ void finish_game(Game<2>& h, uint32_t gidx, uint32_t flags, const Philox& rng, uint32_t gid0,
+                                            int first_rule, bool auto_reset, uint32_t* __restrict__ state, int64_t n,
+                                            uint8_t* __restrict__ done_out, uint8_t* __restrict__ status_out, SmemSink& sink)
+{
+    const uint32_t gid = gid0 + gidx;
+    bool over = false, fresh = (flags & FLAG_FRESH_GAME) != 0u;
+    if (flags & FLAG_ROUND_OVER) {
+        count_score<2, POOL>(h);                                  // azul.py:307
+        over = is_end_of_game(h);                                 // azul.py:308-309
+        if (over) h.misc |= 1u << 12;
+    }
+    if (done_out) done_out[gidx] = h.ended() ? 1 : 0;
+    if (over && auto_reset) { tally_finished(h, sink); fresh = true; }
+    if (fresh) {
+        reset_game<2, POOL>(h, rng, gid, first_rule);
+        if (auto_reset) sink.add(2, 1);
+    } else if (!over) {
+        new_round_philox<2, POOL>(h, rng, gid, PURPOSE_REFILL);   // azul.py:311
+        if (auto_reset) sink.add(2, 1);
+    }
+    h.store(state, n, (int64_t)gidx);
+    if (status_out) status_out[gidx] |= (uint8_t)h.status();
+}
 
 // bits [start, start + 48) of the 180-bit linear mask; start is 0, 48, 96 or 144
 __device__ __forceinline__ uint64_t mask_window(const uint32_t (&lin)[6], int start)
@@ -649,14 +675,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             }
             // Only the cheap, uniform part of Azul.step runs here (move, next player).  Games whose round just ended --
             // and, in self-play mode, slots that need a fresh game -- are flagged in MISC and completed by
-            // k_finish_rounds right after this kernel, 32 at a time with full warps (see azb_queue.cuh).
+            // the finishing phase at the end of this kernel, 32 per warp with every lane busy.
             const bool ended_before = gm.ended();
             const bool stuck = acts && status == (uint32_t)ST_STUCK;
             uint32_t flags = 0u;
             if (A.apply_step && n_valid > 0 && !ended_before) {
                 apply_move<2, POOL>(gm, action);                          // azul.py:304
                 gm.steps += 1u;
-                if (is_end_of_round(gm)) flags = FLAG_ROUND_OVER;         // azul.py:306 -> k_finish_rounds
+                if (is_end_of_round(gm)) flags = FLAG_ROUND_OVER;         // azul.py:306 -> finishing phase
                 else next_player(gm);                                     // azul.py:313
                 if (valid && A.apply_step == 2) sink.add(0, 1);
             } else if (A.apply_step == 2 && acts && (ended_before || stuck)) {
@@ -666,7 +692,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             gm.misc |= flags;
             if (valid && A.apply_step) gm.store(A.state, A.n, g);
             if (valid) {
-                if (A.done_out) A.done_out[g] = ended_before ? 1 : 0;      // finalised by k_finish_rounds for flagged games
+                if (A.done_out) A.done_out[g] = ended_before ? 1 : 0;      // finalised by the finishing phase for flagged games
                 if (A.status_out) A.status_out[g] = (uint8_t)(status | gm.status());
             }
         }
@@ -677,91 +703,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         __syncthreads();
     }
 
+    // ---- the rare, long part of Azul.step for this CTA's own games: the ones flagged above (round over / fresh game) are
+    // collected into a dense list (the A region is free now) and finished 32 per warp with every lane busy, instead of under
+    // divergence inside the tile loop or in a second kernel launch ----
+    __syncthreads();                                   // every state / done / status write of the tile loop is visible to the CTA
+    if (A.apply_step) {
+        uint32_t* list = reinterpret_cast<uint32_t*>(a_tile);
+        __shared__ uint32_t n_list;
+        if (tid == 0) n_list = 0u;
+        __syncthreads();
+        for (int64_t tile = (int64_t)blockIdx.x + (int64_t)part * gridDim.x; tile < tiles; tile += (int64_t)PARTS * gridDim.x) {
+            const int64_t g = tile * TILE_M + row;
+            if (g < A.n && (A.state[3 * A.n + g] & (FLAG_ROUND_OVER | FLAG_FRESH_GAME))) list[atomicAdd(&n_list, 1u)] = (uint32_t)g;
+        }
+        __syncthreads();
+        const uint32_t total = n_list;
+        for (uint32_t i = (uint32_t)tid; i < total; i += THREADS) {
+            const uint32_t gidx = list[i];
+            Game<2> h;
+            h.load(A.state, A.n, (int64_t)gidx);
+            const uint32_t flags = h.misc & (FLAG_ROUND_OVER | FLAG_FRESH_GAME);
+            h.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
+            finish_game<POOL>(h, gidx, flags, rng, A.gid0, A.first_rule, A.apply_step == 2, A.state, A.n, A.done_out, A.status_out, sink);
+        }
+    }
     __syncthreads();
     if (A.counters && tid < AZB_N_COUNTERS && cnt[tid]) atomicAdd(&A.counters[tid], cnt[tid]);
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
-}
-
-// Completes the steps k_policy started: count_score, game-over test and new_round (azul.py:307-311) for the games
-// whose round ended, fresh games for finished / stuck slots in self-play mode.  Persistent warps scan the MISC word
-// of every game (coalesced), park flagged games in a warp-private queue and finish 32 at a time.
-struct FinishArgs {
-    uint32_t* __restrict__ state;
-    int64_t n;
-    uint32_t k0, k1, gid0;
-    int first_rule;
-    int auto_reset;
-    uint8_t* __restrict__ done_out;
-    uint8_t* __restrict__ status_out;
-    unsigned long long* __restrict__ counters;
-};
-
-template <int POOL>
-__global__ void __launch_bounds__(32 * STEP_WARPS) k_finish_rounds(FinishArgs F)
-{
-    constexpr int QWORDS = 9 + 5 * 2;
-    __shared__ uint32_t queues[STEP_WARPS][QWORDS * STEP_QCAP];
-    __shared__ unsigned long long cnt[AZB_N_COUNTERS];
-    if (threadIdx.x < AZB_N_COUNTERS) cnt[threadIdx.x] = 0ull;
-    __syncthreads();
-    SmemSink sink{cnt};
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* q = queues[warp];
-    const int64_t n_rows = (F.n + 31) / 32;
-    const int64_t warps_total = (int64_t)gridDim.x * STEP_WARPS;
-    const Philox rng{F.k0, F.k1};
-    int waiting = 0;
-
-    auto drain = [&](int count) {
-        if (lane < count) {
-            Game<2> h;
-            uint32_t gidx, flags;
-            queue_get<2>(q, waiting - count + lane, h, gidx, flags);
-            const uint32_t gid = F.gid0 + gidx;
-            bool over = false, fresh = (flags & FLAG_FRESH_GAME) != 0u;
-            if (flags & FLAG_ROUND_OVER) {
-                count_score<2, POOL>(h);                                  // azul.py:307
-                over = is_end_of_game(h);                                 // azul.py:308-309
-                if (over) h.misc |= 1u << 12;
-            }
-            if (F.done_out) F.done_out[gidx] = h.ended() ? 1 : 0;
-            if (over && F.auto_reset) { tally_finished(h, sink); fresh = true; }
-            if (fresh) {
-                reset_game<2, POOL>(h, rng, gid, F.first_rule);
-                if (F.auto_reset) sink.add(2, 1);
-            } else if (!over) {
-                new_round_philox<2, POOL>(h, rng, gid, PURPOSE_REFILL);   // azul.py:311
-                if (F.auto_reset) sink.add(2, 1);
-            }
-            h.store(F.state, F.n, (int64_t)gidx);
-            if (F.status_out) F.status_out[gidx] |= (uint8_t)h.status();
-        }
-        waiting -= count;
-        __syncwarp();
-    };
-
-    for (int64_t row = (int64_t)blockIdx.x * STEP_WARPS + warp; row < n_rows; row += warps_total) {
-        const int64_t g = row * 32 + lane;
-        const uint32_t misc = g < F.n ? F.state[3 * F.n + g] : 0u;
-        const uint32_t flags = misc & (FLAG_ROUND_OVER | FLAG_FRESH_GAME);
-        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, flags != 0u);
-        if (hit) {
-            if (flags) {
-                Game<2> gm;
-                gm.load(F.state, F.n, g);
-                gm.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
-                queue_put<2>(q, waiting + __popc(hit & ((1u << lane) - 1u)), gm, (uint32_t)g, flags);
-            }
-            waiting += __popc(hit);
-            __syncwarp();
-            if (waiting >= 32) drain(32);
-        }
-    }
-    if (waiting > 0) drain(waiting);
-    __syncthreads();
-    if (F.counters && threadIdx.x < AZB_N_COUNTERS && cnt[threadIdx.x]) atomicAdd(&F.counters[threadIdx.x], cnt[threadIdx.x]);
 }
 
 // fp32 torch-layout weights -> the bf16 shared-memory image
@@ -857,22 +827,6 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
     else rc = mode == 0 ? pol::launch_policy<0, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<0, 1>(A, grid, (cudaStream_t)stream);
     if (rc) return rc;
     CHECK_LAUNCH();
-    if (apply_step) {
-        pol::FinishArgs F;
-        F.state = state; F.n = h->n_games; F.k0 = A.k0; F.k1 = A.k1; F.gid0 = A.gid0; F.first_rule = h->first_player;
-        F.auto_reset = apply_step == 2; F.done_out = done_out; F.status_out = status_out; F.counters = counters;
-        const int64_t rows = (h->n_games + 31) / 32;
-        // rows of 32 games per warp: more rows fill the queue better, fewer rows finish sooner (4 measured best)
-        constexpr int rows_per_warp = 4;
-        int64_t blocks = (rows + STEP_WARPS * rows_per_warp - 1) / (STEP_WARPS * rows_per_warp);
-        const int64_t resident = (int64_t)h->sm_count * 4;
-        if (blocks > resident) blocks = resident;
-        if (h->tile_pool == AZB_POOL_LID)
-            pol::k_finish_rounds<1><<<dim3((unsigned)blocks), 32 * STEP_WARPS, 0, (cudaStream_t)stream>>>(F);
-        else
-            pol::k_finish_rounds<0><<<dim3((unsigned)blocks), 32 * STEP_WARPS, 0, (cudaStream_t)stream>>>(F);
-        CHECK_LAUNCH();
-    }
     return 0;
 }
 
