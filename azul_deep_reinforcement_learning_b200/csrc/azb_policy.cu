@@ -181,7 +181,8 @@ __device__ __forceinline__ float obs_value(const Game<2>& g, uint32_t pat_me, ui
         constexpr int q = IDX - 31, r = (q % 25) / 5, c = q % 5;
         const uint32_t pat = q < 25 ? pat_me : pat_ot;
         const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, col = (pat >> (6 * r)) & 7u;
-        return (col == (uint32_t)c) ? small_int_to_float(cnt) : 0.0f;
+        // integer select, then ONE unconditional conversion: `cond ? convert(cnt) : 0.0f` compiles to a branch per entry
+        return small_int_to_float(cnt & (0u - (uint32_t)(col == (uint32_t)c)));
     } else if constexpr (IDX < 131) {                 // walls (colour-indexed, game_runner.py:69)
         constexpr int q = IDX - 81, bit = q % 25;
         const uint32_t w = q < 25 ? wall_me : wall_ot;
