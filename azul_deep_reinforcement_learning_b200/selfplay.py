@@ -180,6 +180,11 @@ class GraphedEpisodes:
             runner.mask = self.mask_in
             self.rec_more = self._body(more)
             self.mask_more = runner.mask
+        # the first replay of a graph pays its upload (tens of ms): pay it here, not in the middle of training
+        # (every run() starts with the reset inside the first graph, so the games played here are discarded)
+        self.graph.replay()
+        self.graph_more.replay()
+        torch.cuda.synchronize(dev)
 
     def _body(self, decisions):
         rec = {k: [] for k in RAW_KEYS}

@@ -41,6 +41,32 @@ def a2c_loss_terms(net, obs, mask, action, qval):
     return (-log_prob * advantage).sum(), advantage.pow(2).sum(), entropy.sum()
 
 
+class _Linear(torch.autograd.Function):
+    """``x @ w.T + b`` whose bias gradient is a GEMM with a row of ones (tensor cores) instead of autograd's column
+    reduction over the [N, out] gradient -- a fifth of the update's GPU time at 5*10^5 decisions."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.addmm(b, x, w.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dw = dy.t() @ x
+        db = (torch.ones(1, dy.shape[0], dtype=dy.dtype, device=dy.device) @ dy).squeeze(0)
+        return dx, dw, db
+
+
+def network_outputs(net, x):
+    """(logits [N,180] raw, value [N]) of ``ActorCritic`` (model.py:23-41 before the mask) through :class:`_Linear`."""
+    lin = _Linear.apply
+    logits = lin(torch.relu(lin(x, net.actor_linear1.weight, net.actor_linear1.bias)), net.actor_linear2.weight, net.actor_linear2.bias)
+    value = lin(torch.relu(lin(x, net.critic_linear1.weight, net.critic_linear1.bias)), net.critic_linear2.weight, net.critic_linear2.bias)
+    return logits, value.squeeze(1)
+
+
 def allreduce_gradients(params):
     """C1: one flat all-reduce (sum) over every gradient; the caller already divided by the global count."""
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
@@ -132,8 +158,7 @@ class SelfPlayTrainer:
             for lo in range(0, n_local, chunk):
                 idx = sel[lo:lo + chunk]
                 x = obs[idx].float()
-                logits = self.net.actor_linear2(torch.relu(self.net.actor_linear1(x)))
-                value = self.net.forward_critic(x).squeeze(1)
+                logits, value = network_outputs(self.net, x)
                 dlogits, dvalue = self.runner.engine.a2c_loss_grad(
                     logits.detach(), value.detach().contiguous(), masks[idx].contiguous(), action[idx], qval[idx],
                     1.0, (ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF), sums)

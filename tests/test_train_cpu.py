@@ -65,6 +65,26 @@ def test_alive_chain_equals_the_sequential_bookkeeping():
     assert torch.equal(alive, a)
 
 
+def test_network_outputs_match_the_module():
+    """train.network_outputs (custom Linear with a GEMM bias gradient) == the nn.Module forward, values and gradients."""
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.train import network_outputs
+    torch.manual_seed(5)
+    net = ActorCritic(136, 180)
+    x = torch.randn(37, 136)
+    gl, gv = torch.randn(37, 180), torch.randn(37)
+    logits = net.actor_linear2(torch.relu(net.actor_linear1(x)))
+    value = net.forward_critic(x).squeeze(1)
+    torch.autograd.backward([logits, value], [gl, gv])
+    want = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    l2, v2 = network_outputs(net, x)
+    assert torch.allclose(l2, logits, atol=1e-6) and torch.allclose(v2, value, atol=1e-6)
+    torch.autograd.backward([l2, v2], [gl, gv])
+    for p, w in zip(net.parameters(), want):
+        assert torch.allclose(p.grad, w, rtol=1e-5, atol=1e-6), p.shape
+
+
 def test_discounted_returns():
     from azul_deep_reinforcement_learning_b200.selfplay import discounted_returns
     r = torch.tensor([[1.0, 2.0], [0.0, -1.0], [3.0, 5.0]])

@@ -4,7 +4,7 @@ import torch, time
 from torch.profiler import profile, ProfilerActivity
 from azul_deep_reinforcement_learning_b200.train import SelfPlayTrainer
 tr = SelfPlayTrainer(16384, seed=0)
-for i in range(10):
+for i in range(24):
     t0=time.perf_counter(); b=tr.rollout(); torch.cuda.synchronize(); t1=time.perf_counter(); tr.update(b); torch.cuda.synchronize(); t2=time.perf_counter()
     print("iter", i, "rollout ms %.1f update ms %.1f" % (1e3*(t1-t0), 1e3*(t2-t1)), "T", b["active"].shape[0])
 torch.cuda.synchronize()
