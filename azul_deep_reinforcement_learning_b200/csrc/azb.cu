@@ -138,13 +138,13 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 // games waiting in a warp's queue that trigger a pass: fuller passes cost fewer instructions, earlier passes patch lines that
 // are still in L2 (measured 16 / 20 / 24 / 28 / 32: 201 / 191 / 183 / 186 / 196 us for 4.2 M two-player games)
 constexpr int STEP_DRAIN_AT = 24;
-constexpr int STEP5_QCAP = 48;           // a row that would overflow the queue drains it first
-constexpr int STEP5_WARPS = 2;           // warps per block (fine-grained shared-memory occupancy)
+constexpr int STEP_QCAP = 48;           // a row that would overflow the queue drains it first
+constexpr int STEP_WARPS = 2;           // warps per block (fine-grained shared-memory occupancy)
 
 template <int P, int STAGES>
 struct StepSmem {
     static constexpr int W = 7 + 5 * P;
-    static constexpr int QUEUE = (W + 2) * STEP5_QCAP;
+    static constexpr int QUEUE = (W + 2) * STEP_QCAP;
     static constexpr int TILE = W * 32 + 8;                                  // + the row's 32 action bytes
     static constexpr int MASK = 6 * 32;
     static constexpr int WORDS_PER_WARP = QUEUE + STAGES * TILE + MASK;      // multiple of 4 words: 16-byte aligned parts
@@ -219,18 +219,18 @@ __device__ __forceinline__ void row_flush(const uint32_t* tile, uint32_t* __rest
 }
 
 template <int P, int POOL, int STAGES>
-__global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const uint8_t* __restrict__ action,
+__global__ void __launch_bounds__(32 * STEP_WARPS, 8) k_step(Launch L, const uint8_t* __restrict__ action,
                                                            const int8_t* __restrict__ draws, StepOut O, int aligned)
 {
     using S = StepSmem<P, STAGES>;
-    constexpr int W = S::W, QCAP = STEP5_QCAP;
+    constexpr int W = S::W, QCAP = STEP_QCAP;
     extern __shared__ __align__(16) uint32_t step_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* q = step_smem + (size_t)warp * S::WORDS_PER_WARP;
     uint32_t* tiles = q + S::QUEUE;
     uint32_t* mask_tile = tiles + STAGES * S::TILE;
     const int64_t n_rows = (L.n + 31) / 32;
-    const int64_t warps_total = (int64_t)gridDim.x * STEP5_WARPS;
+    const int64_t warps_total = (int64_t)gridDim.x * STEP_WARPS;
     const Philox rng{L.k0, L.k1};
     int waiting = 0;                                        // warp-uniform: entries in this warp's queue
     const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(32 * STEP5_WARPS, 8) k_step(Launch L, const ui
     auto row_is_fast = [&](int64_t r) { return aligned && r * 32 + 32 <= L.n; };
     const int64_t lane_off = (int64_t)(lane >> 3) * L.n + 4 * (lane & 7), n4 = 4 * L.n;
 
-    const int64_t row0 = (int64_t)blockIdx.x * STEP5_WARPS + warp;
+    const int64_t row0 = (int64_t)blockIdx.x * STEP_WARPS + warp;
     // prologue: rows 0 .. STAGES-2 of this warp in flight
 #pragma unroll
     for (int k = 0; k < STAGES - 1; k++) {
@@ -628,21 +628,21 @@ static int launch_step(const azb_t* h, const Launch& L, const uint8_t* action, c
 {
     constexpr int STAGES = P == 2 ? 4 : 3;       // 2 / 3 / 4 / 5 stages: 183 / 192 / 183 / 198 us for 4.2 M two-player games
     auto kern = k_step<P, POOL, STAGES>;
-    const size_t smem = StepSmem<P, STAGES>::bytes(STEP5_WARPS);
+    const size_t smem = StepSmem<P, STAGES>::bytes(STEP_WARPS);
     static thread_local int per_sm_cached[64] = {0};      // function attributes are per device
     int uncached = 0;
     int& per_sm = h->device < 64 ? per_sm_cached[h->device] : uncached;
     if (per_sm == 0) {
         AZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * STEP5_WARPS, smem));
+        AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * STEP_WARPS, smem));
         if (per_sm < 1) per_sm = 1;
     }
     const int64_t rows = (h->n_games + 31) / 32;
-    int64_t blocks = (rows + STEP5_WARPS - 1) / STEP5_WARPS;
+    int64_t blocks = (rows + STEP_WARPS - 1) / STEP_WARPS;
     const int64_t resident = (int64_t)h->sm_count * per_sm;
     if (blocks > resident) blocks = resident;
-    kern<<<dim3((unsigned)blocks), 32 * STEP5_WARPS, smem, stream>>>(L, action, draws, O, aligned);
+    kern<<<dim3((unsigned)blocks), 32 * STEP_WARPS, smem, stream>>>(L, action, draws, O, aligned);
     return 0;
 }
 

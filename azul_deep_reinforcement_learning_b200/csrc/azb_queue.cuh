@@ -6,10 +6,8 @@
 
 using namespace azb;
 
-constexpr int STEP_QCAP = 64;            // entries per warp queue: < 32 waiting + up to 32 new ones
-constexpr int STEP_WARPS = 4;            // warps per block
 
-template <int P, int QCAP = STEP_QCAP>
+template <int P, int QCAP>
 __device__ __forceinline__ void queue_put(uint32_t* q, int slot, const Game<P>& g, uint32_t gidx, uint32_t status)
 {
     q[0 * QCAP + slot] = g.pl0; q[1 * QCAP + slot] = g.pl1; q[2 * QCAP + slot] = g.pl2;
@@ -24,7 +22,7 @@ __device__ __forceinline__ void queue_put(uint32_t* q, int slot, const Game<P>& 
     q[(7 + 5 * P) * QCAP + slot] = gidx;
     q[(8 + 5 * P) * QCAP + slot] = status;
 }
-template <int P, int QCAP = STEP_QCAP>
+template <int P, int QCAP>
 __device__ __forceinline__ void queue_get(const uint32_t* q, int slot, Game<P>& g, uint32_t& gidx, uint32_t& status)
 {
     g.pl0 = q[0 * QCAP + slot]; g.pl1 = q[1 * QCAP + slot]; g.pl2 = q[2 * QCAP + slot];
