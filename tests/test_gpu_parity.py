@@ -301,6 +301,12 @@ def test_observe_matches_reference_layout():
     eng = engine(8, 2, 1, 0, seed=1)
     obs = eng.observe(0)
     assert obs.shape[1] == 136 and bool((obs.sum(dim=1) == 21).all())
+    # the bfloat16 variant is the float32 observation rounded once (ragged batch: the last block is partial)
+    for players in (2, 3, 4):
+        eng = engine(1000 + players, players, 1, 0, seed=9)
+        eng.rollout_random(37)
+        for persp in (-1, 0, players - 1):
+            assert torch.equal(eng.observe_bf16(persp), eng.observe(persp).to(torch.bfloat16)), (players, persp)
 
 
 def test_stats_match_records():
