@@ -365,7 +365,7 @@ struct BlockSink {
 // Action words of a whole round, computed by the full warp during the end-of-round pass (when all of its games
 // are at the same point) and parked in shared memory: ROUND_WORDS words per game, [word][thread] so that a warp
 // reads 32 consecutive banks.  A round that outlasts them falls back to computing a block in place.
-constexpr int ROUND_WORDS = 20;
+constexpr int ROUND_WORDS = 16;          // 12 / 16 / 20 words: 3.61 / 3.70 / 3.67e10 env steps/s (rounds last ~10.5 steps; longer ones fall back)
 struct RoundWords {
     uint32_t* base;          // &buf[threadIdx.x]
     uint32_t stride;         // blockDim.x
