@@ -74,9 +74,9 @@ __global__ void k_legal_mask(const uint32_t* __restrict__ s, int64_t n, uint32_t
 // The move is cheap and uniform; the end-of-round work (count_score, game-over test, new_round) hits ~10 % of
 // the games of a launch, i.e. ~3 of a warp's 32 lanes.  Each warp therefore walks several rows of 32 games and
 // parks the games whose round just ended in a warp-private shared-memory queue (packed state + game index);
-// whenever 32 are waiting, the warp finishes them together with every lane busy.  No block barrier is involved;
-// the finished games are written back with per-lane (scattered) 4-byte stores that merge in L2 with the
-// coalesced row stores of the same 128-byte lines.
+// once STEP_DRAIN_AT are waiting, the warp finishes them together with (nearly) every lane busy.  No block barrier is
+// involved; the finished games are written back with per-lane (scattered) 4-byte stores that merge in L2 with the
+// whole-line row stores of the same 128-byte lines (which carry an L2 evict_last policy for that reason).
 struct StepOut {
     uint32_t* __restrict__ mask6;
     int16_t* __restrict__ preview;
@@ -135,6 +135,7 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 // (no registers are held by loads in flight), read from the tile with conflict-free 4-byte shared loads, and --
 // on the aligned path -- written back through the tile with 16-byte global stores, so that a row costs
 // ceil(W/4) + 2 global store instructions instead of W + 6 and every 128-byte line is written whole.
+
 // games waiting in a warp's queue that trigger a pass: fuller passes cost fewer instructions, earlier passes patch lines that
 // are still in L2 (measured 16 / 20 / 24 / 28 / 32: 201 / 191 / 183 / 186 / 196 us for 4.2 M two-player games)
 constexpr int STEP_DRAIN_AT = 24;
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, 8) k_step(Launch L, const uin
         }
         const uint32_t over = __ballot_sync(0xFFFFFFFFu, round_over);
         if (over) {
-            if (waiting + __popc(over) > QCAP) drain(waiting);            // waiting < 32 here
+            if (waiting + __popc(over) > QCAP) drain(waiting);            // waiting < STEP_DRAIN_AT here
             if (round_over) queue_put<P, QCAP>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
             waiting += __popc(over);
             __syncwarp();
