@@ -421,6 +421,22 @@ def run_policy(args):
         torch.cuda.current_stream(dev).synchronize()
     e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
     cnt = parallel.reduce_counters(eng.counters.clone()).cpu().tolist()
+    accuracy = None
+    if rank == 0:
+        # logits / value of the kernel (bf16 operands, fp32 accumulation) against the untouched fp32
+        # ActorCritic forward (model.py:23-41) on the CPU, 4,096 of the mid-game states reached above; outside the timing
+        with torch.no_grad():
+            chk = policy_step(eng, packed, mode=1, apply_step=False, want_logits=True, want_mask=False)
+            k = min(4096, G)
+            obs = eng.observe(-1)[:k].cpu()
+            ref_l = net.actor_linear2(torch.relu(net.actor_linear1(obs)))
+            ref_v = net.forward_critic(obs).squeeze(1)
+            got_l, got_v = chk["logits"][:k].cpu(), chk["value"][:k].cpu()
+            accuracy = {"states": k, "reference": "fp32 ActorCritic forward on the CPU (torch)",
+                        "logits_max_abs_err": float((got_l - ref_l).abs().max()),
+                        "logits_mean_abs_err": float((got_l - ref_l).abs().mean()), "logits_max_abs": float(ref_l.abs().max()),
+                        "logits_max_err_rel_to_scale": float((got_l - ref_l).abs().max() / ref_l.abs().max()),
+                        "value_max_abs_err": float((got_v - ref_v).abs().max())}
     if rank == 0:
         value = world * G * args.steps / (dev_ms * 1e-3)
         flop = 2 * (136 * 360 + 180 * 180 + 180)                                  # 163,080 per decision
@@ -449,7 +465,7 @@ def run_policy(args):
                          "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback",
                          "algorithmic_flop_per_decision": flop, "decisions_per_launch": G, "kernel": "pol::k_policy<%d>" % pool},
             "clocks": clocks,
-            "decisions_per_sec": value, "games_per_sec": (cnt[1] / max(cnt[0], 1)) * value,
+            "decisions_per_sec": value, "games_per_sec": (cnt[1] / max(cnt[0], 1)) * value, "accuracy": accuracy,
             "rollout_counters": {"steps": cnt[0], "games": cnt[1], "rounds": cnt[2], "stuck": cnt[6]},
         }
         print(json.dumps(line))
