@@ -160,6 +160,14 @@ __device__ __forceinline__ float ex2f(float x)
 }
 constexpr float LOG2E = 1.4426950408889634f;
 
+// relu + round-to-nearest bf16 + pack of two floats in ONE instruction (cvt's .relu modifier)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 // exact float of a small non-negative integer without the conversion pipe
 __device__ __forceinline__ float small_int_to_float(uint32_t n) { return __uint_as_float(0x4B000000u | n) - 8388608.0f; }
 
@@ -467,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int j = c0 + 8 * q + 2 * e;                  // hidden unit (even, so j and j + 1 are both < or >= 180)
-                    ow[e] = j < HID ? pack_bf16(fmaxf(v[8 * q + 2 * e], 0.0f), fmaxf(v[8 * q + 2 * e + 1], 0.0f))
+                    ow[e] = j < HID ? pack_relu_bf16(v[8 * q + 2 * e], v[8 * q + 2 * e + 1])
                                     : (j == BIAS_K2 ? 0x3F803F80u : 0u);   // the two constant-one units that carry b2
                 }
                 *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = o;
