@@ -251,7 +251,7 @@ class BatchedAzul:
 
 
 class PackedPolicy:
-    """The ``ActorCritic`` parameters (model.py:17-21) in the bf16 shared-memory image of the policy kernel."""
+    """The ``ActorCritic`` parameters (model.py:17-21) in the fp16 shared-memory image of the policy kernel."""
 
     def __init__(self, engine, ac_net):
         self.engine = engine

@@ -7,7 +7,7 @@ equivalent (reference scripts/training.py:8-22, nn_runner.py:53-84, agent.py:39-
 ``batch_size`` episodes are played IN PARALLEL per rank (one game slot each) instead of one after the
 other; everything else follows the reference: discounted returns with gamma = 0.99, the loss of
 ``Agent.update`` (advantage not detached in the actor term, "entropy" = -mean(log pi over legal moves)
-added with +0.1), Adam(lr 3e-4).  Rollouts use the fused bf16 tensor-core policy kernel; the update
+added with +0.1), Adam(lr 3e-4).  Rollouts use the fused tensor-core policy kernel (fp16 operands, fp32 accumulation); the update
 recomputes the forward pass in fp32 with PyTorch autograd on the recorded observations.  With several
 ranks each one plays its own shard of the global game-id range and the only collectives are one flat
 gradient all-reduce per update (C1, 82,081 fp32 values) and the statistics reduction (C2).
@@ -149,7 +149,7 @@ class SelfPlayTrainer:
                 p.grad = torch.zeros_like(p)
         sums = torch.zeros(3, dtype=torch.float64, device=self.device)
         # The dense layers run on the tensor cores through cuBLAS (TF32: fp32 storage and accumulation, 10-bit operand
-        # mantissas -- finer than the bf16 operands the rollout's decisions were taken with); everything between the
+        # mantissas -- about as fine as the fp16 operands the rollout's decisions were taken with); everything between the
         # network outputs and the loss -- masked log-softmax, the three terms, their gradient -- is one kernel
         # (azb_a2c_loss_grad), back-propagated through the layers by autograd.
         tf32 = torch.backends.cuda.matmul.allow_tf32

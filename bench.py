@@ -423,7 +423,7 @@ def run_policy(args):
     cnt = parallel.reduce_counters(eng.counters.clone()).cpu().tolist()
     accuracy = None
     if rank == 0:
-        # logits / value of the kernel (bf16 operands, fp32 accumulation) against the untouched fp32
+        # logits / value of the kernel (fp16 operands, fp32 accumulation) against the untouched fp32
         # ActorCritic forward (model.py:23-41) on the CPU, 4,096 of the mid-game states reached above; outside the timing
         with torch.no_grad():
             chk = policy_step(eng, packed, mode=1, apply_step=False, want_logits=True, want_mask=False)
@@ -456,7 +456,7 @@ def run_policy(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3) + 40, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (MLP) / u32 (rules)", "data": "synthetic", "config": cfg,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (MLP) / u32 (rules)", "data": "synthetic", "config": cfg,
             "e2e": {"value": world * G * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": host_state.numel() * 4,
                     "d2h_bytes_per_step": host_state.numel() * 4 + sum(v.numel() * v.element_size() for v in host_out.values()),
                     "steps": e2e_steps},
@@ -596,7 +596,7 @@ def run_train(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 rollout MLP / tf32 update (fp32 storage) / u32 rules", "data": "synthetic", "config": cfg,
+            "vs_baseline": None, "dtype": "fp16-operand rollout MLP / tf32 update (fp32 storage) / u32 rules", "data": "synthetic", "config": cfg,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 32,
                     "note": "a training batch is end to end by construction: statistics are read back to the host every batch"},
             "gpu_launches": None, "clocks": clocks,

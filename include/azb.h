@@ -151,7 +151,7 @@ int azb_opponent_random(azb_t* h, uint32_t* state, int require_two, int16_t* pla
 /* ---- K4: the policy/value network of azulnet/model.py:12-41 fused with its callers ------------
  * ActorCritic(136, 180, hidden 180): actor 136 -> 180 -> ReLU -> 180 logits, critic 136 -> 180 -> ReLU -> 1.
  * azb_policy_pack_weights converts the eight fp32 parameter tensors (torch layout [out][in], device
- * pointers) into the bf16 image (azb_policy_packed_bytes() bytes, device) the kernel keeps in shared
+ * pointers) into the fp16 image (azb_policy_packed_bytes() bytes, device; biases as fp16 hi + lo pairs) the kernel keeps in shared
  * memory.  azb_policy_step then does, for every 2-player game of the batch, in ONE launch:
  *   observation from the seat to move        GameRunner.get_state            game_runner.py:56-72
  *   both dense layers on tcgen05 tensor cores ActorCritic.forward_actor/critic model.py:23-41

@@ -1,10 +1,11 @@
 """K4 parity: the fused policy kernel (tcgen05 MLP + masked softmax + sampling + step) against plain
 PyTorch fp32 evaluations of the same ActorCritic (reference azulnet/model.py:12-41) on the same states.
 
-Tolerances (north star: logits within 1e-3 relative in bf16): the kernel rounds observation, weights and
-the hidden activations to bf16 and accumulates in fp32, so it is compared (a) tightly, 1e-3 of the logit
-scale, with an fp32 torch evaluation of the SAME bf16-rounded operands, and (b) loosely, 3e-2 of the
-logit scale, with the untouched fp32 model."""
+Tolerances (north star: logits within 1e-3 relative at reduced precision): the kernel rounds observation,
+weights and the hidden activations to fp16 (11-bit significand; the tensor cores take fp16 and bf16 at the same
+rate) and accumulates in fp32, so it is compared (a) tightly, 2e-4 of the logit scale, with a float64 torch
+evaluation of the SAME fp16-rounded operands, and (b) at the north star's 1e-3 of the logit scale with the
+untouched fp32 model."""
 import numpy as np
 import pytest
 
@@ -28,11 +29,11 @@ def _setup(n=4096, pool=1, seed=7, k=23):
     return net, eng, packed
 
 
-def _bf16(x):
-    return x.to(torch.bfloat16).to(torch.float32)
+def _f16(x):
+    return x.to(torch.float16).to(torch.float32)
 
 
-def _torch_forward(net, obs, emulate_bf16):
+def _torch_forward(net, obs, emulate_f16):
     W1a, b1a = net.actor_linear1.weight.cuda(), net.actor_linear1.bias.cuda()
     W2a, b2a = net.actor_linear2.weight.cuda(), net.actor_linear2.bias.cuda()
     W1c, b1c = net.critic_linear1.weight.cuda(), net.critic_linear1.bias.cuda()
@@ -41,12 +42,12 @@ def _torch_forward(net, obs, emulate_bf16):
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        if emulate_bf16:
-            x, W1a, W2a, W1c = _bf16(x), _bf16(W1a), _bf16(W2a), _bf16(W1c)
+        if emulate_f16:
+            x, W1a, W2a, W1c = _f16(x), _f16(W1a), _f16(W2a), _f16(W1c)
         ha = torch.relu(x.double() @ W1a.double().T + b1a.double())
         hc = torch.relu(x.double() @ W1c.double().T + b1c.double())
-        if emulate_bf16:
-            ha = _bf16(ha.float()).double()
+        if emulate_f16:
+            ha = _f16(ha.float()).double()
         logits = ha @ W2a.double().T + b2a.double()
         value = hc @ W2c.double().T + b2c.double()
     finally:
@@ -62,14 +63,14 @@ def test_policy_logits_and_value_match_torch():
             obs = eng.observe(-1)
             out = policy_step(eng, packed, mode=1, apply_step=False, want_logits=True)
             torch.cuda.synchronize()
-            ref_l, ref_v = _torch_forward(net, obs, emulate_bf16=True)
+            ref_l, ref_v = _torch_forward(net, obs, emulate_f16=True)
             scale = float(ref_l.abs().max())
             err = float((out["logits"] - ref_l).abs().max())
-            assert err <= 1e-3 * scale, (err, scale)
-            assert float((out["value"] - ref_v).abs().max()) <= 1e-3 * max(1.0, float(ref_v.abs().max()))
-            full_l, full_v = _torch_forward(net, obs, emulate_bf16=False)
-            assert float((out["logits"] - full_l).abs().max()) <= 3e-2 * float(full_l.abs().max())
-            assert float((out["value"] - full_v).abs().max()) <= 3e-2 * max(1.0, float(full_v.abs().max()))
+            assert err <= 2e-4 * scale, (err, scale)
+            assert float((out["value"] - ref_v).abs().max()) <= 2e-4 * max(1.0, float(ref_v.abs().max()))
+            full_l, full_v = _torch_forward(net, obs, emulate_f16=False)
+            assert float((out["logits"] - full_l).abs().max()) <= 1e-3 * float(full_l.abs().max())
+            assert float((out["value"] - full_v).abs().max()) <= 1e-3 * max(1.0, float(full_v.abs().max()))
 
 
 def test_policy_softmax_argmax_entropy_and_mask():
