@@ -565,7 +565,7 @@ def run_train(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env_steps, games, trans, upd_ms, roll_ms = 0, 0, 0.0, [], []
+    env_steps, games, trans, upd_ms, roll_ms, dec_steps = 0, 0, 0.0, [], [], []
     barrier()
     ev0.record()
     for _ in range(args.steps):
@@ -578,7 +578,7 @@ def run_train(args):
         st = tr.update(batch)
         torch.cuda.synchronize()
         upd_ms.append(1e3 * (time.perf_counter() - t1)); roll_ms.append(1e3 * (t1 - t0))
-        games += args.games; trans = st["transitions"]
+        games += args.games; trans = st["transitions"]; dec_steps.append(int(batch["active"].shape[0]))
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -602,6 +602,7 @@ def run_train(args):
             "gpu_launches": None, "clocks": clocks,
             "games_per_sec": float(tot[1]) / (dev_ms * 1e-3), "agent_decisions_per_batch": trans,
             "rollout_ms": statistics.median(roll_ms), "update_ms": statistics.median(upd_ms),
+            "step_ms": [round(a + b, 2) for a, b in zip(roll_ms, upd_ms)], "decisions_per_step": dec_steps,
             "last": {k: tr.history[-1][k] if tr.history else None for k in ()},
         }
         print(json.dumps(line))
