@@ -720,23 +720,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     // divergence inside the tile loop or in a second kernel launch ----
     __syncthreads();                                   // every state / done / status write of the tile loop is visible to the CTA
     if (A.apply_step) {
+        // the list holds at most FINISH_GROUP tiles' worth of games (every game of a tile can be flagged, e.g. when a whole
+        // batch asks for fresh games), so a CTA with more tiles than that works through them in groups
+        constexpr int FINISH_GROUP = A_BYTES / 4 / TILE_M / PARTS * PARTS;         // 96 tiles = 12,288 entries
+        static_assert(FINISH_GROUP >= PARTS && FINISH_GROUP * TILE_M * 4 <= A_BYTES, "finish list exceeds the A region");
         uint32_t* list = reinterpret_cast<uint32_t*>(a_tile);
         __shared__ uint32_t n_list;
-        if (tid == 0) n_list = 0u;
-        __syncthreads();
-        for (int64_t tile = (int64_t)blockIdx.x + (int64_t)part * gridDim.x; tile < tiles; tile += (int64_t)PARTS * gridDim.x) {
-            const int64_t g = tile * TILE_M + row;
-            if (g < A.n && (A.state[3 * A.n + g] & (FLAG_ROUND_OVER | FLAG_FRESH_GAME))) list[atomicAdd(&n_list, 1u)] = (uint32_t)g;
-        }
-        __syncthreads();
-        const uint32_t total = n_list;
-        for (uint32_t i = (uint32_t)tid; i < total; i += THREADS) {
-            const uint32_t gidx = list[i];
-            Game<2> h;
-            h.load(A.state, A.n, (int64_t)gidx);
-            const uint32_t flags = h.misc & (FLAG_ROUND_OVER | FLAG_FRESH_GAME);
-            h.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
-            finish_game<POOL>(h, gidx, flags, rng, A.gid0, A.first_rule, A.apply_step == 2, A.state, A.n, A.done_out, A.status_out, sink);
+        const int64_t my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;       // tiles blockIdx.x + j * gridDim.x
+        for (int64_t j0 = 0; j0 < my_tiles; j0 += FINISH_GROUP) {
+            if (tid == 0) n_list = 0u;
+            __syncthreads();
+            const int64_t j1 = j0 + FINISH_GROUP < my_tiles ? j0 + FINISH_GROUP : my_tiles;
+            for (int64_t j = j0 + part; j < j1; j += PARTS) {
+                const int64_t g = ((int64_t)blockIdx.x + j * gridDim.x) * TILE_M + row;
+                if (g < A.n && (A.state[3 * A.n + g] & (FLAG_ROUND_OVER | FLAG_FRESH_GAME))) list[atomicAdd(&n_list, 1u)] = (uint32_t)g;
+            }
+            __syncthreads();
+            const uint32_t total = n_list;
+            for (uint32_t i = (uint32_t)tid; i < total; i += THREADS) {
+                const uint32_t gidx = list[i];
+                Game<2> h;
+                h.load(A.state, A.n, (int64_t)gidx);
+                const uint32_t flags = h.misc & (FLAG_ROUND_OVER | FLAG_FRESH_GAME);
+                h.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
+                finish_game<POOL>(h, gidx, flags, rng, A.gid0, A.first_rule, A.apply_step == 2, A.state, A.n, A.done_out, A.status_out, sink);
+            }
+            __syncthreads();                           // the list is reused by the next group
         }
     }
     __syncthreads();

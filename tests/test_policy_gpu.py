@@ -165,3 +165,31 @@ def test_policy_selfplay_auto_reset_counters():
         assert (rec[:, L.end_of_game] == 0).all() and (rec[:, 0:30].sum(axis=1) > 0).all()
         # every new_round after the initial azb_reset is counted once: finished games' rounds + running games' rounds
         assert c["rounds"] == c["turns"] + int(rec[:, L.turn_counter].sum()) - 2048
+
+
+def test_policy_finishing_phase_many_tiles_per_cta():
+    """More than 96 tiles per CTA with EVERY game flagged (a whole batch of ended games asking for fresh ones): the
+    finishing phase at the end of the policy kernel works through its dense list in groups; every slot ends up with a
+    fresh, playable game and the next step runs normally."""
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul, PackedPolicy, policy_step
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.layout import UnpackedLayout
+    with torch.no_grad():
+        n = 148 * 128 * 100 + 77                                  # 100+ tiles for every CTA of a 148-SM GPU, ragged tail
+        torch.manual_seed(0)
+        eng = BatchedAzul(n, 2, 1, 0, seed=3)
+        packed = PackedPolicy(eng, ActorCritic(136, 180))
+        eng.state[3] |= 1 << 12                                   # MISC bit 12: end_of_game in every slot
+        out = policy_step(eng, packed, mode=0, apply_step=True, auto_reset=True, want_mask=False)
+        assert bool((out["done"] == 1).all())                     # (the boards still hold tiles, so an action is reported; it is not played)
+        misc = eng.state[3]
+        assert int(((misc >> 12) & 1).sum()) == 0 and int((misc >> 28).sum()) == 0      # nobody ended, no transient flag left
+        L = UnpackedLayout(2)
+        for lo in (0, n // 2, n - 512):
+            sub = BatchedAzul(512, 2, 1, 0, seed=3, game_id_base=lo, reset=False)
+            sub.state.copy_(eng.state[:, lo:lo + 512])
+            rec = sub.export_records().cpu().numpy()
+            assert (rec[:, 0:30].sum(axis=1) == 20).all() and (rec[:, L.score:L.score + 2] == 0).all()   # 20 tiles on the factories
+        out = policy_step(eng, packed, mode=0, apply_step=True, auto_reset=True, want_mask=False)
+        assert bool((out["action"] < 180).all()) and int(out["status"].max()) == 0
+        assert eng.read_counters()["rounds"] == n and eng.read_counters()["steps"] == n
