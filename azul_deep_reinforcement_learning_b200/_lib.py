@@ -55,7 +55,7 @@ def load():
     L.azb_count_score.argtypes = [vp, vp, vp]
     L.azb_new_round.argtypes = [vp, vp, vp, vp]
     L.azb_round_flags.argtypes = [vp, vp, vp, vp]
-    L.azb_opponent_random.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.azb_opponent_random.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.azb_policy_pack_weights.argtypes = [vp] * 11
     L.azb_policy_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     f32 = ctypes.c_float

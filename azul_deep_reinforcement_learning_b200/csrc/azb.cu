@@ -467,19 +467,10 @@ __global__ void k_export(const uint32_t* __restrict__ s, int32_t* __restrict__ r
 __device__ __forceinline__ void obs_store(float* o, int i, float v) { o[i] = v; }
 __device__ __forceinline__ void obs_store(__nv_bfloat16* o, int i, float v) { o[i] = __float2bfloat16_rn(v); }
 
-// One warp per block and 32 games per warp: every thread builds its game's row in shared memory ([game][D + 1]), then the
-// warp copies the 32 rows -- contiguous in the output -- with coalesced stores (a thread writing its own row directly
-// touches 32 different sectors per store instruction).
+// GameRunner.get_state (game_runner.py:56-72) of one game: D = 32 + 52P values written to o[0..D)
 template <int P, typename T>
-__global__ void __launch_bounds__(32) k_observe(const uint32_t* __restrict__ s, int64_t n, int perspective, T* __restrict__ obs_out)
+__device__ __forceinline__ void observe_row(const Game<P>& gm, int perspective, T* o)
 {
-    constexpr int D = 32 + 52 * P;
-    __shared__ T tile[32 * (D + 1)];
-    const int lane = threadIdx.x;
-    const int64_t g0 = (int64_t)blockIdx.x * 32, g = g0 + lane;
-    Game<P> gm;
-    gm.load(s, n, g < n ? g : n - 1);
-    T* o = tile + lane * (D + 1);
     const int persp = perspective >= 0 ? perspective : gm.seat();
     for (int i = 0; i < 5; i++)
         for (int c = 0; c < 5; c++) {
@@ -509,15 +500,35 @@ __global__ void __launch_bounds__(32) k_observe(const uint32_t* __restrict__ s, 
     }
     const int nf = (int)gm.next_first_player();
     obs_store(o, 31 + 52 * P, nf > 0 ? (float)(((nf - 1 - persp) % P + P) % P + 1) : 0.0f);     // game_runner.py:58-61
+}
+
+// A warp's 32 observation rows ([lane][D + 1] in shared memory) -> the output, where they are contiguous: coalesced
+// stores (a thread writing its own row directly touches 32 different sectors per store instruction).
+template <int P, typename T>
+__device__ __forceinline__ void observe_flush(const T* tile, T* __restrict__ out, int64_t rows, int lane)
+{
+    constexpr int D = 32 + 52 * P;
     __syncwarp();
-    const int64_t rows = n - g0 < 32 ? n - g0 : 32;
-    T* out = obs_out + g0 * D;
     int row = 0, col = lane;
     for (int64_t idx = lane; idx < rows * D; idx += 32) {
         out[idx] = tile[row * (D + 1) + col];
         col += 32;
         if (col >= D) { col -= D; row++; }
     }
+}
+
+// One warp per block and 32 games per warp
+template <int P, typename T>
+__global__ void __launch_bounds__(32) k_observe(const uint32_t* __restrict__ s, int64_t n, int perspective, T* __restrict__ obs_out)
+{
+    constexpr int D = 32 + 52 * P;
+    __shared__ T tile[32 * (D + 1)];
+    const int lane = threadIdx.x;
+    const int64_t g0 = (int64_t)blockIdx.x * 32, g = g0 + lane;
+    Game<P> gm;
+    gm.load(s, n, g < n ? g : n - 1);
+    observe_row<P, T>(gm, perspective, tile + lane * (D + 1));
+    observe_flush<P, T>(tile, obs_out + g0 * D, n - g0 < 32 ? n - g0 : 32, lane);
 }
 
 // Azul.get_statistics raw integers (azul.py:314-315)
@@ -572,27 +583,41 @@ __global__ void k_op(Launch L, const uint8_t* __restrict__ action, const int8_t*
     gm.store(L.state, L.n, g);
 }
 
-// a14: GameRunner.step after the agent's own move: opponent loop, reward, done, next mask
+// a14: GameRunner.step after the agent's own move: opponent loop, reward, done, next mask -- and, optionally, the
+// observation of the resulting state from seat 1's perspective (the next decision's network input) in bfloat16, so
+// that a training rollout needs no separate observation launch.  Blocks are whole warps.
 template <int P, int POOL>
 __global__ void k_opponent_random(Launch L, int require_two, int16_t* __restrict__ player_score,
                                   int16_t* __restrict__ reward_out, uint8_t* __restrict__ done_out,
-                                  uint8_t* __restrict__ status_out, uint32_t* __restrict__ mask6_out)
+                                  uint8_t* __restrict__ status_out, uint32_t* __restrict__ mask6_out,
+                                  __nv_bfloat16* __restrict__ obs_out)
 {
+    constexpr int D = 32 + 52 * P;
+    extern __shared__ __align__(16) unsigned char opp_smem[];          // [warp][32][D + 1] bf16 when obs_out
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g >= L.n) return;
+    const bool valid = g < L.n;
     Game<P> gm;
-    gm.load(L.state, L.n, g);
-    const Philox rng{L.k0, L.k1};
-    uint32_t m[6];
-    const int32_t diff = opponent_random<P, POOL>(gm, rng, L.gid0 + (uint32_t)g, require_two != 0, m);
-    gm.store(L.state, L.n, g);
-    if (player_score) {
-        if (reward_out) reward_out[g] = (int16_t)(diff - (int32_t)player_score[g]);    // game_runner.py:51
-        player_score[g] = (int16_t)diff;                                                // game_runner.py:52
+    gm.load(L.state, L.n, valid ? g : L.n - 1);
+    if (valid) {
+        const Philox rng{L.k0, L.k1};
+        uint32_t m[6];
+        const int32_t diff = opponent_random<P, POOL>(gm, rng, L.gid0 + (uint32_t)g, require_two != 0, m);
+        gm.store(L.state, L.n, g);
+        if (player_score) {
+            if (reward_out) reward_out[g] = (int16_t)(diff - (int32_t)player_score[g]);    // game_runner.py:51
+            player_score[g] = (int16_t)diff;                                                // game_runner.py:52
+        }
+        if (done_out) done_out[g] = gm.ended() ? 1 : 0;
+        if (status_out) status_out[g] = (uint8_t)gm.status();
+        if (mask6_out) store_mask(mask6_out, L.n, g, m);
     }
-    if (done_out) done_out[g] = gm.ended() ? 1 : 0;
-    if (status_out) status_out[g] = (uint8_t)gm.status();
-    if (mask6_out) store_mask(mask6_out, L.n, g, m);
+    if (obs_out) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(opp_smem) + (size_t)warp * 32 * (D + 1);
+        const int64_t g0 = g - lane;
+        observe_row<P, __nv_bfloat16>(gm, 0, tile + lane * (D + 1));
+        if (g0 < L.n) observe_flush<P, __nv_bfloat16>(tile, obs_out + g0 * D, L.n - g0 < 32 ? L.n - g0 : 32, lane);
+    }
 }
 
 template <int P>
@@ -872,13 +897,17 @@ int azb_new_round(azb_t* h, uint32_t* state, const int8_t* draws20, void* stream
 }
 
 int azb_opponent_random(azb_t* h, uint32_t* state, int require_two, int16_t* player_score, int16_t* reward_out,
-                        uint8_t* done_out, uint8_t* status_out, uint32_t* mask6_out, void* stream)
+                        uint8_t* done_out, uint8_t* status_out, uint32_t* mask6_out, void* obs_bf16_out, void* stream)
 {
     CHECK_HANDLE(h);
     if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     const Launch L = make_launch(h, state);
-    DISPATCH_PP(h, (k_opponent_random<P, POOL><<<grid_of(h), h->block_threads, 0, (cudaStream_t)stream>>>(
-                       L, require_two, player_score, reward_out, done_out, status_out, mask6_out)));
+    // with the observation output every warp stages 32 rows in shared memory: 128-thread blocks keep that under 48 KB
+    const int threads = obs_bf16_out ? 128 : h->block_threads;
+    const size_t smem = obs_bf16_out ? (size_t)(threads / 32) * 32 * (32 + 52 * h->players + 1) * sizeof(__nv_bfloat16) : 0;
+    const dim3 grid((unsigned)((h->n_games + threads - 1) / threads));
+    DISPATCH_PP(h, (k_opponent_random<P, POOL><<<grid, threads, smem, (cudaStream_t)stream>>>(
+                       L, require_two, player_score, reward_out, done_out, status_out, mask6_out, (__nv_bfloat16*)obs_bf16_out)));
     CHECK_LAUNCH();
     return 0;
 }

@@ -231,17 +231,21 @@ class BatchedAzul:
             assert draws.numel() == 20 * self.n_games
         _lib.check(self.lib.azb_new_round(self._h, _ptr(self.state), _ptr(draws), self._stream()))
 
-    def opponent_random(self, player_score, require_two=True, want_mask=True):
+    def opponent_random(self, player_score, require_two=True, want_mask=True, want_obs=False):
         """``GameRunner.step``'s opponent loop + reward for every game (K a14).  ``player_score`` (int16 [G]) is
-        updated in place; returns dict(reward int16, done, status uint8[, mask])."""
+        updated in place; returns dict(reward int16, done, status uint8[, mask][, obs bfloat16 [G, 32 + 52P]: the
+        observation of the resulting state from seat 1's perspective])."""
         n = self.n_games
         reward, done, status = self._new((n,), torch.int16), self._new((n,), torch.uint8), self._new((n,), torch.uint8)
         mask = self._new((MASK_WORDS, n), torch.int32) if want_mask else None
+        obs = self._new((n, 32 + 52 * self.players), torch.bfloat16) if want_obs else None
         _lib.check(self.lib.azb_opponent_random(self._h, _ptr(self.state), int(bool(require_two)), _ptr(player_score),
-                                               _ptr(reward), _ptr(done), _ptr(status), _ptr(mask), self._stream()))
+                                               _ptr(reward), _ptr(done), _ptr(status), _ptr(mask), _ptr(obs), self._stream()))
         out = {"reward": reward, "done": done, "status": status}
         if want_mask:
             out["mask"] = mask
+        if want_obs:
+            out["obs"] = obs
         return out
 
     def round_flags(self):

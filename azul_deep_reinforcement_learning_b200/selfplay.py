@@ -14,10 +14,13 @@ DEFAULT_RULES = {"first_player": "Random", "tile_pool": "Lid"}      # game_runne
 
 
 class BatchedGameRunner:
-    def __init__(self, n_games, rules=None, seed=0, device=0, game_id_base=0, opponent=None, opponent_mode=0):
+    def __init__(self, n_games, rules=None, seed=0, device=0, game_id_base=0, opponent=None, opponent_mode=0,
+                 record_obs=False):
         """``opponent``: None = RandomAgent (game_runner.py:29-30) or a ``PackedPolicy`` = a frozen ``Agent``
-        (scripts/run_batch.py:6-8) whose moves come from the fused policy kernel."""
-        self.opponent, self.opponent_mode = opponent, opponent_mode
+        (scripts/run_batch.py:6-8) whose moves come from the fused policy kernel.  ``record_obs``: the opponent /
+        reward kernel also writes the next decision's observation (``self.obs``, bfloat16 [G, 136])."""
+        self.opponent, self.opponent_mode, self.record_obs = opponent, opponent_mode, record_obs
+        self.obs = None
         rules = DEFAULT_RULES if rules is None else rules
         pool, first = rules_to_ints(2, rules)
         self.engine = BatchedAzul(n_games, 2, pool, first, seed=seed, device=device, game_id_base=game_id_base, reset=False)
@@ -32,9 +35,9 @@ class BatchedGameRunner:
         self.player_score.zero_()
         if self.opponent is not None:                 # a fresh board always offers seat 1 >= 2 actions, so the
             self._opponent_policy_moves()             # ":46" and ":84" loop conditions coincide here
-        out = self.engine.opponent_random(self.player_score, require_two=False)
+        out = self.engine.opponent_random(self.player_score, require_two=False, want_obs=self.record_obs)
         self.player_score.zero_()                     # game_runner.py:81: the score baseline restarts at 0
-        self.mask = out["mask"]
+        self.mask, self.obs = out["mask"], out.get("obs")
         return out
 
     def get_state(self):
@@ -57,8 +60,8 @@ class BatchedGameRunner:
     def _after_agent_move(self):
         if self.opponent is not None:
             self._opponent_policy_moves()
-        out = self.engine.opponent_random(self.player_score, require_two=True)
-        self.mask = out["mask"]
+        out = self.engine.opponent_random(self.player_score, require_two=True, want_obs=self.record_obs)
+        self.mask, self.obs = out["mask"], out.get("obs")
         return out
 
     def step(self, actions):
@@ -84,8 +87,8 @@ RAW_KEYS = ("obs", "mask", "reward", "value", "logp", "entropy", "action", "stat
 def _one_decision(runner, packed, rec, record_obs):
     """One agent decision for every game; appends the raw outputs of the kernels (what ``NNRunner.run_episode``
     records, nn_runner.py:27-45) without any per-decision bookkeeping -- see :func:`_alive_chain`."""
-    if record_obs:
-        rec["obs"].append(runner.engine.observe_bf16(0))
+    if record_obs:                           # the previous opponent / reward launch already wrote it when asked to
+        rec["obs"].append(runner.obs if runner.obs is not None else runner.engine.observe_bf16(0))
     rec["mask"].append(runner.mask)          # every opponent_random call returns a new tensor: no copy needed
     out = runner.step_policy(packed)
     rec["reward"].append(out["reward"])
@@ -171,15 +174,16 @@ class GraphedEpisodes:
         with torch.cuda.graph(self.graph):
             runner.reset()
             self.rec = self._body(decisions)
-            self.mask_out = runner.mask
-        # continuation: starts from the engine's current state and the legal mask in self.mask_in (copied in before a
+            self.mask_out, self.obs_out = runner.mask, runner.obs
+        # continuation: starts from the engine's current state and the legal mask / observation in self.mask_in / self.obs_in (copied in before a
         # replay: a graph reads fixed addresses)
         self.mask_in = torch.zeros_like(self.mask_out)
+        self.obs_in = None if self.obs_out is None else torch.zeros_like(self.obs_out)
         self.graph_more = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_more, pool=self.graph.pool()):
-            runner.mask = self.mask_in
+            runner.mask, runner.obs = self.mask_in, self.obs_in
             self.rec_more = self._body(more)
-            self.mask_more = runner.mask
+            self.mask_more, self.obs_more = runner.mask, runner.obs
         # the first replay of a graph pays its upload (tens of ms): pay it here, not in the middle of training
         # (every run() starts with the reset inside the first graph, so the games played here are discarded)
         self.graph.replay()
@@ -197,16 +201,18 @@ class GraphedEpisodes:
         self.graph.replay()
         chunk = dict(self.rec)
         chunk["active"], alive = _alive_chain(chunk["status"], chunk["done"], torch.ones(G, dtype=torch.bool, device=dev))
-        chunks, mask, t = [chunk], self.mask_out, self.decisions
+        chunks, mask, obs, t = [chunk], self.mask_out, self.obs_out, self.decisions
         while t < max_decisions and bool(alive.any()):
             self.mask_in.copy_(mask)
+            if obs is not None:
+                self.obs_in.copy_(obs)
             self.graph_more.replay()
             chunk = {k: v.clone() for k, v in self.rec_more.items()}
             chunk["active"], alive = _alive_chain(chunk["status"], chunk["done"], alive)
             chunks.append(chunk)
-            mask = self.mask_more
+            mask, obs = self.mask_more, self.obs_more
             t += self.more
-        self.runner.mask = mask
+        self.runner.mask, self.runner.obs = mask, obs
         return _finish_batch(chunks, alive)
 
 

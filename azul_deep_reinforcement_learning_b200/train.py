@@ -112,7 +112,7 @@ class SelfPlayTrainer:
         self.params = list(self.net.parameters())
         self.opt = torch.optim.Adam(self.params, lr=learning_rate)       # agent.py:37
         self.runner = BatchedGameRunner(games_per_rank, rules=rules, seed=seed, device=device,
-                                        game_id_base=parallel.shard(rank, games_per_rank))
+                                        game_id_base=parallel.shard(rank, games_per_rank), record_obs=True)
         self.packed = PackedPolicy(self.runner.engine, self.net)
         self.graphed = GraphedEpisodes(self.runner, self.packed) if use_cuda_graph else None
         self.history = []

@@ -144,9 +144,11 @@ int azb_round_flags(azb_t* h, const uint32_t* state, uint8_t* flags, void* strea
  * (RandomAgent, :87-97, Philox words): opponent moves until it is seat 1's turn with >= 2 legal actions
  * (require_two != 0, :46) or just seat 1's turn (require_two == 0, GameRunner.reset :84-85) or the game
  * is over; then reward = (score1 - score2 after count_score on a copy) - player_score, player_score updated
- * in place (int16 [G], :48-52), done = is_end_of_game, mask6 = legal mask of the resulting state. */
+ * in place (int16 [G], :48-52), done = is_end_of_game, mask6 = legal mask of the resulting state.
+ * obs_bf16_out (optional): GameRunner.get_state of the resulting state from seat 1's perspective, bfloat16 [G][32 + 52P]
+ * (what azb_observe_bf16(perspective 0) would write) -- the next decision's network input, recorded by training. */
 int azb_opponent_random(azb_t* h, uint32_t* state, int require_two, int16_t* player_score, int16_t* reward_out,
-                        uint8_t* done_out, uint8_t* status_out, uint32_t* mask6_out, void* stream);
+                        uint8_t* done_out, uint8_t* status_out, uint32_t* mask6_out, void* obs_bf16_out, void* stream);
 
 /* ---- K4: the policy/value network of azulnet/model.py:12-41 fused with its callers ------------
  * ActorCritic(136, 180, hidden 180): actor 136 -> 180 -> ReLU -> 180 logits, critic 136 -> 180 -> ReLU -> 1.

@@ -118,8 +118,8 @@ def test_cuda_graph_rollout_equals_eager():
     from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner, GraphedEpisodes, run_episodes
     torch.manual_seed(2)
     net = ActorCritic(136, 180)
-    a = BatchedGameRunner(768, seed=21)
-    b = BatchedGameRunner(768, seed=21)
+    a = BatchedGameRunner(768, seed=21)                   # records observations with a separate azb_observe_bf16 launch
+    b = BatchedGameRunner(768, seed=21, record_obs=True)  # the opponent / reward kernel writes them
     pa, pb = PackedPolicy(a.engine, net), PackedPolicy(b.engine, net)
     graphed = GraphedEpisodes(b, pb, decisions=40)        # (its warm-up advances b's per-slot RNG position)
     for rep in range(2):                                  # replaying twice: buffers are reused correctly
@@ -131,7 +131,7 @@ def test_cuda_graph_rollout_equals_eager():
         assert not bool(eager["active"][T:].any()) and not bool(g["active"][T:].any())
         act = eager["active"][:T]
         assert torch.equal(act, g["active"][:T])
-        for k in ("reward", "action", "logp", "value", "entropy"):
+        for k in ("reward", "action", "logp", "value", "entropy", "obs"):
             assert torch.equal(eager[k][:T][act], g[k][:T][act]), (rep, k)
         assert torch.equal(a.engine.state, b.engine.state)
 
