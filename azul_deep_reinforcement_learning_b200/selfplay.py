@@ -8,7 +8,7 @@ softmax + sampling + the agent's ``Azul.step``) and the opponent loop + reward (
 """
 import torch
 
-from .engine import BatchedAzul, PackedPolicy, mask_to_bool, policy_step, rules_to_ints
+from .engine import BatchedAzul, mask_to_bool, policy_step, rules_to_ints
 
 DEFAULT_RULES = {"first_player": "Random", "tile_pool": "Lid"}      # game_runner.py:23
 
