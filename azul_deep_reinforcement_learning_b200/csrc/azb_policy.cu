@@ -391,11 +391,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     // one-time: barriers, tensor memory, and the weight image -> shared memory as bulk async copies (TMA, no registers
     // and no thread time: the first observation tile is built while the 180 KB arrive)
     const uint32_t bar_w = bar1 + 24;
+    // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream is still draining
+    // (its launch latency, barrier setup and TMEM allocation then overlap that tail); nothing the previous kernel may have
+    // written -- game state, the weight image -- is read before this point.  The next grid is released right away: it
+    // cannot get an SM before one of this grid's CTAs exits, and it waits here too.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
         mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"((uint32_t)PACKED_BYTES) : "memory");
         constexpr uint32_t CHUNK = 32768;
         for (uint32_t off = 0; off < (uint32_t)PACKED_BYTES; off += CHUNK) {
@@ -800,7 +808,13 @@ template <int POOL, int MODE>
 static int launch_policy(const PolicyArgs& A, int grid, cudaStream_t stream)
 {
     AZB_CUDA(cudaFuncSetAttribute(k_policy<POOL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    k_policy<POOL, MODE><<<grid, THREADS, SMEM_BYTES, stream>>>(A);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see griddepcontrol in k_policy
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    AZB_CUDA(cudaLaunchKernelEx(&cfg, k_policy<POOL, MODE>, A));
     return 0;
 }
 
