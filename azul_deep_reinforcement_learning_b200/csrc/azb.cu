@@ -108,7 +108,7 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
     if (O.mask6 || O.status) {
         uint32_t m[6];
         legal_mask(gm, m);
-        if (!gm.ended() && (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u && gm.current_player() != 0u)
+        if (!gm.ended() && m[0] == 0u /* words 1..5 are subsets of word 0 */ && gm.current_player() != 0u)
             status |= ST_STUCK;
         if (O.mask6) {
             if (policy) {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, 8) k_step(Launch L, const uin
             const bool any_moved = __any_sync(0xFFFFFFFFu, moved);
             uint32_t m[6];
             legal_mask(gm, m);
-            if (!round_over && !gm.ended() && (m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u && gm.current_player() != 0u)
+            if (!round_over && !gm.ended() && m[0] == 0u /* words 1..5 are subsets of word 0 */ && gm.current_player() != 0u)
                 status |= ST_STUCK;
             if (any_moved) gm.store(tile, 32, lane);
             if (O.mask6) {

@@ -755,7 +755,7 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
         if (remaining > 0 && phase == 0) {
             uint32_t m[6];
             legal_mask(g, m);
-            if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5]) == 0u) {
+            if (m[0] == 0u) {                                         // words 1..5 are subsets of word 0 (the floor takes any source)
                 sink.add(6, 1);                                       // stuck round: abort the game
                 phase = 2;
             } else {
