@@ -1,4 +1,6 @@
 """``azulnet.agent`` drop-in: the A2C agent (reference ``azulnet/agent.py:9-81``)."""
+import os
+
 import numpy as np
 import torch
 import torch.optim as optim
@@ -6,6 +8,24 @@ import torch.optim as optim
 from .model import ActorCritic
 
 _KEYS = ["reward", "actor_loss", "critic_loss", "entropy_loss", "ac_loss"]
+
+
+def load_ac_net(base_net_file, num_in=136, num_out=180):
+    """Load a saved network.  ``base_net_file`` is a path, or -- like the reference (agent.py:36) -- a bare name that
+    resolves to ``/results/<name>.mx``; ``<name>.pt`` next to it is tried too.  Accepted contents: a pickled
+    ``ActorCritic`` module (what the reference writes, nn_runner.py:83-84), a bare ``state_dict`` (what this package's
+    ``NNRunner.train`` writes) or the trainer's checkpoint dict ``{"ac_net": state_dict, "optimizer": ..., "batch": n}``."""
+    candidates = [base_net_file, base_net_file + ".pt", base_net_file + ".mx",
+                  "/results/" + base_net_file + ".mx", "/results/" + base_net_file + ".pt"]
+    path = next((c for c in candidates if os.path.isfile(c)), None)
+    if path is None:
+        raise FileNotFoundError("no saved network among " + ", ".join(candidates))
+    obj = torch.load(path, map_location="cpu", weights_only=False)
+    if isinstance(obj, torch.nn.Module):
+        return obj
+    net = ActorCritic(num_in, num_out)
+    net.load_state_dict(obj["ac_net"] if isinstance(obj, dict) and "ac_net" in obj else obj)
+    return net
 
 
 class Agent:
@@ -35,7 +55,7 @@ class Agent:
             if base_net == "Blue Adam":
                 self.ac_net = ActorCritic(self.num_in, self.num_out)
         else:
-            self.ac_net = torch.load("/results/" + base_net_file + ".mx", weights_only=False)   # agent.py:36
+            self.ac_net = load_ac_net(base_net_file, self.num_in, self.num_out)                  # agent.py:36
         self.ac_optimizer = optim.Adam(self.ac_net.parameters(), lr=learning_rate)
 
     def update(self, qvals, rewards, values, log_probs, entropy):

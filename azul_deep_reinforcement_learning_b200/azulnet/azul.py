@@ -274,6 +274,7 @@ class Azul:
             raise IllegalMove                                            # azul.py:301-302, state untouched
         self._eng.move(torch.tensor([a], dtype=torch.uint8))             # azul.py:304
         self._total_steps += 1
+        steps = self._total_steps                                        # azb_move does not count steps: carried on the host
         ended = False
         if self._flags() & 1:                                            # azul.py:306
             self._eng.count_score()                                      # azul.py:307
@@ -285,7 +286,6 @@ class Azul:
                 self._new_round_on_device()                              # azul.py:311
         else:
             self._eng.next_player()                                      # azul.py:313
-        steps = self._total_steps
         self._from_device()
         self._total_steps = steps
         if ended:

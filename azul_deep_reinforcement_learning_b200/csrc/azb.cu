@@ -689,6 +689,9 @@ int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_p
     if (tile_pool != AZB_POOL_RANDOM && tile_pool != AZB_POOL_LID) return azb_fail(AZB_E_INVALID, "tile_pool must be 0 (Random) or 1 (Lid)%s");
     if (first_player < 0 || first_player > players) return azb_fail(AZB_E_INVALID, "first_player must be 0 (Random) or 1..players%s");   // IllegalRule, azul.py:40-41
     if (n_games < 1 || n_games > (int64_t)1 << 31) return azb_fail(AZB_E_INVALID, "n_games out of range%s");
+    // the Philox counter carries a 32-bit global game id: ids beyond 2^32 would alias streams
+    if (game_id_base > 0xFFFFFFFFull || game_id_base + (uint64_t)n_games > (1ull << 32))
+        return azb_fail(AZB_E_INVALID, "game_id_base + n_games exceeds the 32-bit global game id of the draw schedule%s");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -902,8 +905,9 @@ int azb_opponent_random(azb_t* h, uint32_t* state, int require_two, int16_t* pla
     CHECK_HANDLE(h);
     if (!state) return azb_fail(AZB_E_INVALID, "state is null%s");
     const Launch L = make_launch(h, state);
-    // with the observation output every warp stages 32 rows in shared memory: 128-thread blocks keep that under 48 KB
-    const int threads = obs_bf16_out ? 128 : h->block_threads;
+    // with the observation output every warp stages 32 rows in shared memory (32 x (33 + 52P) bf16 per warp): 128-thread
+    // blocks for 2 / 3 players (35 / 47 KB), 64-thread blocks for 4 players (31 KB) stay under the 48 KB default limit
+    const int threads = obs_bf16_out ? (h->players == 4 ? 64 : 128) : h->block_threads;
     const size_t smem = obs_bf16_out ? (size_t)(threads / 32) * 32 * (32 + 52 * h->players + 1) * sizeof(__nv_bfloat16) : 0;
     const dim3 grid((unsigned)((h->n_games + threads - 1) / threads));
     DISPATCH_PP(h, (k_opponent_random<P, POOL><<<grid, threads, smem, (cudaStream_t)stream>>>(

@@ -47,15 +47,19 @@ class BatchedGameRunner:
     def get_valid_moves(self):
         return mask_to_bool(self.mask)
 
-    def _opponent_policy_moves(self, max_rounds=16):
+    def _opponent_policy_moves(self, max_rounds=64, check_every=1):
         """``while (current_player != 1 or #valid < 2) and not end: opponent_move()`` (game_runner.py:46-47) with an
         Agent opponent: each launch lets every game that is still in the opponent's hands take one policy decision
-        (``act_filter = 1``); typically one or two launches per agent decision."""
-        for _ in range(max_rounds):
+        (``act_filter = 1``); typically one or two launches per agent decision.  The loop runs until no game acted
+        (checked on the host every ``check_every`` launches: a launch in which nobody acts changes nothing); a round
+        is at most 20 takes long, so ``max_rounds`` launches can only be exceeded by a bug -- that raises."""
+        for i in range(max_rounds):
             out = policy_step(self.engine, self.opponent, mode=self.opponent_mode, apply_step=True, want_mask=False,
                               act_filter=1)
-            if not bool((out["action"] != 255).any()):
+            if (i + 1) % check_every == 0 and not bool((out["action"] != 255).any()):
                 return
+        if bool((out["action"] != 255).any()):
+            raise RuntimeError("opponent loop did not hand the move back to seat 1 within %d policy launches" % max_rounds)
 
     def _after_agent_move(self):
         if self.opponent is not None:

@@ -14,6 +14,7 @@ gradient all-reduce per update (C1, 82,081 fp32 values) and the statistics reduc
 """
 import argparse
 import csv
+import os
 import time
 
 import torch
@@ -128,21 +129,16 @@ class SelfPlayTrainer:
             batch["stats"] = self.runner.engine.stats().to(torch.float64)
         return batch
 
-    def update(self, batch, chunk=1 << 18):
-        """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch.
+    def load_parameters(self, state_dict):
+        """Replace the network parameters (e.g. a checkpoint or a reference ``ac_net.state_dict()``); Adam restarts."""
+        self.net.load_state_dict({k: v.to(self.device) for k, v in state_dict.items()})
+        self.opt = torch.optim.Adam(self.params, lr=self.opt.param_groups[0]["lr"])
 
-        Gradients are accumulated as SUMS over the local decisions; one all-reduce carries them together with the
-        decision count and the batch statistics, then every rank divides by the global count (the means of
-        agent.py:47-56 over the global batch) and takes the same Adam step.  The host is not synchronised before
-        the statistics are read at the end."""
-        act = batch["active"]
-        T, G = act.shape
-        sel = act.reshape(-1).nonzero(as_tuple=True)[0]
-        n_local = int(sel.numel())
-        obs = batch["obs"].reshape(T * G, -1)
-        masks = batch["mask"].permute(0, 2, 1).reshape(T * G, 6)
-        action = batch["action"].reshape(-1)
-        qval = batch["qval"].reshape(-1)
+    def accumulate_gradients(self, obs, masks, action, qval, chunk=1 << 18):
+        """Forward recomputation + the loss of ``Agent.update`` (agent.py:45-56) + back-propagation for N recorded
+        decisions: obs bfloat16 / float32 [N,136], masks int32 [N,6] (legal-mask words), action int64 [N], qval float32 [N].
+        Leaves the SUMS over the decisions (not yet divided by a count) in ``p.grad`` and returns the float64 [3] sums of
+        the actor / critic / entropy terms."""
         self.opt.zero_grad(set_to_none=False)
         for p in self.params:
             if p.grad is None:
@@ -155,16 +151,44 @@ class SelfPlayTrainer:
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32_update
         try:
-            for lo in range(0, n_local, chunk):
-                idx = sel[lo:lo + chunk]
-                x = obs[idx].float()
+            for lo in range(0, int(obs.shape[0]), chunk):
+                x = obs[lo:lo + chunk].float()
                 logits, value = network_outputs(self.net, x)
                 dlogits, dvalue = self.runner.engine.a2c_loss_grad(
-                    logits.detach(), value.detach().contiguous(), masks[idx].contiguous(), action[idx], qval[idx],
-                    1.0, (ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF), sums)
+                    logits.detach(), value.detach().contiguous(), masks[lo:lo + chunk].contiguous(), action[lo:lo + chunk],
+                    qval[lo:lo + chunk], 1.0, (ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF), sums)
                 torch.autograd.backward([logits, value], [dlogits, dvalue])
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
+        return sums
+
+    def update_decisions(self, obs, masks, action, qval):
+        """One single-process ``Agent.update`` (agent.py:39-62) on N recorded decisions: means over the N decisions,
+        Adam step.  Returns the loss statistics of agent.py:58-59; ``self.last_grads`` holds the mean gradients."""
+        n = int(obs.shape[0])
+        sums = self.accumulate_gradients(obs, masks, action, qval)
+        for p in self.params:
+            p.grad.mul_(1.0 / n)
+        self.last_grads = {name: p.grad.clone() for name, p in self.net.named_parameters()}
+        self.opt.step()
+        a, c, e = (sums / n).cpu().tolist()
+        return {"actor_loss": a, "critic_loss": c, "entropy_loss": e,
+                "ac_loss": ACTOR_COEFF * a + CRITIC_COEFF * c + ENTROPY_COEFF * e}
+
+    def update(self, batch):
+        """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch.
+
+        Gradients are accumulated as SUMS over the local decisions; one all-reduce carries them together with the
+        decision count and the batch statistics, then every rank divides by the global count (the means of
+        agent.py:47-56 over the global batch) and takes the same Adam step.  The host is not synchronised before
+        the statistics are read at the end."""
+        act = batch["active"]
+        T, G = act.shape
+        sel = act.reshape(-1).nonzero(as_tuple=True)[0]
+        n_local = int(sel.numel())
+        obs = batch["obs"].reshape(T * G, -1)[sel]
+        masks = batch["mask"].permute(0, 2, 1).reshape(T * G, 6)[sel]
+        sums = self.accumulate_gradients(obs, masks, batch["action"].reshape(-1)[sel], batch["qval"].reshape(-1)[sel])
         t0 = time.perf_counter()
         one = torch.ones(1, dtype=torch.float64, device=self.device)
         wins = (batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum().reshape(1)
@@ -187,9 +211,31 @@ class SelfPlayTrainer:
         out["win_percent"] = s[16] / games
         return out
 
-    def train(self, batches=1000, net_name=None, log=print):
+    def save_checkpoint(self, path, batch):
+        """``<net_name>.pt``: network ``state_dict`` (parameter names of model.py:17-21, loadable by
+        ``Agent(base_net_file=...)``), optimiser state and the number of batches done (nn_runner.py:83-84 saves the
+        pickled module instead)."""
+        torch.save({"ac_net": {k: v.detach().cpu() for k, v in self.net.state_dict().items()},
+                    "optimizer": self.opt.state_dict(), "batch": int(batch)}, path)
+
+    def load_checkpoint(self, path):
+        """Resume from :meth:`save_checkpoint` output (or from any file ``Agent(base_net_file=...)`` accepts: then Adam
+        restarts).  Returns the number of batches already done."""
+        from .azulnet.agent import load_ac_net
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+        if isinstance(obj, dict) and "ac_net" in obj:
+            self.net.load_state_dict({k: v.to(self.device) for k, v in obj["ac_net"].items()})
+            if "optimizer" in obj:
+                self.opt.load_state_dict(obj["optimizer"])
+            return int(obj.get("batch", 0))
+        self.load_parameters(load_ac_net(path).state_dict())
+        return 0
+
+    def train(self, batches=1000, net_name=None, log=print, start_batch=0, checkpoint_every=1000):
+        """Batches ``start_batch + 1 .. batches``.  With ``net_name``: one CSV row per batch in ``<net_name>.csv``
+        (appended to when resuming) and ``<net_name>.pt`` every ``checkpoint_every`` batches and at the end."""
         writer = fh = None
-        for b in range(batches):
+        for b in range(start_batch, batches):
             t0 = time.perf_counter()
             batch = self.rollout()
             torch.cuda.synchronize(self.device)
@@ -203,14 +249,15 @@ class SelfPlayTrainer:
             if self.rank == 0:
                 if net_name is not None:
                     if writer is None:
-                        fh = open(net_name + ".csv", "w", newline="")
+                        resume = start_batch > 0 and os.path.exists(net_name + ".csv")
+                        fh = open(net_name + ".csv", "a" if resume else "w", newline="")
                         writer = csv.DictWriter(fh, fieldnames=list(st.keys()))
-                        writer.writeheader()
+                        if not resume:
+                            writer.writeheader()
                     writer.writerow(st)
                     fh.flush()
-                    if (b + 1) % 1000 == 0 or b + 1 == batches:           # nn_runner.py:83-84, as a state_dict
-                        torch.save({"ac_net": self.net.state_dict(), "optimizer": self.opt.state_dict(), "batch": b + 1},
-                                   net_name + ".pt")
+                    if (b + 1) % checkpoint_every == 0 or b + 1 == batches:  # nn_runner.py:83-84, as a state_dict
+                        self.save_checkpoint(net_name + ".pt", b + 1)
                 if log:
                     log("batch %d: %.0f games/s  reward %.2f  score %.1f vs %.1f  win %.1f%%  loss %.3f" % (
                         b + 1, st["games_per_sec"], st["reward"], st["player_score"], st["opponent_score"],
@@ -227,13 +274,18 @@ def main(argv=None):
     ap.add_argument("--batches", type=int, default=1000)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--resume", default=None, metavar="FILE",
+                    help="continue from a checkpoint written by this script (<net_name>.pt) or start from any saved "
+                         "network Agent(base_net_file=...) accepts")
+    ap.add_argument("--checkpoint-every", type=int, default=1000)
     args = ap.parse_args(argv)
     rank, world, local = parallel.world()
     if world > 1:
         parallel.init("nccl", local)
     torch.cuda.set_device(local)
     tr = SelfPlayTrainer(args.batch_size, learning_rate=args.lr, seed=args.seed, device=local, rank=rank, world=world)
-    tr.train(batches=args.batches, net_name=args.net_name)
+    start = tr.load_checkpoint(args.resume) if args.resume else 0
+    tr.train(batches=args.batches, net_name=args.net_name, start_batch=start, checkpoint_every=args.checkpoint_every)
     if world > 1:
         dist.destroy_process_group()
 

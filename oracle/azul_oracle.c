@@ -548,6 +548,53 @@ int ao_opponent_random(int32_t *rec, int players, int pool, uint64_t seed, uint3
 
 int ao_random_action(const uint32_t *mask6, uint32_t word) { return random_action(mask6, word); }
 
+/* GameRunner.get_state (game_runner.py:56-72): displays (25) | centre (6) | pattern_lines[order] (25P) |
+ * walls[order] (25P) | floors[order] (P) | score[order] (P) | next first player seen from `perspective` (1);
+ * order = [perspective] + the other seats ascending (:57).  obs has 32 + 52P entries. */
+void ao_observe(const int32_t *rec, int players, int perspective, int32_t *obs)
+{
+    ao_game g; from_record(&g, rec, players);
+    int P = players, order[MAXP], n = 0, k = 0;
+    if (perspective < 0) perspective = seat(&g);                       /* opponent_move, game_runner.py:38 */
+    order[n++] = perspective;
+    for (int p = 0; p < P; p++) if (p != perspective) order[n++] = p;
+    for (int i = 0; i < 5; i++) for (int c = 0; c < 5; c++) obs[k++] = g.displays[i][c];
+    for (int c = 0; c < 6; c++) obs[k++] = g.center[c];
+    for (int s = 0; s < P; s++) for (int r = 0; r < 5; r++) for (int c = 0; c < 5; c++) obs[k++] = g.pattern_lines[order[s]][r][c];
+    for (int s = 0; s < P; s++) for (int r = 0; r < 5; r++) for (int c = 0; c < 5; c++) obs[k++] = g.walls[order[s]][r][c] != 0;
+    for (int s = 0; s < P; s++) obs[k++] = g.floors[order[s]];
+    for (int s = 0; s < P; s++) obs[k++] = g.score[order[s]];
+    /* :58-61; Python's % is non-negative */
+    obs[k++] = g.next_first_player > 0 ? (((g.next_first_player - 1 - perspective) % P + P) % P) + 1 : 0;
+}
+
+/* The loop test of GameRunner.step / GameRunner.reset as a function of the state alone:
+ *   step  (game_runner.py:46): (current_player != 1 or #valid < 2) and not is_end_of_game()   [require_two != 0]
+ *   reset (game_runner.py:84): current_player != 1                                            [require_two == 0]
+ * (the reference's is_end_of_game() recomputes the test from the walls, azul.py:184-191).  1 = the opponent moves next. */
+int ao_runner_continues(const int32_t *rec, int players, int require_two)
+{
+    ao_game g; from_record(&g, rec, players);
+    if (!require_two) return g.current_player != 1;
+    uint32_t m[6]; legal_mask(&g, m);
+    int n_valid = 0;
+    for (int p = 0; p < 6; p++) n_valid += __builtin_popcount(m[p]);
+    return (g.current_player != 1 || n_valid < 2) && !is_end_of_game(&g);
+}
+
+/* Azul.get_statistics (azul.py:314-315) as ten integers: player_score, opponent_score, rounds,
+ * first_player_stats[0], sum(first_player_stats), -floor_penalty[0], max_combo[0], completed rows,
+ * completed columns, completed colours of seat 0 (percent_first_player = 100 * [3] / [4], win = [0] > [1]) */
+void ao_statistics(const int32_t *rec, int players, int32_t *out)
+{
+    ao_game g; from_record(&g, rec, players);
+    int fps = 0;
+    for (int p = 0; p < players; p++) fps += g.first_player_stats[p];
+    out[0] = g.score[0]; out[1] = g.score[1]; out[2] = g.turn_counter; out[3] = g.first_player_stats[0]; out[4] = fps;
+    out[5] = -g.floor_penalty[0]; out[6] = g.max_combo[0]; out[7] = g.completed_lines[0][0];
+    out[8] = g.completed_lines[0][2]; out[9] = g.completed_lines[0][1];
+}
+
 /* SPEC of azb_rollout_random: K env steps per slot, random agents on every seat, auto-reset.
  *   per step:  mask; if empty -> STUCK: count, reset, recompute mask
  *              action word = Philox(gid, T>>2, ACTION, 0)[T&3]

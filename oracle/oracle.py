@@ -48,11 +48,14 @@ def lib():
         L.ao_random_action.argtypes = [u32p, U32]
         L.ao_opponent_random.argtypes = [i32p, I, I, U64, U32, I, u32p]
         L.ao_philox4x32_10.argtypes = [u32p, u32p, u32p]
+        L.ao_observe.argtypes = [i32p, I, I, i32p]
+        L.ao_runner_continues.argtypes = [i32p, I, I]
+        L.ao_statistics.argtypes = [i32p, I, i32p]
         L.ao_rollout_random.argtypes = [i32p, ctypes.c_int64, I, I, I, U64, U32, I, i64p]
         L.ao_rollout_random_mt.argtypes = [i32p, ctypes.c_int64, I, I, I, U64, U32, I, i64p, I]
         for f in ("ao_init", "ao_new_round", "ao_reset_philox", "ao_move", "ao_next_player", "ao_count_score",
                   "ao_score_preview", "ao_legal_mask", "ao_philox4x32_10", "ao_rollout_random",
-                  "ao_rollout_random_mt"):
+                  "ao_rollout_random_mt", "ao_observe", "ao_statistics"):
             getattr(L, f).restype = None
         _lib = L
     return _lib
@@ -129,6 +132,24 @@ class Game:
         dd = _draws(draws)
         return lib().ao_step(_rec(self.rec), self.players, self.tile_pool, int(action),
                              dd[1] if dd else None, seed, gid)
+
+
+def observe(rec, players, perspective=0):
+    """``GameRunner.get_state`` (game_runner.py:56-72) of one record: int32 [32 + 52P]; perspective -1 = the mover."""
+    out = np.zeros(32 + 52 * players, dtype=np.int32)
+    lib().ao_observe(_rec(np.ascontiguousarray(rec, dtype=np.int32)), players, perspective, _p(out, ctypes.c_int32))
+    return out
+
+
+def runner_continues(rec, players, require_two=True):
+    """The ``while`` test of ``GameRunner.step`` (:46, require_two) / ``GameRunner.reset`` (:84) on this state."""
+    return bool(lib().ao_runner_continues(_rec(np.ascontiguousarray(rec, dtype=np.int32)), players, int(require_two)))
+
+
+def statistics(rec, players):
+    out = np.zeros(10, dtype=np.int32)
+    lib().ao_statistics(_rec(np.ascontiguousarray(rec, dtype=np.int32)), players, _p(out, ctypes.c_int32))
+    return out
 
 
 def philox4x32_10(ctr, key):

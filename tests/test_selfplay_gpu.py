@@ -183,3 +183,52 @@ def test_fused_a2c_loss_gradient_matches_autograd():
         assert float((p.grad - w).abs().max()) <= 2e-5 * max(1.0, float(w.abs().max())), p.shape
     ref = torch.stack([a, c, e]).double()
     assert float(((sums - ref).abs() / ref.abs().clamp_min(1.0)).max()) < 1e-5
+
+
+def test_training_cli_csv_checkpoint_and_resume(tmp_path):
+    """scripts/training.py equivalent (train.py main): writes <net>.csv (one row per batch) and <net>.pt; --resume continues
+    the batch numbering, appends to the CSV, restores parameters + Adam state; the checkpoint loads as an opponent Agent."""
+    import csv
+    from azul_deep_reinforcement_learning_b200 import train
+    from azul_deep_reinforcement_learning_b200.azulnet.agent import Agent
+    name = str(tmp_path / "run1")
+    train.main(["128", name, "--batches", "2", "--seed", "3"])
+    rows = list(csv.DictReader(open(name + ".csv")))
+    assert [int(r["batch"]) for r in rows] == [1, 2]
+    for k in ("reward", "actor_loss", "critic_loss", "entropy_loss", "ac_loss", "player_score", "opponent_score", "rounds",
+              "percent_first_player", "floor_penalty", "max_combo", "completed_rows", "completed_columns", "completed_colors",
+              "win_percent"):                                        # agent.py:12 + game_runner.py:12 statistic names
+        assert k in rows[0] and np.isfinite(float(rows[0][k])), k
+    ck = torch.load(name + ".pt", map_location="cpu", weights_only=False)
+    assert ck["batch"] == 2 and ck["optimizer"]["state"][0]["step"] == 2
+    # resume: two more batches
+    train.main(["128", name, "--batches", "4", "--seed", "3", "--resume", name + ".pt"])
+    rows = list(csv.DictReader(open(name + ".csv")))
+    assert [int(r["batch"]) for r in rows] == [1, 2, 3, 4]
+    ck2 = torch.load(name + ".pt", map_location="cpu", weights_only=False)
+    assert ck2["batch"] == 4 and ck2["optimizer"]["state"][0]["step"] == 4
+    assert not torch.equal(ck["ac_net"]["actor_linear1.weight"], ck2["ac_net"]["actor_linear1.weight"])
+    # a resumed trainer starts from exactly the saved parameters
+    tr = train.SelfPlayTrainer(64, seed=3, use_cuda_graph=False)
+    assert tr.load_checkpoint(name + ".pt") == 4
+    for k, v in tr.net.state_dict().items():
+        assert torch.equal(v.cpu(), ck2["ac_net"][k])
+    # ... and the checkpoint is a valid base_net / opponent (scripts/run_batch.py:6-8)
+    a = Agent(base_net_file=name)
+    assert torch.equal(a.ac_net.actor_linear2.bias, ck2["ac_net"]["actor_linear2.bias"])
+
+
+def test_opponent_random_observation_for_3_and_4_players():
+    """azb_opponent_random with the observation output for P = 3, 4 (shared-memory staging sized per player count)."""
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul
+    for players in (3, 4):
+        eng = BatchedAzul(1000, players, 1, 0, seed=players)
+        eng.rollout_random(7)
+        ps = torch.zeros(1000, dtype=torch.int16, device="cuda")
+        out = eng.opponent_random(ps, require_two=True, want_obs=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out["obs"].float(), eng.observe(0))
+        rec = eng.export_records().cpu().numpy()
+        L = UnpackedLayout(players)
+        for i in range(0, 1000, 37):
+            assert np.array_equal(O.observe(rec[i], players, 0), out["obs"][i].float().cpu().numpy().astype(np.int32))

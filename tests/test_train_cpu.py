@@ -137,3 +137,22 @@ def test_two_rank_gradient_allreduce_matches_global_batch(tmp_path):
             got = torch.load(tmp_path / (name % r))
             for g1, g2 in zip(got, ref):
                 assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-6), name
+
+
+def test_saved_networks_load_back_through_agent(tmp_path):
+    """Every format the package (or the reference, nn_runner.py:83-84 / agent.py:36) writes loads back through
+    ``Agent(base_net_file=...)``: pickled module (.mx), bare state_dict (.pt), trainer checkpoint dict (.pt)."""
+    from azul_deep_reinforcement_learning_b200.azulnet.agent import Agent
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    torch.manual_seed(11)
+    net = ActorCritic(136, 180)
+    want = {k: v.clone() for k, v in net.state_dict().items()}
+    torch.save(net, str(tmp_path / "module.mx"))
+    torch.save(net.state_dict(), str(tmp_path / "bare.pt"))
+    torch.save({"ac_net": net.state_dict(), "optimizer": torch.optim.Adam(net.parameters()).state_dict(), "batch": 7},
+               str(tmp_path / "ckpt.pt"))
+    for name in ("module.mx", "module", "bare.pt", "bare", "ckpt.pt", "ckpt"):
+        a = Agent(base_net_file=str(tmp_path / name))
+        got = a.ac_net.state_dict()
+        assert set(got) == set(want) and all(torch.equal(got[k], want[k]) for k in want), name
+        assert len(a.ac_optimizer.param_groups[0]["params"]) == 8
