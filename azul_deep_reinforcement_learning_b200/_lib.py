@@ -13,7 +13,7 @@ SYMBOLS = [
     "azb_rollout_random", "azb_score_preview", "azb_import_state", "azb_export_state", "azb_observe",
     "azb_stats", "azb_move", "azb_next_player", "azb_count_score", "azb_new_round", "azb_round_flags",
     "azb_opponent_random", "azb_policy_packed_bytes", "azb_policy_pack_weights", "azb_policy_step",
-    "azb_observe_bf16", "azb_a2c_loss_grad",
+    "azb_observe_bf16", "azb_a2c_loss_grad", "azb_policy_rollout", "azb_discounted_returns",
 ]
 
 
@@ -60,6 +60,8 @@ def load():
     L.azb_policy_step.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     f32 = ctypes.c_float
     L.azb_a2c_loss_grad.argtypes = [vp, i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp]
+    L.azb_policy_rollout.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i64] + [vp] * 16
+    L.azb_discounted_returns.argtypes = [vp, i32, ctypes.c_double, vp, vp, vp, vp, vp, vp]
     if L.azb_abi_version() != ABI_VERSION:
         raise AzbError("libazb.so ABI %d != binding ABI %d: rebuild" % (L.azb_abi_version(), ABI_VERSION))
     _lib = L

@@ -119,7 +119,47 @@ __global__ void __launch_bounds__(256) k_a2c_loss_grad(Args A)
     }
 }
 
+// Discounted returns of NNRunner.train (nn_runner.py:72-75) over the decision records of azb_policy_rollout's runner mode:
+// one thread per game walks its decisions backwards, q = r + gamma * q (double, like the reference's numpy loop; the
+// reference then casts to float32, agent.py:41), and scatters q to the decision's compact slot.
+__global__ void k_returns(int64_t n, int k, double gamma, const int16_t* __restrict__ reward_rec,
+                          const uint8_t* __restrict__ flags_rec, const int32_t* __restrict__ slot_rec,
+                          float* __restrict__ qval, double* __restrict__ reward_sum)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double q = 0.0, total = 0.0;
+    if (g < n) {
+        for (int t = k - 1; t >= 0; t--) {
+            const int64_t i = (int64_t)t * n + g;
+            if (!(flags_rec[i] & 1)) continue;
+            const double r = (double)reward_rec[i];
+            q = r + gamma * q;
+            total += r;
+            const int32_t slot = slot_rec[i];
+            if (slot >= 0) qval[slot] = (float)q;
+        }
+    }
+    if (reward_sum) {                                   // sum of the episode rewards (Agent.update's "reward" statistic, agent.py:58)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+        if ((threadIdx.x & 31) == 0 && total != 0.0) atomicAdd(reward_sum, total);
+    }
+}
+
 }  // namespace a2c
+
+extern "C" int azb_discounted_returns(azb_t* h, int k_decisions, double gamma, const int16_t* reward_rec,
+                                      const uint8_t* flags_rec, const int32_t* slot_rec, float* qval, double* reward_sum,
+                                      void* stream)
+{
+    CHECK_HANDLE(h);
+    if (k_decisions < 0) return azb_fail(AZB_E_INVALID, "k_decisions < 0%s");
+    if (!reward_rec || !flags_rec || !slot_rec || !qval) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    a2c::k_returns<<<(unsigned)((h->n_games + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        h->n_games, k_decisions, gamma, reward_rec, flags_rec, slot_rec, qval, reward_sum);
+    CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int azb_a2c_loss_grad(azb_t* h, int64_t n, const float* logits, const float* value, const uint32_t* mask_rows,
                                  const int64_t* action, const float* qval, float scale, float actor_coeff,

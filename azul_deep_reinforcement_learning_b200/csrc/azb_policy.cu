@@ -304,6 +304,24 @@ struct PolicyArgs {
     uint8_t* __restrict__ done_out;          // [n]
     uint8_t* __restrict__ status_out;        // [n]
     uint32_t* __restrict__ mask6_out;        // [6][n] legal mask used for the decision
+    // ---- persistent form (azb_policy_rollout): k_decisions decisions per game in one launch, state resident ----
+    int k_decisions;     // >= 1; the per-game outputs above then hold the LAST decision
+    int runner_mode;     // 0 self-play (every seat decides); 1 GameRunner.step semantics (game_runner.py:43-55): after each
+                         // decision the random opponent moves until seat 1 is to move with >= 2 legal actions, the reward is taken
+                         // and the decision is recorded; an ended game stays ended (one episode per slot)
+    int16_t* __restrict__ player_score;      // [n] runner mode: GameRunner.player_score (game_runner.py:52)
+    // decision records of the runner mode.  Compact: slot = atomic counter n_dec (device), capacity rec_cap
+    uint32_t* __restrict__ n_dec;            // [1]
+    int64_t rec_cap;
+    uint32_t* __restrict__ state_rec;        // [17][rec_cap] packed state the decision was taken on (update kernel input)
+    uint8_t* __restrict__ action_rec;        // [rec_cap]
+    float* __restrict__ logp_rec;            // [rec_cap] optional
+    float* __restrict__ value_rec;           // [rec_cap] optional
+    // per (decision index, game): [k_decisions][n]
+    int32_t* __restrict__ slot_rec;          // compact slot of the decision, -1 when the game took none
+    int16_t* __restrict__ reward_rec;        // GameRunner.step reward (game_runner.py:51)
+    uint8_t* __restrict__ flags_rec;         // bit 0 a decision was taken, bit 1 game over after it
+    uint32_t* __restrict__ steps_used;       // [1] optional: max over CTAs of the decision iterations actually run
 };
 
 constexpr uint32_t PURPOSE_POLICY = 4;
@@ -433,6 +451,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     const int64_t tiles = (A.n + TILE_M - 1) / TILE_M;
     const int col0 = part * PART_COLS;                 // this thread's 48 epilogue columns
 
+    // Persistent form: a CTA owns the tiles blockIdx.x + j * gridDim.x for the whole launch and takes k_decisions decisions for
+    // each of their games; between decisions the packed state stays in global memory (L2-resident: 68 B per game), written and
+    // re-read by this CTA only, so block barriers order everything.
+    const int64_t my_tiles = (int64_t)blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    int it = 0;
+    for (; it < A.k_decisions; it++) {
     // software pipeline over tiles: the next tile's state is loaded during this tile's epilogues and its observation
     // is built by parts 1..3 while part 0 plays this tile's moves
     Game<2> nxt;
@@ -441,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         nxt.load(A.state_in, A.n, g0 < A.n ? g0 : A.n - 1);
         build_obs_tile(nxt, a_tile, row, part);
     }
-    mbar_wait(bar_w, 0);                                  // weights and vectors have landed (every thread reads the vectors)
+    if (it == 0) mbar_wait(bar_w, 0);                     // weights and vectors have landed (every thread reads the vectors)
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t g = tile * TILE_M + row;
         const bool valid = g < A.n;
@@ -693,6 +717,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 if (A.logp_out) A.logp_out[g] = logp;
                 if (A.entropy_out) A.entropy_out[g] = entropy;
             }
+            if (A.runner_mode) {
+                // NNRunner.run_episode's per-decision record (nn_runner.py:27-45) in compact form: the warp's deciding games take
+                // consecutive slots (one atomic per warp); the packed state the decision was taken on is what the update
+                // kernel rebuilds observation and mask from
+                const bool decides = valid && n_valid > 0 && !gm.ended();
+                const uint32_t votes = __ballot_sync(0xFFFFFFFFu, decides);
+                uint32_t base = 0;
+                if (votes && (tid & 31) == 0) base = atomicAdd(A.n_dec, (uint32_t)__popc(votes));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const int64_t slot = (int64_t)base + __popc(votes & ((1u << (tid & 31)) - 1u));
+                const bool fits = decides && slot < A.rec_cap;
+                if (fits) {
+                    gm.store(A.state_rec, A.rec_cap, slot);
+                    A.action_rec[slot] = (uint8_t)action;
+                    if (A.logp_rec) A.logp_rec[slot] = logp;
+                    if (A.value_rec) A.value_rec[slot] = value;
+                }
+                if (valid) {
+                    A.slot_rec[(int64_t)it * A.n + g] = fits ? (int32_t)slot : -1;
+                    A.flags_rec[(int64_t)it * A.n + g] = decides ? 1 : 0;         // bit 1 (done) is added by the opponent phase
+                }
+            }
             // Only the cheap, uniform part of Azul.step runs here (move, next player).  Games whose round just ended --
             // and, in self-play mode, slots that need a fresh game -- are flagged in MISC and completed by
             // the finishing phase at the end of this kernel, 32 per warp with every lane busy.
@@ -727,14 +773,50 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     // collected into a dense list (the A region is free now) and finished 32 per warp with every lane busy, instead of under
     // divergence inside the tile loop or in a second kernel launch ----
     __syncthreads();                                   // every state / done / status write of the tile loop is visible to the CTA
-    if (A.apply_step) {
+    bool any_alive = true;
+    if (A.runner_mode) {
+        // GameRunner.step after the agent's move (game_runner.py:46-55), one thread per game of this CTA's tiles: finish the
+        // round the move may have ended, let the random opponent play until seat 1 is to move with >= 2 legal actions (or the
+        // game is over), take the reward from a score preview, and close the decision's record
+        bool alive = false;
+        for (int64_t j = part; j < my_tiles; j += PARTS) {
+            const int64_t g = ((int64_t)blockIdx.x + j * gridDim.x) * TILE_M + row;
+            if (g >= A.n) continue;
+            const bool decided = A.flags_rec[(int64_t)it * A.n + g] & 1;
+            if (!decided) { A.reward_rec[(int64_t)it * A.n + g] = 0; continue; }
+            Game<2> h;
+            h.load(A.state, A.n, g);
+            const uint32_t gid = A.gid0 + (uint32_t)g;
+            if (h.misc & FLAG_ROUND_OVER) {
+                h.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
+                count_score<2, POOL>(h);                                  // azul.py:307
+                if (is_end_of_game(h)) h.misc |= 1u << 12;                // azul.py:308-309
+                else new_round_philox<2, POOL>(h, rng, gid, PURPOSE_REFILL);   // azul.py:311
+            }
+            uint32_t m2[6];
+            const int32_t diff = opponent_random<2, POOL>(h, rng, gid, true, m2);
+            h.store(A.state, A.n, g);
+            const int32_t before = (int32_t)A.player_score[g];
+            A.player_score[g] = (int16_t)diff;                            // game_runner.py:52
+            A.reward_rec[(int64_t)it * A.n + g] = (int16_t)(diff - before);   // game_runner.py:51
+            const bool over = h.ended();
+            A.flags_rec[(int64_t)it * A.n + g] = (uint8_t)(1 | (over ? 2 : 0));
+            if (A.done_out) A.done_out[g] = over ? 1 : 0;
+            if (A.status_out) A.status_out[g] |= (uint8_t)h.status();
+            if (A.mask6_out) {
+#pragma unroll
+                for (int p = 0; p < 6; p++) A.mask6_out[p * A.n + g] = m2[p];
+            }
+            alive |= !over && !(h.status() & ST_STUCK);
+        }
+        any_alive = __syncthreads_or(alive ? 1 : 0) != 0;
+    } else if (A.apply_step) {
         // the list holds at most FINISH_GROUP tiles' worth of games (every game of a tile can be flagged, e.g. when a whole
         // batch asks for fresh games), so a CTA with more tiles than that works through them in groups
         constexpr int FINISH_GROUP = A_BYTES / 4 / TILE_M / PARTS * PARTS;         // 96 tiles = 12,288 entries
         static_assert(FINISH_GROUP >= PARTS && FINISH_GROUP * TILE_M * 4 <= A_BYTES, "finish list exceeds the A region");
         uint32_t* list = reinterpret_cast<uint32_t*>(a_tile);
         __shared__ uint32_t n_list;
-        const int64_t my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;       // tiles blockIdx.x + j * gridDim.x
         for (int64_t j0 = 0; j0 < my_tiles; j0 += FINISH_GROUP) {
             if (tid == 0) n_list = 0u;
             __syncthreads();
@@ -756,6 +838,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             __syncthreads();                           // the list is reused by the next group
         }
     }
+    __syncthreads();                                   // the next decision reads the states written above
+    if (!any_alive) { it++; break; }                   // runner mode: every episode of this CTA is over
+    }   // decision loop
+    if (A.steps_used && tid == 0) atomicMax(A.steps_used, (uint32_t)it);
     __syncthreads();
     if (A.counters && tid < AZB_N_COUNTERS && cnt[tid]) atomicAdd(&A.counters[tid], cnt[tid]);
     if (warp == 0) {
@@ -854,6 +940,42 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
     A.act_filter = act_filter;
     A.logits_out = logits_out; A.value_out = value_out; A.action_out = action_out; A.logp_out = logp_out;
     A.entropy_out = entropy_out; A.done_out = done_out; A.status_out = status_out; A.mask6_out = mask6_out;
+    A.k_decisions = 1; A.runner_mode = 0; A.player_score = nullptr; A.n_dec = nullptr; A.rec_cap = 0; A.state_rec = nullptr;
+    A.action_rec = nullptr; A.logp_rec = nullptr; A.value_rec = nullptr; A.slot_rec = nullptr; A.reward_rec = nullptr;
+    A.flags_rec = nullptr; A.steps_used = nullptr;
+    const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;
+    const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+    int rc = 0;
+    if (h->tile_pool == AZB_POOL_LID) rc = mode == 0 ? pol::launch_policy<1, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<1, 1>(A, grid, (cudaStream_t)stream);
+    else rc = mode == 0 ? pol::launch_policy<0, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<0, 1>(A, grid, (cudaStream_t)stream);
+    if (rc) return rc;
+    CHECK_LAUNCH();
+    return 0;
+}
+
+int azb_policy_rollout(azb_t* h, uint32_t* state, const void* packed, int mode, int k_decisions, int runner_mode,
+                       int16_t* player_score, uint32_t* n_dec, int64_t rec_cap, uint32_t* state_rec, uint8_t* action_rec,
+                       float* logp_rec, float* value_rec, int32_t* slot_rec, int16_t* reward_rec, uint8_t* flags_rec,
+                       uint32_t* steps_used, uint8_t* action_out, float* logp_out, float* value_out, uint32_t* mask6_out,
+                       uint8_t* done_out, uint8_t* status_out, unsigned long long* counters, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !packed) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    if (h->players != 2) return azb_fail(AZB_E_INVALID, "the policy network is defined for 2 players (136 inputs, agent.py:29)%s");
+    if (mode != 0 && mode != 1) return azb_fail(AZB_E_INVALID, "mode must be 0 (sample) or 1 (argmax)%s");
+    if (k_decisions < 1) return azb_fail(AZB_E_INVALID, "k_decisions must be >= 1%s");
+    if (runner_mode != 0 && runner_mode != 1) return azb_fail(AZB_E_INVALID, "runner_mode must be 0 (self-play) or 1 (GameRunner)%s");
+    if (runner_mode && (!player_score || !n_dec || rec_cap < 1 || !state_rec || !action_rec || !slot_rec || !reward_rec || !flags_rec))
+        return azb_fail(AZB_E_INVALID, "runner mode needs player_score, n_dec, rec_cap and the state / action / slot / reward / flags records%s");
+    pol::PolicyArgs A;
+    A.state_in = state; A.state = state; A.n = h->n_games; A.packed = (const unsigned char*)packed;
+    A.k0 = (uint32_t)h->seed; A.k1 = (uint32_t)(h->seed >> 32); A.gid0 = (uint32_t)h->game_id_base;
+    A.mode = mode; A.apply_step = runner_mode ? 1 : 2; A.first_rule = h->first_player; A.counters = counters; A.act_filter = 0;
+    A.logits_out = nullptr; A.value_out = value_out; A.action_out = action_out; A.logp_out = logp_out; A.entropy_out = nullptr;
+    A.done_out = done_out; A.status_out = status_out; A.mask6_out = mask6_out;
+    A.k_decisions = k_decisions; A.runner_mode = runner_mode; A.player_score = player_score; A.n_dec = n_dec; A.rec_cap = rec_cap;
+    A.state_rec = state_rec; A.action_rec = action_rec; A.logp_rec = logp_rec; A.value_rec = value_rec; A.slot_rec = slot_rec;
+    A.reward_rec = reward_rec; A.flags_rec = flags_rec; A.steps_used = steps_used;
     const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     int rc = 0;

@@ -248,6 +248,36 @@ class BatchedAzul:
             out["obs"] = obs
         return out
 
+    # -- K4, persistent form ------------------------------------------------------------------
+    def policy_rollout(self, packed, k_decisions, mode=0, want_last=False):
+        """Self-play (BASELINE.json configs[3]): ``k_decisions`` env steps per game in ONE launch, every seat's move sampled
+        from the policy (``mode`` 1: argmax), finished games tallied in ``self.counters`` and replaced; the packed state
+        stays on the device between decisions.  ``want_last``: returns the last decision's action / logp / value."""
+        out = None
+        if want_last:
+            if getattr(self, "_last_out", None) is None:
+                self._last_out = {"action": self._new((self.n_games,), torch.uint8), "logp": self._new((self.n_games,), torch.float32),
+                                  "value": self._new((self.n_games,), torch.float32)}
+            out = self._last_out
+        _lib.check(self.lib.azb_policy_rollout(
+            self._h, _ptr(self.state), _ptr(packed.buf), int(mode), int(k_decisions), 0, None, None, 0, None, None, None, None,
+            None, None, None, None, _ptr(out["action"]) if out else None, _ptr(out["logp"]) if out else None,
+            _ptr(out["value"]) if out else None, None, None, None, _ptr(self.counters), self._stream()))
+        return out
+
+    def policy_rollout_host(self, packed, host_state, k_decisions, host_last=None, host_counters=None, mode=0):
+        """End-to-end form of :meth:`policy_rollout` on HOST buffers (pinned): state in, ``k_decisions`` decisions per game,
+        state + the last decision's action / logp / value + the counters out.  Returns after the results are on the host."""
+        self.state.copy_(host_state, non_blocking=True)
+        out = self.policy_rollout(packed, k_decisions, mode, want_last=host_last is not None)
+        host_state.copy_(self.state, non_blocking=True)
+        if host_last is not None:
+            for k, v in host_last.items():
+                v.copy_(out[k], non_blocking=True)
+        if host_counters is not None:
+            host_counters.copy_(self.counters, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+
     def round_flags(self):
         out = self._new((self.n_games,), torch.uint8)
         _lib.check(self.lib.azb_round_flags(self._h, _ptr(self.state), _ptr(out), self._stream()))
@@ -296,6 +326,54 @@ def policy_step(engine, packed, mode=0, apply_step=True, want_logits=False, want
     if want_logits:
         out["logits"] = logits
     return out
+
+
+class EpisodeRecords:
+    """Device buffers for the decision records of ``azb_policy_rollout``'s runner mode (one episode per game slot, at most
+    ``max_decisions`` agent decisions each, ``capacity`` decisions in total) -- what ``NNRunner.run_episode`` /
+    ``NNRunner.train`` collect in Python lists (nn_runner.py:17-47,58-75)."""
+
+    def __init__(self, engine, max_decisions, capacity=None, want_logp_value=False):
+        n, dev = engine.n_games, engine.device
+        self.engine, self.k, self.cap = engine, int(max_decisions), int(capacity or max_decisions * n)
+        # a sibling handle over the compact state records: observation / legal mask of a recorded decision are functions
+        # of the packed state it was taken on
+        self.view = BatchedAzul(self.cap, 2, engine.tile_pool, engine.first_player, seed=engine.seed, device=dev.index, reset=False)
+        self.state_rec = self.view.state
+        self.action_rec = torch.zeros(self.cap, dtype=torch.uint8, device=dev)
+        self.qval = torch.zeros(self.cap, dtype=torch.float32, device=dev)
+        self.logp_rec = torch.zeros(self.cap, dtype=torch.float32, device=dev) if want_logp_value else None
+        self.value_rec = torch.zeros(self.cap, dtype=torch.float32, device=dev) if want_logp_value else None
+        self.slot_rec = torch.full((self.k, n), -1, dtype=torch.int32, device=dev)
+        self.reward_rec = torch.zeros((self.k, n), dtype=torch.int16, device=dev)
+        self.flags_rec = torch.zeros((self.k, n), dtype=torch.uint8, device=dev)
+        self.meta = torch.zeros(2, dtype=torch.int32, device=dev)           # [0] n_dec, [1] decision iterations run
+        self.reward_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def clear(self):
+        self.meta.zero_()
+        self.flags_rec.zero_()
+        self.reward_sum.zero_()
+
+
+def runner_rollout(engine, packed, records, player_score, mode=0, out=None):
+    """``NNRunner.run_episode`` for every game slot in ONE launch (``azb_policy_rollout``, runner mode): agent decisions by the
+    fused policy kernel, opponent loop + reward after each, decision records into ``records``.  The episodes must have
+    been started (``BatchedGameRunner.reset``)."""
+    r = records
+    _lib.check(engine.lib.azb_policy_rollout(
+        engine._h, _ptr(engine.state), _ptr(packed.buf), int(mode), r.k, 1, _ptr(player_score), _ptr(r.meta), r.cap,
+        _ptr(r.state_rec), _ptr(r.action_rec), _ptr(r.logp_rec), _ptr(r.value_rec), _ptr(r.slot_rec), _ptr(r.reward_rec),
+        _ptr(r.flags_rec), ctypes.c_void_p(r.meta.data_ptr() + 4), None, None, None,
+        _ptr(out["mask"]) if out else None, _ptr(out["done"]) if out else None, _ptr(out["status"]) if out else None,
+        None, engine._stream()))
+
+
+def discounted_returns_records(engine, records, gamma):
+    """nn_runner.py:72-75 on the decision records: fills ``records.qval`` (compact) and ``records.reward_sum``."""
+    r = records
+    _lib.check(engine.lib.azb_discounted_returns(engine._h, r.k, float(gamma), _ptr(r.reward_rec), _ptr(r.flags_rec),
+                                                _ptr(r.slot_rec), _ptr(r.qval), _ptr(r.reward_sum), engine._stream()))
 
 
 def mask_to_bool(mask6):

@@ -8,7 +8,8 @@ softmax + sampling + the agent's ``Azul.step``) and the opponent loop + reward (
 """
 import torch
 
-from .engine import BatchedAzul, mask_to_bool, policy_step, rules_to_ints
+from .engine import (BatchedAzul, EpisodeRecords, discounted_returns_records, mask_to_bool, policy_step, rules_to_ints,
+                     runner_rollout)
 
 DEFAULT_RULES = {"first_player": "Random", "tile_pool": "Lid"}      # game_runner.py:23
 
@@ -218,6 +219,34 @@ class GraphedEpisodes:
             t += self.more
         self.runner.mask, self.runner.obs = mask, obs
         return _finish_batch(chunks, alive)
+
+
+class PersistentEpisodes:
+    """``NNRunner.run_episode`` for every game slot with the whole episode loop on the device: ``GameRunner.reset`` (two
+    launches), then ONE persistent launch of the fused policy kernel that takes every agent decision, plays the random
+    opponent's moves, takes the rewards and writes the decision records, then the discounted returns (one launch).  The
+    recorded decisions are those of :func:`run_episodes` (same Philox schedule); only their storage differs (compact
+    slots in arbitrary order instead of [T, G])."""
+
+    def __init__(self, runner, packed, max_decisions=160, capacity=None, want_logp_value=False):
+        assert runner.opponent is None, "the persistent rollout plays the RandomAgent opponent"
+        self.runner, self.packed = runner, packed
+        n = runner.n_games
+        if capacity is None:                       # ~30 decisions per episode on average; small batches get the full K x G
+            capacity = max_decisions * n if n <= 4096 else 56 * n
+        self.records = EpisodeRecords(runner.engine, max_decisions, capacity, want_logp_value)
+        self.out = {"mask": torch.zeros((6, n), dtype=torch.int32, device=runner.device),
+                    "done": torch.zeros(n, dtype=torch.uint8, device=runner.device),
+                    "status": torch.zeros(n, dtype=torch.uint8, device=runner.device)}
+
+    def run(self, gamma=0.99, mode=0):
+        r = self.records
+        self.runner.reset()
+        r.clear()
+        runner_rollout(self.runner.engine, self.packed, r, self.runner.player_score, mode=mode, out=self.out)
+        discounted_returns_records(self.runner.engine, r, gamma)
+        self.runner.mask = self.out["mask"]
+        return r
 
 
 def discounted_returns(reward, active, gamma):

@@ -23,7 +23,7 @@ import torch.distributed as dist
 from . import parallel
 from .azulnet.model import ActorCritic
 from .engine import PackedPolicy
-from .selfplay import BatchedGameRunner, GraphedEpisodes, discounted_returns, run_episodes
+from .selfplay import BatchedGameRunner, GraphedEpisodes, PersistentEpisodes, discounted_returns, run_episodes
 
 ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF = 1.0, 0.5, 0.1          # agent.py:47-49
 
@@ -104,7 +104,7 @@ def global_count(n_local, device):
 
 class SelfPlayTrainer:
     def __init__(self, games_per_rank=1024, learning_rate=3e-4, gamma=0.99, seed=0, device=0, rank=0, world=1,
-                 rules=None, max_decisions=160, use_cuda_graph=True, tf32_update=True):
+                 rules=None, max_decisions=160, use_cuda_graph=True, tf32_update=True, rollout=None):
         self.rank, self.world, self.gamma, self.max_decisions = rank, world, gamma, max_decisions
         self.tf32_update = tf32_update
         self.device = torch.device("cuda", device)
@@ -115,12 +115,23 @@ class SelfPlayTrainer:
         self.runner = BatchedGameRunner(games_per_rank, rules=rules, seed=seed, device=device,
                                         game_id_base=parallel.shard(rank, games_per_rank), record_obs=True)
         self.packed = PackedPolicy(self.runner.engine, self.net)
-        self.graphed = GraphedEpisodes(self.runner, self.packed) if use_cuda_graph else None
+        # rollout engine: "persistent" = whole episodes in one launch of the fused policy kernel (azb_policy_rollout, runner
+        # mode); "graph" / "eager" = one policy + one opponent launch per decision (CUDA-graph replay / plain loop)
+        self.rollout_kind = rollout if rollout is not None else ("persistent" if use_cuda_graph else "eager")
+        self.graphed = self.episodes = None
+        if self.rollout_kind == "persistent":
+            self.runner.record_obs = False
+            self.episodes = PersistentEpisodes(self.runner, self.packed, max_decisions=max_decisions)
+        elif self.rollout_kind == "graph":
+            self.graphed = GraphedEpisodes(self.runner, self.packed)
         self.history = []
 
     def rollout(self):
         with torch.no_grad():
             self.packed.update(self.net)
+            if self.episodes is not None:
+                recs = self.episodes.run(self.gamma)
+                return {"records": recs, "stats": self.runner.engine.stats().to(torch.float64)}
             if self.graphed is not None:
                 batch = self.graphed.run(max_decisions=self.max_decisions)
             else:
@@ -182,18 +193,32 @@ class SelfPlayTrainer:
         decision count and the batch statistics, then every rank divides by the global count (the means of
         agent.py:47-56 over the global batch) and takes the same Adam step.  The host is not synchronised before
         the statistics are read at the end."""
-        act = batch["active"]
-        T, G = act.shape
-        sel = act.reshape(-1).nonzero(as_tuple=True)[0]
-        n_local = int(sel.numel())
-        obs = batch["obs"].reshape(T * G, -1)[sel]
-        masks = batch["mask"].permute(0, 2, 1).reshape(T * G, 6)[sel]
-        sums = self.accumulate_gradients(obs, masks, batch["action"].reshape(-1)[sel], batch["qval"].reshape(-1)[sel])
+        if "records" in batch:                        # compact decision records of the persistent rollout
+            recs = batch["records"]
+            G = self.runner.n_games
+            n_local = int(recs.meta[0])
+            if n_local > recs.cap:
+                raise RuntimeError("decision records overflowed: %d decisions, capacity %d" % (n_local, recs.cap))
+            obs = recs.view.observe_bf16(-1)[:n_local]
+            masks = recs.view.legal_mask().t()[:n_local]
+            sums = self.accumulate_gradients(obs, masks, recs.action_rec[:n_local].long(), recs.qval[:n_local])
+            reward_total = recs.reward_sum.reshape(1)
+            unfinished = (G - ((recs.flags_rec >> 1) & 1).sum()).double().reshape(1)
+        else:
+            act = batch["active"]
+            T, G = act.shape
+            sel = act.reshape(-1).nonzero(as_tuple=True)[0]
+            n_local = int(sel.numel())
+            obs = batch["obs"].reshape(T * G, -1)[sel]
+            masks = batch["mask"].permute(0, 2, 1).reshape(T * G, 6)[sel]
+            sums = self.accumulate_gradients(obs, masks, batch["action"].reshape(-1)[sel], batch["qval"].reshape(-1)[sel])
+            reward_total = batch["reward"].double().mul(act).sum().reshape(1)
+            unfinished = torch.full((1,), float(batch["unfinished"]), dtype=torch.float64, device=self.device)
         t0 = time.perf_counter()
         one = torch.ones(1, dtype=torch.float64, device=self.device)
         wins = (batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum().reshape(1)
-        stats = torch.cat([one * n_local, sums, batch["reward"].double().mul(act).sum().reshape(1), one * G,
-                           batch["stats"].sum(dim=0), wins])
+        stats = torch.cat([one * n_local, sums, reward_total, one * G,
+                           batch["stats"].sum(dim=0), wins, unfinished])
         stats = allreduce_gradients_and_stats(self.params, stats)
         inv = (1.0 / stats[0].clamp_min(1.0)).float()
         for p in self.params:
@@ -209,6 +234,7 @@ class SelfPlayTrainer:
                    percent_first_player=100.0 * s[9] / max(s[10], 1.0), floor_penalty=g[5], max_combo=g[6],
                    completed_rows=g[7], completed_columns=g[8], completed_colors=g[9])
         out["win_percent"] = s[16] / games
+        out["unfinished"] = int(s[17])
         return out
 
     def save_checkpoint(self, path, batch):
@@ -243,8 +269,7 @@ class SelfPlayTrainer:
             st = self.update(batch)
             torch.cuda.synchronize(self.device)
             t2 = time.perf_counter()
-            st.update(batch=b + 1, rollout_s=t1 - t0, update_s=t2 - t1, games_per_sec=st["games"] / (t2 - t0),
-                      unfinished=batch["unfinished"])
+            st.update(batch=b + 1, rollout_s=t1 - t0, update_s=t2 - t1, games_per_sec=st["games"] / (t2 - t0))
             self.history.append(st)
             if self.rank == 0:
                 if net_name is not None:

@@ -177,6 +177,36 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
                     float* logp_out, float* value_out, float* entropy_out, uint32_t* mask6_out, uint8_t* done_out,
                     uint8_t* status_out, float* logits_out, unsigned long long* counters, int act_filter, void* stream);
 
+/* ---- K4, persistent form: k_decisions decisions per game in ONE launch, the packed state resident on the device in
+ * between (each CTA owns its games for the whole launch; no launch, no host copy per env step).
+ * runner_mode 0 -- self-play (BASELINE.json configs[3]): every seat's move is sampled from the policy, Azul.step
+ *   (azul.py:296-313) with Philox refills, finished games are tallied in `counters` and replaced by fresh ones.
+ * runner_mode 1 -- NNRunner.run_episode (nn_runner.py:17-47) over GameRunner.step (game_runner.py:43-55) for one episode
+ *   per slot: seat 1 decides; after each decision the random opponent (RandomAgent, :87-97) moves until seat 1 is to move
+ *   with >= 2 legal actions or the game is over, the reward is (score1 - score2 after count_score on a copy) -
+ *   player_score (int16 [G], updated in place).  The caller starts the episodes (azb_reset + azb_opponent_random with
+ *   require_two = 0 = GameRunner.reset, :76-85).  Ended games take no further decisions; a CTA whose episodes are all over
+ *   stops early.  Decision records:
+ *     compact, slot = old value of the device counter n_dec[0] (uint32, zeroed by the caller), capacity rec_cap:
+ *       state_rec uint32 [W][rec_cap] (packed state the decision was taken on: observation and legal mask are functions of
+ *       it), action_rec uint8 [rec_cap], logp_rec / value_rec float [rec_cap] (optional)
+ *     per (decision index t, game g), [k_decisions][G]: slot_rec int32 (-1: no decision / record full), reward_rec int16,
+ *       flags_rec uint8 (bit 0 decision taken, bit 1 game over after it)
+ *     steps_used uint32 [1] (optional, zeroed by the caller): decision iterations actually run (max over CTAs).
+ * action_out / logp_out / value_out / mask6_out / done_out / status_out ([G], optional) hold the LAST decision's outputs
+ * (runner mode: mask6_out / done_out describe the state after the opponent loop). */
+int azb_policy_rollout(azb_t* h, uint32_t* state, const void* packed, int mode, int k_decisions, int runner_mode,
+                       int16_t* player_score, uint32_t* n_dec, int64_t rec_cap, uint32_t* state_rec, uint8_t* action_rec,
+                       float* logp_rec, float* value_rec, int32_t* slot_rec, int16_t* reward_rec, uint8_t* flags_rec,
+                       uint32_t* steps_used, uint8_t* action_out, float* logp_out, float* value_out, uint32_t* mask6_out,
+                       uint8_t* done_out, uint8_t* status_out, unsigned long long* counters, void* stream);
+
+/* Discounted returns of NNRunner.train (nn_runner.py:72-75) over the records of azb_policy_rollout's runner mode:
+ * q_t = r_t + gamma * q_{t+1} over each game's decisions (accumulated in double like the reference's numpy loop), written
+ * as float to qval[slot] (float [rec_cap]); reward_sum (double [1], optional) += the sum of all rewards. */
+int azb_discounted_returns(azb_t* h, int k_decisions, double gamma, const int16_t* reward_rec, const uint8_t* flags_rec,
+                           const int32_t* slot_rec, float* qval, double* reward_sum, void* stream);
+
 /* ---- a19: the loss of Agent.update and its gradient at the network outputs --------------------
  * For n recorded agent decisions (device arrays): logits float [n][180] (raw actor outputs), value float [n],
  * mask_rows uint32 [n][6] (the legal-mask words of each decision), action int64 [n], qval float [n]

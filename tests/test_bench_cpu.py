@@ -10,7 +10,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--k-steps", "64"], capture_output=True, text=True, timeout=300, cwd=REPO)
+                          "--warmup", "0", "--k-steps", "64", "--pyref-seconds", "0"], capture_output=True, text=True, timeout=300, cwd=REPO)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
@@ -27,3 +27,18 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0", "--k-steps", "64"], capture_output=True, text=True, timeout=120, cwd=REPO, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_python_reference_leg_when_the_reference_is_staged():
+    """cpu_baseline.python_reference: the UNMODIFIED reference's GameRunner loop from baseline/_ref (staged by build());
+    reports 'unavailable' instead of failing where the tree was not staged."""
+    import pytest
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--k-steps", "64", "--pyref-seconds", "2"], capture_output=True, text=True, timeout=300, cwd=REPO)
+    assert out.returncode == 0, out.stderr[-2000:]
+    py = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]["python_reference"]
+    if not os.path.isdir(os.path.join(REPO, "baseline", "_ref", "azulnet")):
+        assert "unavailable" in py
+        pytest.skip("baseline/_ref not staged")
+    assert py["kind"] == "reference" and py["cores"] >= 1 and py["games"] > 0 and py["value"] > 100
+    assert py["single_core_value"] > 100 and py["unit"] == "env_steps/s" and "cpu_model" in py

@@ -9,8 +9,9 @@
 * ``Agent.update`` (agent.py:39-62) through the trainer's update: loss terms, gradients, parameters after two Adam steps.
 
 Tolerances: integer outputs bit-exact.  Logits / value (fp16 tensor-core operands, fp32 accumulation)
-per element |got - ref| <= 1e-3 * max(|ref|, floor) with floor = the largest |logit| of that decision's row (1.0 for the
-value); log-probabilities and the entropy term 2e-3 absolute (they are differences of logits and a log-sum-exp)."""
+per element |got - ref| <= 1e-3 * max(|ref|, floor) with floor = the largest |logit| of that decision's row (the largest
+|value| of the batch for the value head); log-probabilities and the entropy term 2e-3 + 1e-3 * floor absolute (they are differences of logits and a
+log-sum-exp).  Gradients of the update: see test_trainer_update_matches_reference_agent_update."""
 import numpy as np
 import pytest
 
@@ -141,9 +142,9 @@ def test_policy_kernel_matches_reference_actor_critic(tag, scale):
     assert (np.abs(got_sel - ref_sel) <= LOGIT_RTOL * np.maximum(np.abs(ref_sel), floor[:, None])).all()
     # value (critic head)
     ref_v = z[tag + "_value"].astype(np.float64)
-    assert (np.abs(out["value"] - ref_v) <= LOGIT_RTOL * np.maximum(np.abs(ref_v), 1.0)).all()
+    assert (np.abs(out["value"] - ref_v) <= LOGIT_RTOL * np.maximum(np.abs(ref_v), np.abs(ref_v).max())).all()
     # entropy term -mean(log pi over legal) (nn_runner.py:36-40)
-    assert np.abs(out["entropy"] - z[tag + "_entropy"]).max() <= LOGP_ATOL
+    assert (np.abs(out["entropy"] - z[tag + "_entropy"]) <= LOGP_ATOL + LOGIT_RTOL * floor).all()
     # "Max" action selection (agent.py:70-71): the reference's argmax, or an action whose probability ties it
     same = out["action"] == z[tag + "_argmax"]
     p_chosen = np.exp(out["logp"].astype(np.float64))
@@ -164,16 +165,21 @@ def test_policy_kernel_sampled_logp_matches_reference(tag, scale):
     assert valid[np.arange(nf), act].all()
     ref = torch.from_numpy(z[tag + "_logits_full"].astype(np.float64)).masked_fill(~torch.from_numpy(valid), float("-inf"))
     ref_logp = torch.log_softmax(ref, dim=1).numpy()                          # model.py:40 on the reference's own logits
-    assert np.abs(out["logp"][:nf] - ref_logp[np.arange(nf), act]).max() <= LOGP_ATOL
+    floor = z[tag + "_logits_absmax"][:nf].astype(np.float64)
+    assert (np.abs(out["logp"][:nf] - ref_logp[np.arange(nf), act]) <= LOGP_ATOL + LOGIT_RTOL * floor).all()
     assert len(np.unique(act)) > 20
 
 
-def test_trainer_update_matches_reference_agent_update():
+@pytest.mark.parametrize("tf32,grad_tol,flip_frac", [(False, 2e-4, 2e-3), (True, 2e-2, 0.05)])
+def test_trainer_update_matches_reference_agent_update(tf32, grad_tol, flip_frac):
     """Two ``Agent.update`` calls of the live reference (update.npz) through SelfPlayTrainer.update_decisions: the loss
-    terms, the gradient of the first update and the parameters after both Adam steps."""
+    terms, the gradient of the first update and the parameters after both Adam steps.  Gradient tolerance per tensor,
+    relative to its largest entry: fp32 GEMMs 2e-4; reduced-precision tensor-core operands (10/11-bit significands) 2e-2 --
+    each entry is a sum over the batch's decisions with heavy cancellation, so operand rounding shows at ~1 % of the scale."""
     from azul_deep_reinforcement_learning_b200.train import SelfPlayTrainer
     z = load_update_golden()
-    tr = SelfPlayTrainer(64, learning_rate=float(z["learning_rate"]), gamma=float(z["gamma"]), seed=0, device=0, use_cuda_graph=False)
+    tr = SelfPlayTrainer(64, learning_rate=float(z["learning_rate"]), gamma=float(z["gamma"]), seed=0, device=0, use_cuda_graph=False,
+                         tf32_update=tf32)
     tr.load_parameters({n: torch.from_numpy(z["param0_" + n]) for n in PARAM_NAMES})
     named = dict(tr.net.named_parameters())
     for b in (0, 1):
@@ -190,10 +196,10 @@ def test_trainer_update_matches_reference_agent_update():
             for name in PARAM_NAMES:
                 want = torch.from_numpy(z["grad1_" + name]).cuda()
                 err = float((tr.last_grads[name] - want).abs().max())
-                assert err <= 3e-3 * float(want.abs().max()), (name, err, float(want.abs().max()))
+                assert err <= grad_tol * float(want.abs().max()), (name, err, float(want.abs().max()))
         for name in PARAM_NAMES:
             want = torch.from_numpy(z["param%d_" % (b + 1) + name]).cuda()
             diff = (named[name].detach() - want).abs()
             # Adam's first steps are ~lr * sign(g): only entries whose gradient is at rounding level may land elsewhere
             assert float(diff.max()) <= 2.1 * float(z["learning_rate"]) * (b + 1), name
-            assert float((diff > 2e-5).float().mean()) < 0.02, (name, float((diff > 2e-5).float().mean()))
+            assert float((diff > 2e-5).float().mean()) < flip_frac, (name, float((diff > 2e-5).float().mean()))

@@ -232,3 +232,67 @@ def test_opponent_random_observation_for_3_and_4_players():
         L = UnpackedLayout(players)
         for i in range(0, 1000, 37):
             assert np.array_equal(O.observe(rec[i], players, 0), out["obs"][i].float().cpu().numpy().astype(np.int32))
+
+
+def test_persistent_selfplay_rollout_equals_stepwise():
+    """azb_policy_rollout (self-play, K decisions in one launch, state resident) == K launches of azb_policy_step with
+    auto-reset: identical states and counters, for both pools and a ragged batch with several tiles per CTA."""
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import BatchedAzul, PackedPolicy, policy_step
+    torch.manual_seed(4)
+    net = ActorCritic(136, 180)
+    for pool, n in ((1, 148 * 128 * 2 + 77), (0, 1000)):
+        a = BatchedAzul(n, 2, pool, 0, seed=13)
+        b = BatchedAzul(n, 2, pool, 0, seed=13)
+        pa, pb = PackedPolicy(a, net), PackedPolicy(b, net)
+        K = 70                                                    # longer than a game: resets happen
+        for _ in range(K):
+            last = policy_step(a, pa, mode=0, apply_step=True, auto_reset=True, want_mask=False)
+        got = b.policy_rollout(pb, K, want_last=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a.state, b.state)
+        assert torch.equal(a.counters, b.counters) and int(a.counters[1]) > 0
+        assert torch.equal(last["action"], got["action"]) and torch.equal(last["logp"], got["logp"])
+
+
+def test_persistent_runner_rollout_equals_episode_loop():
+    """azb_policy_rollout (runner mode: agent decision + opponent loop + reward + record, whole episodes in one launch)
+    reproduces run_episodes (one policy launch + one opponent launch per decision): per game the same actions, rewards,
+    decision states and final state; discounted returns equal nn_runner.py:72-75 on those rewards."""
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import PackedPolicy
+    from azul_deep_reinforcement_learning_b200.selfplay import (BatchedGameRunner, PersistentEpisodes, discounted_returns,
+                                                                 run_episodes)
+    torch.manual_seed(6)
+    net = ActorCritic(136, 180)
+    n = 700
+    a, b = BatchedGameRunner(n, seed=31), BatchedGameRunner(n, seed=31)
+    pa, pb = PackedPolicy(a.engine, net), PackedPolicy(b.engine, net)
+    eager = run_episodes(a, pa, max_decisions=160, record_obs=True)
+    pers = PersistentEpisodes(b, pb, max_decisions=160, want_logp_value=True)
+    r = pers.run(gamma=0.99)
+    torch.cuda.synchronize()
+    assert eager["unfinished"] == 0
+    assert torch.equal(a.engine.state, b.engine.state) and torch.equal(a.player_score, b.player_score)
+    act = eager["active"]                                         # [T, G]
+    T = act.shape[0]
+    n_dec, used = int(r.meta[0]), int(r.meta[1])
+    assert n_dec == int(act.sum()) and used <= 160 and n_dec <= r.cap
+    flags = r.flags_rec[:T]
+    assert torch.equal((flags & 1).bool(), act) and int(r.flags_rec[T:].sum()) == 0
+    slots = r.slot_rec[:T][act].long()
+    assert int(slots.min()) >= 0 and len(torch.unique(slots)) == n_dec      # every decision owns one slot
+    assert torch.equal(r.action_rec[slots].long(), eager["action"][act])
+    assert torch.equal(r.reward_rec[:T][act].float(), eager["reward"][act])
+    assert torch.equal(r.logp_rec[slots], eager["logp"][act]) and torch.equal(r.value_rec[slots], eager["value"][act])
+    # the recorded states reproduce the recorded observations and masks
+    obs = r.view.observe_bf16(-1)
+    assert torch.equal(obs[slots], eager["obs"][act])
+    mask = r.view.legal_mask()                                    # [6, cap]
+    assert torch.equal(mask[:, slots], eager["mask"].permute(1, 0, 2)[:, act])
+    # done flag: the last decision of every game
+    done_t = ((flags >> 1) & 1).bool()
+    assert int(done_t.sum()) == n and bool((done_t <= act).all())
+    q = discounted_returns(eager["reward"], act, 0.99)
+    assert torch.allclose(r.qval[slots], q[act], rtol=1e-6, atol=1e-5)
+    assert abs(float(r.reward_sum) - float(eager["reward"][act].sum())) < 1e-6
