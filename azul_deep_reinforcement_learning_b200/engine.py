@@ -376,6 +376,50 @@ def discounted_returns_records(engine, records, gamma):
                                                 _ptr(r.slot_rec), _ptr(r.qval), _ptr(r.reward_sum), engine._stream()))
 
 
+PARAM_ORDER = ["actor_linear1.weight", "actor_linear1.bias", "actor_linear2.weight", "actor_linear2.bias",
+               "critic_linear1.weight", "critic_linear1.bias", "critic_linear2.weight", "critic_linear2.bias"]
+PARAM_SHAPES = [(180, 136), (180,), (180, 180), (180,), (180, 136), (180,), (1, 180), (1,)]
+
+
+class UpdateGradients:
+    """``Agent.update``'s gradient (agent.py:39-62) on the tensor cores (``azb_a2c_update_gradients``): a flat fp32 buffer
+    holding the eight parameter gradients (``self.grads[name]`` are views into it, in PARAM_ORDER), the float64 [3] loss
+    sums and the kernels' workspace for ``capacity`` decisions."""
+
+    def __init__(self, engine, capacity):
+        self.engine, self.cap = engine, int(capacity)
+        dev = engine.device
+        sizes = [int(np.prod(sh)) for sh in PARAM_SHAPES]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.grads, off = {}, 0
+        for name, sh, n in zip(PARAM_ORDER, PARAM_SHAPES, sizes):
+            self.grads[name] = self.flat[off:off + n].view(sh)
+            off += n
+        self.sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.workspace = torch.empty(engine.lib.azb_update_workspace_bytes(self.cap), dtype=torch.uint8, device=dev)
+
+    def run(self, packed, state_rec, action, qval, n_dec=None, n_fixed=0, coeffs=(1.0, 0.5, 0.1), want_outputs=False, zero=True):
+        """Gradient SUMS over the decisions into ``self.flat`` (zeroed first unless ``zero`` is False); ``n_dec``: device
+        uint32 / int32 [1] tensor with the decision count (no host sync), else ``n_fixed``."""
+        e = self.engine
+        assert state_rec.dtype == torch.int32 and state_rec.shape == (17, self.cap) and state_rec.is_contiguous()
+        assert action.dtype == torch.uint8 and qval.dtype == torch.float32 and action.numel() >= self.cap and qval.numel() >= self.cap
+        if zero:
+            self.flat.zero_()
+            self.sums.zero_()
+        logits = value = None
+        if want_outputs:
+            n = int(n_dec) if n_dec is not None else int(n_fixed)
+            logits = torch.zeros((n, N_ACTIONS), dtype=torch.float32, device=e.device)
+            value = torch.zeros(n, dtype=torch.float32, device=e.device)
+        g = self.grads
+        _lib.check(e.lib.azb_a2c_update_gradients(
+            e._h, _ptr(state_rec), self.cap, _ptr(action), _ptr(qval), _ptr(n_dec), int(n_fixed), _ptr(packed.buf),
+            float(coeffs[0]), float(coeffs[1]), float(coeffs[2]), _ptr(self.workspace),
+            *[_ptr(g[name]) for name in PARAM_ORDER], _ptr(self.sums), _ptr(logits), _ptr(value), e._stream()))
+        return logits, value
+
+
 def mask_to_bool(mask6):
     """uint32 ``[6, G]`` mask words -> bool ``[G, 180]`` in the reference's action order."""
     m = mask6.to(torch.int64) & 0xFFFFFFFF

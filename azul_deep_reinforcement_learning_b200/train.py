@@ -7,10 +7,11 @@ equivalent (reference scripts/training.py:8-22, nn_runner.py:53-84, agent.py:39-
 ``batch_size`` episodes are played IN PARALLEL per rank (one game slot each) instead of one after the
 other; everything else follows the reference: discounted returns with gamma = 0.99, the loss of
 ``Agent.update`` (advantage not detached in the actor term, "entropy" = -mean(log pi over legal moves)
-added with +0.1), Adam(lr 3e-4).  Rollouts use the fused tensor-core policy kernel (fp16 operands, fp32 accumulation); the update
-recomputes the forward pass in fp32 with PyTorch autograd on the recorded observations.  With several
-ranks each one plays its own shard of the global game-id range and the only collectives are one flat
-gradient all-reduce per update (C1, 82,081 fp32 values) and the statistics reduction (C2).
+added with +0.1), Adam(lr 3e-4).  Rollouts are one launch of the persistent fused tensor-core policy kernel per batch
+(fp16 operands, fp32 accumulation); the update recomputes the forward pass and runs the whole backward pass on the
+recorded decision states with hand-written tcgen05 kernels (azb_a2c_update_gradients).  With several ranks each one plays
+its own shard of the global game-id range and the only collectives are one flat fp32 gradient all-reduce per update (C1,
+82,081 values) and the statistics reduction (C2, 18 float64).
 """
 import argparse
 import csv
@@ -22,7 +23,7 @@ import torch.distributed as dist
 
 from . import parallel
 from .azulnet.model import ActorCritic
-from .engine import PackedPolicy
+from .engine import PackedPolicy, UpdateGradients
 from .selfplay import BatchedGameRunner, GraphedEpisodes, PersistentEpisodes, discounted_returns, run_episodes
 
 ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF = 1.0, 0.5, 0.1          # agent.py:47-49
@@ -82,17 +83,20 @@ def allreduce_gradients(params):
 
 
 def allreduce_gradients_and_stats(params, stats):
-    """C1 + C2 in ONE collective: every gradient (sums over the local decisions, not yet divided by a count) and the
-    statistics vector travel as one float64 buffer; returns the reduced statistics.  No host synchronisation."""
-    flat = torch.cat([p.grad.reshape(-1).double() for p in params] + [stats.double().reshape(-1)])
+    """C1 + C2: every gradient (sums over the local decisions, not yet divided by a count) as ONE flat fp32 all-reduce
+    (82,081 values = 328 KB) and the statistics vector as a second, tiny float64 one; returns the reduced statistics.
+    No host synchronisation."""
+    stats = stats.double().reshape(-1).clone()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    off = 0
-    for p in params:
-        n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
-        off += n
-    return flat[off:]
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+    return stats
 
 
 def global_count(n_local, device):
@@ -102,9 +106,19 @@ def global_count(n_local, device):
     return float(t.item())
 
 
+STAT_FIELDS = 18        # n_decisions, 3 loss sums, reward sum, games, 10 game statistics sums, wins, unfinished
+
+
 class SelfPlayTrainer:
+    """``NNRunner.train`` (nn_runner.py:53-84) with ``games_per_rank`` episodes played in parallel per rank.
+
+    ``rollout``: "persistent" (default; whole episodes in one launch of the fused policy kernel), "graph" (CUDA-graph
+    replay of one policy + one opponent launch per decision) or "eager".  ``update``: "tensor" (default with the persistent
+    rollout: ``azb_a2c_update_gradients``, hand-written tcgen05 forward / backward on the decision records) or "autograd"
+    (PyTorch autograd over cuBLAS GEMMs, TF32 or -- ``tf32_update=False`` -- fp32: the reference path of the tests)."""
+
     def __init__(self, games_per_rank=1024, learning_rate=3e-4, gamma=0.99, seed=0, device=0, rank=0, world=1,
-                 rules=None, max_decisions=160, use_cuda_graph=True, tf32_update=True, rollout=None):
+                 rules=None, max_decisions=160, use_cuda_graph=True, tf32_update=True, rollout=None, update=None):
         self.rank, self.world, self.gamma, self.max_decisions = rank, world, gamma, max_decisions
         self.tf32_update = tf32_update
         self.device = torch.device("cuda", device)
@@ -115,8 +129,6 @@ class SelfPlayTrainer:
         self.runner = BatchedGameRunner(games_per_rank, rules=rules, seed=seed, device=device,
                                         game_id_base=parallel.shard(rank, games_per_rank), record_obs=True)
         self.packed = PackedPolicy(self.runner.engine, self.net)
-        # rollout engine: "persistent" = whole episodes in one launch of the fused policy kernel (azb_policy_rollout, runner
-        # mode); "graph" / "eager" = one policy + one opponent launch per decision (CUDA-graph replay / plain loop)
         self.rollout_kind = rollout if rollout is not None else ("persistent" if use_cuda_graph else "eager")
         self.graphed = self.episodes = None
         if self.rollout_kind == "persistent":
@@ -124,8 +136,20 @@ class SelfPlayTrainer:
             self.episodes = PersistentEpisodes(self.runner, self.packed, max_decisions=max_decisions)
         elif self.rollout_kind == "graph":
             self.graphed = GraphedEpisodes(self.runner, self.packed)
+        self.update_kind = update if update is not None else ("tensor" if self.rollout_kind == "persistent" else "autograd")
+        assert self.update_kind in ("tensor", "autograd")
+        # every parameter gradient is a view into ONE flat fp32 buffer (PARAM_ORDER): the tensor-core kernels add into
+        # it, autograd accumulates into the views in place, and the gradient all-reduce is a single collective on it
+        cap = self.episodes.records.cap if self.episodes is not None else 128
+        self.tc = UpdateGradients(self.runner.engine, cap)
+        for name, p in self.net.named_parameters():
+            p.grad = self.tc.grads[name]
+        self._host_stats = torch.zeros((2, STAT_FIELDS), dtype=torch.float64).pin_memory()
+        self._pending = []                                   # (slot, event) of statistics on their way to the host
+        self._slot = 0
         self.history = []
 
+    # ---- rollout ---------------------------------------------------------------------------
     def rollout(self):
         with torch.no_grad():
             self.packed.update(self.net)
@@ -145,20 +169,15 @@ class SelfPlayTrainer:
         self.net.load_state_dict({k: v.to(self.device) for k, v in state_dict.items()})
         self.opt = torch.optim.Adam(self.params, lr=self.opt.param_groups[0]["lr"])
 
+    # ---- gradients -------------------------------------------------------------------------
     def accumulate_gradients(self, obs, masks, action, qval, chunk=1 << 18):
-        """Forward recomputation + the loss of ``Agent.update`` (agent.py:45-56) + back-propagation for N recorded
-        decisions: obs bfloat16 / float32 [N,136], masks int32 [N,6] (legal-mask words), action int64 [N], qval float32 [N].
-        Leaves the SUMS over the decisions (not yet divided by a count) in ``p.grad`` and returns the float64 [3] sums of
-        the actor / critic / entropy terms."""
-        self.opt.zero_grad(set_to_none=False)
-        for p in self.params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
+        """The "autograd" path: forward recomputation + the loss of ``Agent.update`` (agent.py:45-56) + back-propagation
+        for N recorded decisions: obs bfloat16 / float32 [N,136], masks int32 [N,6] (legal-mask words), action int64 [N],
+        qval float32 [N].  Leaves the SUMS over the decisions (not yet divided by a count) in ``p.grad`` and returns the
+        float64 [3] sums of the actor / critic / entropy terms.  The dense layers run through cuBLAS (TF32 or fp32);
+        everything between the network outputs and the loss is one kernel (azb_a2c_loss_grad)."""
+        self.tc.flat.zero_()
         sums = torch.zeros(3, dtype=torch.float64, device=self.device)
-        # The dense layers run on the tensor cores through cuBLAS (TF32: fp32 storage and accumulation, 10-bit operand
-        # mantissas -- about as fine as the fp16 operands the rollout's decisions were taken with); everything between the
-        # network outputs and the loss -- masked log-softmax, the three terms, their gradient -- is one kernel
-        # (azb_a2c_loss_grad), back-propagated through the layers by autograd.
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32_update
         try:
@@ -173,11 +192,7 @@ class SelfPlayTrainer:
             torch.backends.cuda.matmul.allow_tf32 = tf32
         return sums
 
-    def update_decisions(self, obs, masks, action, qval):
-        """One single-process ``Agent.update`` (agent.py:39-62) on N recorded decisions: means over the N decisions,
-        Adam step.  Returns the loss statistics of agent.py:58-59; ``self.last_grads`` holds the mean gradients."""
-        n = int(obs.shape[0])
-        sums = self.accumulate_gradients(obs, masks, action, qval)
+    def _step(self, n, sums):
         for p in self.params:
             p.grad.mul_(1.0 / n)
         self.last_grads = {name: p.grad.clone() for name, p in self.net.named_parameters()}
@@ -186,45 +201,83 @@ class SelfPlayTrainer:
         return {"actor_loss": a, "critic_loss": c, "entropy_loss": e,
                 "ac_loss": ACTOR_COEFF * a + CRITIC_COEFF * c + ENTROPY_COEFF * e}
 
-    def update(self, batch):
+    def update_decisions(self, obs, masks, action, qval):
+        """One single-process ``Agent.update`` (agent.py:39-62) on N explicitly given decisions through the autograd path:
+        means over the N decisions, Adam step.  Returns the loss statistics of agent.py:58-59; ``self.last_grads`` holds
+        the mean gradients."""
+        return self._step(int(obs.shape[0]), self.accumulate_gradients(obs, masks, action, qval))
+
+    def update_states(self, state_rec, action, qval):
+        """:meth:`update_decisions` through the tensor-core path: state_rec int32 [17, N] (packed states the decisions
+        were taken on), action uint8 [N], qval float32 [N]."""
+        n = int(state_rec.shape[1])
+        tc = self.tc if self.tc.cap == n else UpdateGradients(self.runner.engine, n)
+        self.packed.update(self.net)
+        tc.run(self.packed, state_rec.contiguous(), action, qval, n_fixed=n, coeffs=(ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF))
+        if tc is not self.tc:
+            self.tc.flat.copy_(tc.flat)
+        return self._step(n, tc.sums)
+
+    # ---- update ----------------------------------------------------------------------------
+    def update(self, batch, defer_stats=False):
         """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch.
 
-        Gradients are accumulated as SUMS over the local decisions; one all-reduce carries them together with the
-        decision count and the batch statistics, then every rank divides by the global count (the means of
-        agent.py:47-56 over the global batch) and takes the same Adam step.  The host is not synchronised before
-        the statistics are read at the end."""
+        Gradients are accumulated as SUMS over the local decisions in the flat fp32 buffer; one fp32 all-reduce carries
+        them and a tiny float64 one the decision count and the batch statistics; every rank then divides by the global
+        count (the means of agent.py:47-56 over the global batch) and takes the same Adam step.  Nothing here waits for
+        the GPU: the statistics travel to pinned host memory asynchronously and are read by :meth:`fetch_stats`
+        (``defer_stats=True``: later -- the training loop reads them one batch late -- otherwise right away)."""
+        G = self.runner.n_games
         if "records" in batch:                        # compact decision records of the persistent rollout
             recs = batch["records"]
-            G = self.runner.n_games
-            n_local = int(recs.meta[0])
-            if n_local > recs.cap:
-                raise RuntimeError("decision records overflowed: %d decisions, capacity %d" % (n_local, recs.cap))
-            obs = recs.view.observe_bf16(-1)[:n_local]
-            masks = recs.view.legal_mask().t()[:n_local]
-            sums = self.accumulate_gradients(obs, masks, recs.action_rec[:n_local].long(), recs.qval[:n_local])
+            n_local = recs.meta[:1].double()
+            if self.update_kind == "tensor":
+                self.tc.run(self.packed, recs.state_rec, recs.action_rec, recs.qval, n_dec=recs.meta[:1],
+                            coeffs=(ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF))
+                sums = self.tc.sums
+            else:
+                n = min(int(recs.meta[0]), recs.cap)
+                obs = recs.view.observe_bf16(-1)[:n]
+                masks = recs.view.legal_mask().t()[:n]
+                sums = self.accumulate_gradients(obs, masks, recs.action_rec[:n].long(), recs.qval[:n])
             reward_total = recs.reward_sum.reshape(1)
             unfinished = (G - ((recs.flags_rec >> 1) & 1).sum()).double().reshape(1)
+            overflow = (recs.meta[:1] > recs.cap).double()
         else:
             act = batch["active"]
-            T, G = act.shape
+            T = act.shape[0]
             sel = act.reshape(-1).nonzero(as_tuple=True)[0]
-            n_local = int(sel.numel())
+            n_local = torch.full((1,), float(sel.numel()), dtype=torch.float64, device=self.device)
             obs = batch["obs"].reshape(T * G, -1)[sel]
             masks = batch["mask"].permute(0, 2, 1).reshape(T * G, 6)[sel]
             sums = self.accumulate_gradients(obs, masks, batch["action"].reshape(-1)[sel], batch["qval"].reshape(-1)[sel])
             reward_total = batch["reward"].double().mul(act).sum().reshape(1)
             unfinished = torch.full((1,), float(batch["unfinished"]), dtype=torch.float64, device=self.device)
-        t0 = time.perf_counter()
+            overflow = torch.zeros(1, dtype=torch.float64, device=self.device)
         one = torch.ones(1, dtype=torch.float64, device=self.device)
         wins = (batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum().reshape(1)
-        stats = torch.cat([one * n_local, sums, reward_total, one * G,
-                           batch["stats"].sum(dim=0), wins, unfinished])
-        stats = allreduce_gradients_and_stats(self.params, stats)
-        inv = (1.0 / stats[0].clamp_min(1.0)).float()
-        for p in self.params:
-            p.grad.mul_(inv)
+        stats = torch.cat([n_local, sums, reward_total, one * G, batch["stats"].sum(dim=0), wins, unfinished + 1e9 * overflow])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.tc.flat, op=dist.ReduceOp.SUM)          # C1: 82,081 fp32 gradient sums
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)                  # C2: 18 float64 counters
+        self.tc.flat.mul_((1.0 / stats[0].clamp_min(1.0)).float())
         self.opt.step()
-        s = stats.cpu().tolist()
+        slot = self._slot
+        self._slot ^= 1
+        self._host_stats[slot].copy_(stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((slot, ev))
+        return None if defer_stats else self.fetch_stats()
+
+    def fetch_stats(self):
+        """Statistics of the oldest update whose numbers have not been read yet (waits for that copy only)."""
+        slot, ev = self._pending.pop(0)
+        t0 = time.perf_counter()
+        ev.synchronize()
+        s = self._host_stats[slot].tolist()
+        if s[17] >= 1e9:
+            raise RuntimeError("decision records overflowed their capacity (raise max_decisions / capacity)")
         n_global, games = max(s[0], 1.0), s[5]
         out = {"transitions": s[0], "games": games, "actor_loss": s[1] / n_global, "critic_loss": s[2] / n_global,
                "entropy_loss": s[3] / n_global, "reward": s[4] / games, "update_sync_s": time.perf_counter() - t0}
@@ -259,34 +312,43 @@ class SelfPlayTrainer:
 
     def train(self, batches=1000, net_name=None, log=print, start_batch=0, checkpoint_every=1000):
         """Batches ``start_batch + 1 .. batches``.  With ``net_name``: one CSV row per batch in ``<net_name>.csv``
-        (appended to when resuming) and ``<net_name>.pt`` every ``checkpoint_every`` batches and at the end."""
+        (appended to when resuming) and ``<net_name>.pt`` every ``checkpoint_every`` batches and at the end.  The host
+        never waits for the batch it just launched: a batch's statistics are read (and logged) while the next one runs."""
         writer = fh = None
+        marks = []                                           # (batch number, host time at launch)
+
+        def finish(b, t_launch):
+            nonlocal writer, fh
+            st = self.fetch_stats()
+            now = time.perf_counter()
+            st.update(batch=b, batch_s=now - t_launch, games_per_sec=st["games"] / max(now - t_launch, 1e-9))
+            self.history.append(st)
+            if self.rank != 0:
+                return
+            if net_name is not None:
+                if writer is None:
+                    resume = start_batch > 0 and os.path.exists(net_name + ".csv")
+                    fh = open(net_name + ".csv", "a" if resume else "w", newline="")
+                    writer = csv.DictWriter(fh, fieldnames=list(st.keys()))
+                    if not resume:
+                        writer.writeheader()
+                writer.writerow(st)
+                fh.flush()
+            if log:
+                log("batch %d: %.0f games/s  reward %.2f  score %.1f vs %.1f  win %.1f%%  loss %.3f" % (
+                    b, st["games_per_sec"], st["reward"], st["player_score"], st["opponent_score"],
+                    100 * st["win_percent"], st["ac_loss"]))
+
         for b in range(start_batch, batches):
             t0 = time.perf_counter()
-            batch = self.rollout()
-            torch.cuda.synchronize(self.device)
-            t1 = time.perf_counter()
-            st = self.update(batch)
-            torch.cuda.synchronize(self.device)
-            t2 = time.perf_counter()
-            st.update(batch=b + 1, rollout_s=t1 - t0, update_s=t2 - t1, games_per_sec=st["games"] / (t2 - t0))
-            self.history.append(st)
-            if self.rank == 0:
-                if net_name is not None:
-                    if writer is None:
-                        resume = start_batch > 0 and os.path.exists(net_name + ".csv")
-                        fh = open(net_name + ".csv", "a" if resume else "w", newline="")
-                        writer = csv.DictWriter(fh, fieldnames=list(st.keys()))
-                        if not resume:
-                            writer.writeheader()
-                    writer.writerow(st)
-                    fh.flush()
-                    if (b + 1) % checkpoint_every == 0 or b + 1 == batches:  # nn_runner.py:83-84, as a state_dict
-                        self.save_checkpoint(net_name + ".pt", b + 1)
-                if log:
-                    log("batch %d: %.0f games/s  reward %.2f  score %.1f vs %.1f  win %.1f%%  loss %.3f" % (
-                        b + 1, st["games_per_sec"], st["reward"], st["player_score"], st["opponent_score"],
-                        100 * st["win_percent"], st["ac_loss"]))
+            self.update(self.rollout(), defer_stats=True)
+            marks.append((b + 1, t0))
+            if len(marks) > 1:                               # the previous batch's numbers are on the host by now
+                finish(*marks.pop(0))
+            if self.rank == 0 and net_name is not None and ((b + 1) % checkpoint_every == 0 or b + 1 == batches):
+                self.save_checkpoint(net_name + ".pt", b + 1)                  # nn_runner.py:83-84, as a state_dict
+        while marks:
+            finish(*marks.pop(0))
         if fh:
             fh.close()
         return self.history

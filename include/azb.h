@@ -223,6 +223,25 @@ int azb_a2c_loss_grad(azb_t* h, int64_t n, const float* logits, const float* val
                       const int64_t* action, const float* qval, float scale, float actor_coeff, float critic_coeff,
                       float entropy_coeff, float* dlogits, float* dvalue, double* sums, void* stream);
 
+/* ---- a19 on the tensor cores: the whole of Agent.update's gradient (agent.py:39-62) for recorded decisions, no library
+ * GEMM and no autograd.  Inputs: the decision records of azb_policy_rollout's runner mode -- state_rec uint32 [W][capacity]
+ * (packed state each decision was taken on; observation and legal mask are rebuilt from it), action uint8 [capacity], qval
+ * float [capacity] (azb_discounted_returns) -- and the decision count, either on the device (n_dec uint32 [1], clamped to
+ * capacity; no host synchronisation) or n_fixed when n_dec is NULL; `packed` = the current parameters' image
+ * (azb_policy_pack_weights).  Forward recomputation (model.py:23-41), masked log-softmax, the three loss terms with the
+ * reference's non-detached advantage, and the backward pass through both heads run as tcgen05 GEMMs (fp16 operands, fp32
+ * accumulation).  The gradient SUMS over the decisions are ADDED to the eight fp32 buffers in torch layout ([out][in]):
+ * grad_w1a [180][136], grad_b1a [180], grad_w2a [180][180], grad_b2a [180], grad_w1c [180][136], grad_b1c [180],
+ * grad_w2c [180], grad_b2c [1]; sums double [3] += the unscaled actor / critic / entropy loss terms.  workspace: device
+ * scratch of azb_update_workspace_bytes(capacity) bytes.  logits_out float [n][180] / value_out float [n] (optional): the
+ * recomputed network outputs. */
+int64_t azb_update_workspace_bytes(int64_t capacity);
+int azb_a2c_update_gradients(azb_t* h, const uint32_t* state_rec, int64_t capacity, const uint8_t* action, const float* qval,
+                             const uint32_t* n_dec, int64_t n_fixed, const void* packed, float actor_coeff, float critic_coeff,
+                             float entropy_coeff, void* workspace, float* grad_w1a, float* grad_b1a, float* grad_w2a,
+                             float* grad_b2a, float* grad_w1c, float* grad_b1c, float* grad_w2c, float* grad_b2c, double* sums,
+                             float* logits_out, float* value_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ def lib():
 
 def test_header_symbols_exported(lib):
     hdr = open(os.path.join(REPO, "include", "azb.h")).read()
-    declared = set(re.findall(r"^\s*(?:const char\*|int)\s+(azb_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:const char\*|int64_t|int)\s+(azb_\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name

@@ -296,3 +296,69 @@ def test_persistent_runner_rollout_equals_episode_loop():
     q = discounted_returns(eager["reward"], act, 0.99)
     assert torch.allclose(r.qval[slots], q[act], rtol=1e-6, atol=1e-5)
     assert abs(float(r.reward_sum) - float(eager["reward"][act].sum())) < 1e-6
+
+
+def _autograd_reference(net, recs, n, coeffs):
+    """fp32 torch autograd of train.a2c_loss_terms (pinned to the reference's Agent.update by tests/test_update_golden_cpu.py)
+    on the first n decision records: gradient SUMS per parameter name, loss sums, logits, value."""
+    from azul_deep_reinforcement_learning_b200.engine import mask_rows_to_bool
+    from azul_deep_reinforcement_learning_b200.train import a2c_loss_terms
+    obs = recs.view.observe(-1)[:n]
+    rows = recs.view.legal_mask().t()[:n].contiguous()
+    action, qval = recs.action_rec[:n].long(), recs.qval[:n]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        net.zero_grad()
+        a, c, e = a2c_loss_terms(net, obs, mask_rows_to_bool(rows), action, qval)
+        (coeffs[0] * a + coeffs[1] * c + coeffs[2] * e).backward()
+        with torch.no_grad():
+            logits = net.actor_linear2(torch.relu(net.actor_linear1(obs)))
+            value = net.forward_critic(obs).squeeze(1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return {k: p.grad.clone() for k, p in net.named_parameters()}, torch.stack([a, c, e]).double().detach(), logits, value
+
+
+@pytest.mark.parametrize("games,scale", [(300, 1.0), (1500, 2.5)])
+def test_tensor_core_update_gradients_match_autograd(games, scale):
+    """azb_a2c_update_gradients (forward recomputation, loss and the whole backward pass as tcgen05 GEMMs, fp16 operands /
+    fp32 accumulation) against fp32 autograd of the reference's loss on the decision records of a real rollout:
+    recomputed logits / value, the three loss sums and all eight parameter gradients; decision count read on the device."""
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import PARAM_ORDER, PackedPolicy, UpdateGradients
+    from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner, PersistentEpisodes
+    torch.manual_seed(3)
+    net = ActorCritic(136, 180).cuda()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(scale)
+    gr = BatchedGameRunner(games, seed=8)
+    packed = PackedPolicy(gr.engine, net)
+    recs = PersistentEpisodes(gr, packed, max_decisions=160).run(gamma=0.99)
+    n = int(recs.meta[0])
+    assert 20 * games < n <= recs.cap
+    coeffs = (1.0, 0.5, 0.1)
+    want, want_sums, want_logits, want_value = _autograd_reference(net, recs, n, coeffs)
+    upd = UpdateGradients(gr.engine, recs.cap)
+    logits, value = upd.run(packed, recs.state_rec, recs.action_rec, recs.qval, n_dec=recs.meta[:1], coeffs=coeffs, want_outputs=True)
+    torch.cuda.synchronize()
+    # forward recomputation: same bound as the policy kernel (per element, floor = the row's largest |logit|)
+    floor = want_logits.abs().max(dim=1, keepdim=True).values
+    assert bool(((logits - want_logits).abs() <= 1e-3 * torch.maximum(want_logits.abs(), floor)).all())
+    assert bool(((value - want_value).abs() <= 1e-3 * torch.maximum(want_value.abs(), want_value.abs().max())).all())
+    assert float(((upd.sums - want_sums).abs() / want_sums.abs().clamp_min(1.0)).max()) < 2e-3
+    # gradients: the critic and the actor's second layer to ~1e-3 of the tensor's largest entry; the actor's first layer
+    # additionally sees hidden units whose pre-activation lies within the forward rounding error of zero switch their ReLU
+    # derivative (each switch moves an entry by a whole term of the sum): a few per cent at 10^4 decisions, less with more
+    for name in PARAM_ORDER:
+        g, w = upd.grads[name].double(), want[name].double()
+        err = float((g - w).abs().max())
+        tol = 6e-2 if name.startswith("actor_linear1") else 1e-2
+        assert err <= tol * float(w.abs().max()), (name, err, float(w.abs().max()))
+        assert float((g * w).sum() / (g.norm() * w.norm())) > 0.9998, name
+    # a second call without zeroing accumulates; n_fixed (host count) gives the same result as the device counter
+    flat1 = upd.flat.clone()
+    upd.run(packed, recs.state_rec, recs.action_rec, recs.qval, n_fixed=n, coeffs=coeffs, zero=False)
+    torch.cuda.synchronize()
+    assert float((upd.flat - 2 * flat1).abs().max()) <= 2e-3 * float(flat1.abs().max())
