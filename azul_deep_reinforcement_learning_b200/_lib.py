@@ -62,7 +62,7 @@ def load():
     f32 = ctypes.c_float
     L.azb_a2c_loss_grad.argtypes = [vp, i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp]
     L.azb_policy_rollout.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i64] + [vp] * 16
-    L.azb_discounted_returns.argtypes = [vp, i32, ctypes.c_double, vp, vp, vp, vp, vp, vp]
+    L.azb_discounted_returns.argtypes = [vp, i32, ctypes.c_double, vp, vp, vp, vp, vp, vp, vp]
     L.azb_update_workspace_bytes.argtypes = [i64]
     L.azb_update_workspace_bytes.restype = i64
     L.azb_a2c_update_gradients.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, f32, f32, f32] + [vp] * 13

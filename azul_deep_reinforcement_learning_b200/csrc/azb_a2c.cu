@@ -124,9 +124,10 @@ __global__ void __launch_bounds__(256) k_a2c_loss_grad(Args A)
 // reference then casts to float32, agent.py:41), and scatters q to the decision's compact slot.
 __global__ void k_returns(int64_t n, int k, double gamma, const int16_t* __restrict__ reward_rec,
                           const uint8_t* __restrict__ flags_rec, const int32_t* __restrict__ slot_rec,
-                          float* __restrict__ qval, double* __restrict__ reward_sum)
+                          float* __restrict__ qval, double* __restrict__ reward_sum, const uint32_t* __restrict__ steps_used)
 {
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (steps_used && (int)*steps_used < k) k = (int)*steps_used;      // decision iterations the rollout actually ran
     double q = 0.0, total = 0.0;
     if (g < n) {
         for (int t = k - 1; t >= 0; t--) {
@@ -150,13 +151,13 @@ __global__ void k_returns(int64_t n, int k, double gamma, const int16_t* __restr
 
 extern "C" int azb_discounted_returns(azb_t* h, int k_decisions, double gamma, const int16_t* reward_rec,
                                       const uint8_t* flags_rec, const int32_t* slot_rec, float* qval, double* reward_sum,
-                                      void* stream)
+                                      const uint32_t* steps_used, void* stream)
 {
     CHECK_HANDLE(h);
     if (k_decisions < 0) return azb_fail(AZB_E_INVALID, "k_decisions < 0%s");
     if (!reward_rec || !flags_rec || !slot_rec || !qval) return azb_fail(AZB_E_INVALID, "null buffer%s");
     a2c::k_returns<<<(unsigned)((h->n_games + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        h->n_games, k_decisions, gamma, reward_rec, flags_rec, slot_rec, qval, reward_sum);
+        h->n_games, k_decisions, gamma, reward_rec, flags_rec, slot_rec, qval, reward_sum, steps_used);
     CHECK_LAUNCH();
     return 0;
 }

@@ -14,7 +14,8 @@
 //       dHc = dv w2c * (Hc > 0);  grad w2c += dv Hc;  grad b2c += dv        CUDA cores
 //     and writes the operand tiles X, Ha, dL, dHa, dHc (fp16, in the shared-memory core-matrix layout) to HBM.
 //   k_update_dw       dW = A^T B summed over all tiles, both operands MN-major straight from those tiles (bulk-copied
-//     into a two-stage shared-memory ring), accumulators in TMEM for the whole kernel:
+//     into a four-stage shared-memory ring of half tiles), accumulators in TMEM for the whole kernel; the three products
+//     run side by side in one launch (CTA b works on product b % 3):
 //       grad W2a | b2a = dL^T  [Ha | 1]      grad W1a | b1a = dHa^T [X | 1]      grad W1c | b1c = dHc^T [X | 1]
 //     (the bias gradients are the columns of the constant-one inputs), reduced into the global gradient with atomics.
 // Gradients are SUMS over the decisions (the caller divides by the global decision count after the all-reduce).
@@ -33,6 +34,12 @@ using namespace pol;
 constexpr int X_TILE_BYTES = K1_CHUNKS * M_GROUPS * 128;     // 36,864: [18 chunks][16 row groups][8 rows][8 halves]
 constexpr int H_TILE_BYTES = A_BYTES;                        // 49,152: [24 chunks][16 row groups][8 rows][8 halves]
 constexpr int CHUNKS_PER_PART = PART_COLS / 8;               // 6
+// In HBM a tile is stored as two halves of 64 decisions, each [column chunk][8 row groups][8 rows][8 halves] and
+// contiguous, so that k_update_dw can stream half tiles (a four-stage ring instead of two stages of whole tiles).
+__device__ __forceinline__ int hbm_off(int chunk, int row, int chunks)
+{
+    return (((row >> 6) * chunks + chunk) * 8 + ((row >> 3) & 7)) * 128 + (row & 7) * 16;
+}
 
 struct FwdArgs {
     const uint32_t* __restrict__ state_rec;   // [17][cap] packed states the decisions were taken on
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
 #pragma unroll
             for (int c = 0; c < CHUNKS_PER_PART; c++) {
                 const int off = ((CHUNKS_PER_PART * part + c) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16;
-                *reinterpret_cast<uint4*>(g_x + off) = *reinterpret_cast<const uint4*>(t1 + off);
+                *reinterpret_cast<uint4*>(g_x + hbm_off(CHUNKS_PER_PART * part + c, row, K1_CHUNKS)) = *reinterpret_cast<const uint4*>(t1 + off);
             }
         }
         mbar_wait(bar1, phase);
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
                 }
                 const int off = (((c0 >> 3) + qq) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16;
                 *reinterpret_cast<uint4*>(t1 + off) = o;
-                *reinterpret_cast<uint4*>(g_ha + off) = o;
+                *reinterpret_cast<uint4*>(g_ha + hbm_off((c0 >> 3) + qq, row, K2_CHUNKS)) = o;
             }
 #pragma unroll
             for (int i = 0; i < 16; i++) hmask |= (uint64_t)((c0 + i < HID && v[i] > 0.0f) ? 1u : 0u) << (16 * cc + i);
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
                 o.z = pack_f16(v[8 * qq + 4], v[8 * qq + 5]); o.w = pack_f16(v[8 * qq + 6], v[8 * qq + 7]);
                 const int off = (((c0 >> 3) + qq) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16;
                 *reinterpret_cast<uint4*>(t1 + off) = o;
-                *reinterpret_cast<uint4*>(g_dl + off) = o;
+                *reinterpret_cast<uint4*>(g_dl + hbm_off((c0 >> 3) + qq, row, K2_CHUNKS)) = o;
             }
         }
         fence_async_smem();
@@ -362,8 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
                 uint4 o;
                 o.x = pack_f16(d[8 * qq + 0], d[8 * qq + 1]); o.y = pack_f16(d[8 * qq + 2], d[8 * qq + 3]);
                 o.z = pack_f16(d[8 * qq + 4], d[8 * qq + 5]); o.w = pack_f16(d[8 * qq + 6], d[8 * qq + 7]);
-                const int off = (((c0 >> 3) + qq) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16;
-                *reinterpret_cast<uint4*>(g_dhc + off) = o;
+                *reinterpret_cast<uint4*>(g_dhc + hbm_off((c0 >> 3) + qq, row, K2_CHUNKS)) = o;
             }
             // column sums over the warp's 32 rows: lane l keeps columns l (c = 0, 1) and 32 + l (c = 2)
 #pragma unroll
@@ -393,8 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
                 uint4 o;
                 o.x = pack_f16(v[8 * qq + 0], v[8 * qq + 1]); o.y = pack_f16(v[8 * qq + 2], v[8 * qq + 3]);
                 o.z = pack_f16(v[8 * qq + 4], v[8 * qq + 5]); o.w = pack_f16(v[8 * qq + 6], v[8 * qq + 7]);
-                const int off = (((c0 >> 3) + qq) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16;
-                *reinterpret_cast<uint4*>(g_dha + off) = o;
+                *reinterpret_cast<uint4*>(g_dha + hbm_off((c0 >> 3) + qq, row, K2_CHUNKS)) = o;
             }
         }
         tc_fence_before();
@@ -434,34 +439,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
 // dW = sum over tiles of A_tile^T B_tile.  A tile: [128 decisions][192 columns], B tile: [128 decisions][NB columns], both
 // fp16 in the core-matrix layout [column chunk][row group][8 rows][8 columns] -- i.e. MN-major operands (the M / N index is
 // the contiguous one, K = the decision).  M = 192 is covered by two M = 128 MMAs (the second reads 64 columns past the A
-// tile: the B tile follows it in the stage buffer, its values only reach accumulator rows >= 192, which are dropped).
+// half tile: the B half follows it in the stage buffer, its values only reach accumulator rows >= 192, which are dropped).
 // ---------------------------------------------------------------------------------------------------------------------
-struct DwArgs {
+struct DwGemm {
     const unsigned char* __restrict__ a_tiles;   // [tiles][49152]
     const unsigned char* __restrict__ b_tiles;   // [tiles][b_bytes]
-    int b_bytes;
-    const uint32_t* __restrict__ n_dec;
-    int64_t n_fixed, cap;
+    int b_bytes, nb;                             // nb = columns of the B tile (192 or 144) = N of the MMA
     float* __restrict__ grad_w;                  // [180][ld] +=
     int ld, n_cols;                              // columns < n_cols go to grad_w[row][col]
     float* __restrict__ grad_b;                  // [180] += column bias_col
     int bias_col;
     int critic_rows;                             // 1: accumulator row j is critic unit critic_unit(j) (dHc tiles)
 };
+struct DwArgs {
+    DwGemm gemm[3];                              // CTA b works on gemm[b % 3]: the three products run side by side
+    const uint32_t* __restrict__ n_dec;
+    int64_t n_fixed, cap;
+};
 
 constexpr int DW_THREADS = 256;
-constexpr int DW_STAGE_BYTES = 2 * H_TILE_BYTES;             // A tile + room for the larger B tile
+constexpr int DW_STAGES = 4;
+constexpr int DW_HALF_A = H_TILE_BYTES / 2;                  // 24,576: half an A tile (64 decisions)
+constexpr int DW_STAGE_BYTES = 2 * DW_HALF_A;                // A half + room for the larger B half
 
-template <int NB>
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(DW_THREADS, 1) k_update_dw(DwArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bars[5];                             // full[2], empty[2], done
+    __shared__ uint64_t bars[2 * DW_STAGES + 1];             // full[S], empty[S], done
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), done = smem_u32(&bars[4]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[DW_STAGES]), done = smem_u32(&bars[2 * DW_STAGES]);
     if (tid == 0) {
-        for (int i = 0; i < 5; i++) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < 2 * DW_STAGES + 1; i++) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -476,37 +490,44 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_update_dw(DwArgs A)
     int64_t n = A.n_dec ? (int64_t)*A.n_dec : A.n_fixed;
     n = n < A.cap ? n : A.cap;
     const int64_t tiles = (n + TILE_M - 1) / TILE_M;
-    const int64_t my_tiles = (int64_t)blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // CTA b: product b % 3, and among that product's CTAs number b / 3 of (gridDim.x - role + 2) / 3
+    const int role = (int)(blockIdx.x % 3u), rank = (int)(blockIdx.x / 3u), ranks = ((int)gridDim.x - role + 2) / 3;
+    const DwGemm& G = A.gemm[role];
+    const int NB = G.nb;
+    const int64_t my_tiles = rank < tiles ? (tiles - rank + ranks - 1) / ranks : 0;
+    const int64_t my_halves = 2 * my_tiles;                  // work items: half tiles of 64 decisions
 
     if (tid == 0 && my_tiles > 0) {
-        // producer and MMA issuer in one thread: tile i + 1 is in flight while the MMAs of tile i run
+        // producer and MMA issuer in one thread: up to DW_STAGES - 1 half tiles are in flight while the MMAs of one run
         const uint32_t idesc = instr_desc(NB) | (1u << 15) | (1u << 16);     // A and B MN-major
+        const int b_half = G.b_bytes / 2;
         auto load = [&](int64_t i) {
-            const int s = (int)(i & 1);
-            const int64_t t = (int64_t)blockIdx.x + i * gridDim.x;
+            const int s = (int)(i % DW_STAGES);
+            const int64_t t = (int64_t)rank + (i >> 1) * ranks;
             const uint32_t dst = smem_u32(smem) + s * DW_STAGE_BYTES, bar = full0 + 8 * s;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(H_TILE_BYTES + A.b_bytes)) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(DW_HALF_A + b_half)) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(A.a_tiles + t * H_TILE_BYTES), "r"((uint32_t)H_TILE_BYTES), "r"(bar) : "memory");
+                         ::"r"(dst), "l"(G.a_tiles + t * H_TILE_BYTES + (i & 1) * DW_HALF_A), "r"((uint32_t)DW_HALF_A), "r"(bar) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + H_TILE_BYTES), "l"(A.b_tiles + t * (int64_t)A.b_bytes), "r"((uint32_t)A.b_bytes), "r"(bar) : "memory");
+                         ::"r"(dst + DW_HALF_A), "l"(G.b_tiles + t * (int64_t)G.b_bytes + (i & 1) * b_half), "r"((uint32_t)b_half), "r"(bar) : "memory");
         };
-        load(0);
-        for (int64_t i = 0; i < my_tiles; i++) {
-            const int s = (int)(i & 1);
-            if (i + 1 < my_tiles) {
-                if (i >= 1) mbar_wait(empty0 + 8 * (s ^ 1), (uint32_t)(((i - 1) >> 1) & 1));    // the MMAs of tile i - 1 released that stage
-                load(i + 1);
+        for (int64_t i = 0; i < DW_STAGES - 1 && i < my_halves; i++) load(i);
+        for (int64_t i = 0; i < my_halves; i++) {
+            const int s = (int)(i % DW_STAGES);
+            const int64_t nx = i + DW_STAGES - 1;            // refill the stage the MMAs of item i - 1 read
+            if (nx < my_halves) {
+                if (i >= 1) mbar_wait(empty0 + 8 * (int)(nx % DW_STAGES), (uint32_t)(((i - 1) / DW_STAGES) & 1));
+                load(nx);
             }
-            mbar_wait(full0 + 8 * s, (uint32_t)((i >> 1) & 1));
+            mbar_wait(full0 + 8 * s, (uint32_t)((i / DW_STAGES) & 1));
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem) + s * DW_STAGE_BYTES, b_addr = a_addr + H_TILE_BYTES;
+            const uint32_t a_addr = smem_u32(smem) + s * DW_STAGE_BYTES, b_addr = a_addr + DW_HALF_A;
 #pragma unroll 1
-            for (int ks = 0; ks < TILE_M / 16; ks++) {
-                // MN-major: SBO = next 8 columns (a whole chunk: M_GROUPS * 128 bytes), LBO = next 8 decisions (128 bytes)
-                const uint64_t bd = smem_desc(b_addr + ks * 256, 128, M_GROUPS * 128);
-                const uint64_t ad0 = smem_desc(a_addr + ks * 256, 128, M_GROUPS * 128);
-                const uint64_t ad1 = smem_desc(a_addr + 16 * (M_GROUPS * 128) + ks * 256, 128, M_GROUPS * 128);
+            for (int ks = 0; ks < 64 / 16; ks++) {
+                // MN-major: SBO = next 8 columns (a chunk of the half tile: 8 row groups = 1,024 bytes), LBO = next 8 decisions (128 bytes)
+                const uint64_t bd = smem_desc(b_addr + ks * 256, 128, 1024);
+                const uint64_t ad0 = smem_desc(a_addr + ks * 256, 128, 1024);
+                const uint64_t ad1 = smem_desc(a_addr + 16 * 1024 + ks * 256, 128, 1024);   // columns 128..255: runs 8 KB into the B half
                 umma(tmem_base, ad0, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
                 umma(tmem_base + NB, ad1, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
             }
@@ -517,21 +538,30 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_update_dw(DwArgs A)
     if (my_tiles > 0) {
         mbar_wait(done, 0);
         tc_fence_after();
-        // ---- epilogue: accumulator rows (TMEM lanes) = M index; warps 0-3 take M tile 0, warps 4-7 M tile 1 ----
+        // ---- epilogue: accumulator rows (TMEM lanes) = M index; warps 0-3 take M tile 0, warps 4-7 M tile 1; the sums of
+        // this CTA's tiles are added to the global gradient with 16-byte vector reductions ----
         const int mt = warp >> 2;
         const int j = mt * 128 + (warp & 3) * 32 + lane;                       // accumulator row
-        const int out_row = j < 192 ? (A.critic_rows ? critic_unit(j) : (j < HID ? j : -1)) : -1;
+        const int out_row = j < 192 ? (G.critic_rows ? critic_unit(j) : (j < HID ? j : -1)) : -1;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * NB);
 #pragma unroll 1
         for (int c0 = 0; c0 < NB; c0 += 16) {
             float v[16];
             tmem_ld16(taddr + c0, v);
             if (out_row >= 0) {
+                float* wrow = G.grad_w + (int64_t)out_row * G.ld;           // rows are 16-byte aligned: ld = 180 or 136
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
+                for (int i = 0; i < 16; i += 4) {
                     const int col = c0 + i;
-                    if (col < A.n_cols) atomicAdd(A.grad_w + (int64_t)out_row * A.ld + col, v[i]);
-                    else if (col == A.bias_col) atomicAdd(A.grad_b + out_row, v[i]);
+                    if (col + 4 <= G.n_cols) {
+                        red_add_v4(wrow + col, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            if (col + e < G.n_cols) atomicAdd(wrow + col + e, v[i + e]);
+                            else if (col + e == G.bias_col) atomicAdd(G.grad_b + out_row, v[i + e]);
+                        }
+                    }
                 }
             }
         }
@@ -584,24 +614,18 @@ int azb_a2c_update_gradients(azb_t* h, const uint32_t* state_rec, int64_t capaci
     AZB_CUDA(cudaFuncSetAttribute(upd::k_update_fwd_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
     upd::k_update_fwd_bwd<<<grid, pol::THREADS, pol::SMEM_BYTES, st>>>(F);
     CHECK_LAUNCH();
-    const int dw_smem = 2 * upd::DW_STAGE_BYTES;
-    AZB_CUDA(cudaFuncSetAttribute(upd::k_update_dw<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
-    AZB_CUDA(cudaFuncSetAttribute(upd::k_update_dw<144>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    const int dw_smem = upd::DW_STAGES * upd::DW_STAGE_BYTES;
+    AZB_CUDA(cudaFuncSetAttribute(upd::k_update_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     upd::DwArgs D;
     D.n_dec = n_dec; D.n_fixed = n_fixed; D.cap = capacity;
     // grad W2a | b2a = dL^T [Ha | 1]
-    D.a_tiles = F.dl; D.b_tiles = F.ha; D.b_bytes = upd::H_TILE_BYTES; D.grad_w = grad_w2a; D.ld = pol::HID; D.n_cols = pol::HID;
-    D.grad_b = grad_b2a; D.bias_col = pol::BIAS_K2; D.critic_rows = 0;
-    upd::k_update_dw<192><<<grid, upd::DW_THREADS, dw_smem, st>>>(D);
-    CHECK_LAUNCH();
+    D.gemm[0] = upd::DwGemm{F.dl, F.ha, upd::H_TILE_BYTES, 192, grad_w2a, pol::HID, pol::HID, grad_b2a, pol::BIAS_K2, 0};
     // grad W1a | b1a = dHa^T [X | 1]
-    D.a_tiles = F.dha; D.b_tiles = F.xt; D.b_bytes = upd::X_TILE_BYTES; D.grad_w = grad_w1a; D.ld = pol::OBS; D.n_cols = pol::OBS;
-    D.grad_b = grad_b1a; D.bias_col = pol::BIAS_K1; D.critic_rows = 0;
-    upd::k_update_dw<144><<<grid, upd::DW_THREADS, dw_smem, st>>>(D);
-    CHECK_LAUNCH();
+    D.gemm[1] = upd::DwGemm{F.dha, F.xt, upd::X_TILE_BYTES, 144, grad_w1a, pol::OBS, pol::OBS, grad_b1a, pol::BIAS_K1, 0};
     // grad W1c | b1c = dHc^T [X | 1]
-    D.a_tiles = F.dhc; D.grad_w = grad_w1c; D.grad_b = grad_b1c; D.critic_rows = 1;
-    upd::k_update_dw<144><<<grid, upd::DW_THREADS, dw_smem, st>>>(D);
+    D.gemm[2] = upd::DwGemm{F.dhc, F.xt, upd::X_TILE_BYTES, 144, grad_w1c, pol::OBS, pol::OBS, grad_b1c, pol::BIAS_K1, 1};
+    const int dw_grid = h->sm_count < 3 ? 3 : h->sm_count;       // every product needs at least one CTA
+    upd::k_update_dw<<<dw_grid, upd::DW_THREADS, dw_smem, st>>>(D);
     CHECK_LAUNCH();
     return 0;
 }

@@ -373,7 +373,8 @@ def discounted_returns_records(engine, records, gamma):
     """nn_runner.py:72-75 on the decision records: fills ``records.qval`` (compact) and ``records.reward_sum``."""
     r = records
     _lib.check(engine.lib.azb_discounted_returns(engine._h, r.k, float(gamma), _ptr(r.reward_rec), _ptr(r.flags_rec),
-                                                _ptr(r.slot_rec), _ptr(r.qval), _ptr(r.reward_sum), engine._stream()))
+                                                _ptr(r.slot_rec), _ptr(r.qval), _ptr(r.reward_sum),
+                                                ctypes.c_void_p(r.meta.data_ptr() + 4), engine._stream()))
 
 
 PARAM_ORDER = ["actor_linear1.weight", "actor_linear1.bias", "actor_linear2.weight", "actor_linear2.bias",

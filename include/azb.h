@@ -203,9 +203,10 @@ int azb_policy_rollout(azb_t* h, uint32_t* state, const void* packed, int mode, 
 
 /* Discounted returns of NNRunner.train (nn_runner.py:72-75) over the records of azb_policy_rollout's runner mode:
  * q_t = r_t + gamma * q_{t+1} over each game's decisions (accumulated in double like the reference's numpy loop), written
- * as float to qval[slot] (float [rec_cap]); reward_sum (double [1], optional) += the sum of all rewards. */
+ * as float to qval[slot] (float [rec_cap]); reward_sum (double [1], optional) += the sum of all rewards; steps_used
+ * (device uint32 [1], optional: azb_policy_rollout's output) bounds the walk to the decision iterations actually run. */
 int azb_discounted_returns(azb_t* h, int k_decisions, double gamma, const int16_t* reward_rec, const uint8_t* flags_rec,
-                           const int32_t* slot_rec, float* qval, double* reward_sum, void* stream);
+                           const int32_t* slot_rec, float* qval, double* reward_sum, const uint32_t* steps_used, void* stream);
 
 /* ---- a19: the loss of Agent.update and its gradient at the network outputs --------------------
  * For n recorded agent decisions (device arrays): logits float [n][180] (raw actor outputs), value float [n],
