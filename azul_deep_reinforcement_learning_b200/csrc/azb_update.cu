@@ -121,6 +121,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
     double acc_a = 0.0, acc_c = 0.0, acc_e = 0.0;            // loss sums (part 0 threads)
     float gw2c_lo = 0.0f, gw2c_hi = 0.0f, gb2c = 0.0f;       // lane l of a warp: critic columns col0 + l and col0 + 32 + l (l < 16)
 
+    // the packed state of a tile's decisions is loaded one tile ahead (before the previous tile's last epilogue)
+    Game<2> nxt;
+    if ((int64_t)blockIdx.x < tiles) {
+        const int64_t g0 = (int64_t)blockIdx.x * TILE_M + row;
+        nxt.load(A.state_rec, A.cap, g0 < n ? g0 : n - 1);
+    }
     mbar_wait(bar_w, 0);
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t g = tile * TILE_M + row;
@@ -135,8 +141,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
         // ---- observation of the recorded state (mover's perspective, game_runner.py:56-72) and its legal mask ----
         uint64_t mybits;
         {
-            Game<2> gm;
-            gm.load(A.state_rec, A.cap, gl);
+            const Game<2> gm = nxt;
             build_obs_tile(gm, t1, row, part);
             uint32_t m[6], lin[6];
             legal_mask(gm, m);
@@ -381,6 +386,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
         }
         gw2c_lo += gsum_lo; gw2c_hi += gsum_hi;
         if (part == 0) gb2c += dv;
+        if (tile + gridDim.x < tiles) {                    // in flight during epilogue 3
+            const int64_t g2 = (tile + gridDim.x) * TILE_M + row;
+            nxt.load(A.state_rec, A.cap, g2 < n ? g2 : n - 1);
+        }
         mbar_wait(bar3, phase);
         tc_fence_after();
         phase ^= 1;
