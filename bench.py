@@ -72,6 +72,7 @@ def parse_args():
                     help="--mode step: random-agent env steps before the timed step (0 = fresh games: no round can end)")
     ap.add_argument("--policy-k", type=int, default=64, help="policy: decisions per game per launch of the persistent self-play kernel")
     ap.add_argument("--pyref-worker", type=float, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--pyref-kind", default="runner", choices=["runner", "selfplay", "train"], help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -122,9 +123,13 @@ def cpu_model_name():
     return "unknown"
 
 
-def pyref_worker(seconds):
-    """One process of the Python-reference leg: the UNMODIFIED reference's GameRunner (game_runner.py:9-85, default
-    rules) with seat 1 driven by its RandomAgent against its RandomAgent opponent (BASELINE.json configs[0])."""
+def pyref_worker(seconds, kind="runner"):
+    """One process of the Python-reference leg, on the UNMODIFIED reference (baseline/_ref):
+    runner    GameRunner (game_runner.py:9-85, default rules), seat 1 driven by its RandomAgent against its RandomAgent
+              opponent (BASELINE.json configs[0])
+    selfplay  NNRunner.run_episode (nn_runner.py:17-47) of a random-init Agent against a random-init Agent opponent
+              (scripts/run_batch.py: every seat sampled from the policy, configs[3])
+    train     NNRunner.train(batch_size=10, batches=1) (scripts/training.py defaults, configs[4])"""
     sys.path.insert(0, PYREF_DIR)
     import numpy as np
     if not hasattr(np, "int"):
@@ -135,17 +140,49 @@ def pyref_worker(seconds):
     import torch
     torch.set_num_threads(1)
     from azulnet.game_runner import GameRunner, RandomAgent
-    agent, gr = RandomAgent(), GameRunner()
+    if kind == "runner":
+        agent, gr = RandomAgent(), GameRunner()
 
-    def episode(seed):
-        random.seed(seed)
-        gr.reset()
-        done = False
-        while not done:
-            valid = gr.get_valid_moves()
-            a = agent.get_a_output(None, torch.from_numpy(valid.reshape(1, 180)))
-            _, done = gr.step(a)
-        return gr.move_counter
+        def episode(seed):
+            random.seed(seed)
+            gr.reset()
+            done = False
+            while not done:
+                valid = gr.get_valid_moves()
+                a = agent.get_a_output(None, torch.from_numpy(valid.reshape(1, 180)))
+                _, done = gr.step(a)
+            return gr.move_counter, 1
+    else:
+        from azulnet.agent import Agent
+        from azulnet.nn_runner import NNRunner
+        torch.manual_seed(0)
+        learner = Agent()
+        gr = GameRunner(opponent=Agent()) if kind == "selfplay" else GameRunner()
+        runner = NNRunner(learner, gr)
+        counted = {"steps": 0}
+        orig_step = gr.game.__class__.step
+
+        def episode(seed):
+            import numpy
+            random.seed(seed)
+            numpy.random.seed(seed % (2 ** 31))
+            if kind == "selfplay":
+                runner.run_episode()
+                return gr.move_counter, 1
+            n0 = counted["steps"]
+            orig_reset = gr.reset
+
+            def reset():                                  # GameRunner.reset zeroes move_counter: bank the finished episode first
+                counted["steps"] += gr.move_counter
+                orig_reset()
+            gr.reset = reset
+            try:
+                runner.train(net_name=None, batch_size=10, batches=1)
+            finally:
+                gr.reset = orig_reset
+            counted["steps"] += gr.move_counter
+            gr.move_counter = 0
+            return counted["steps"] - n0, 10
 
     seed = os.getpid() * 1000
     episode(seed)                                     # warm-up
@@ -156,15 +193,16 @@ def pyref_worker(seconds):
     while time.perf_counter() - t0 < seconds:
         seed += 1
         try:
-            steps += episode(seed)
-            games += 1
+            st, n = episode(seed)
+            steps += st
+            games += n
         except (ValueError, IndexError):              # stuck round: the reference crashes; not counted
             crashed += 1
     print(json.dumps({"steps": steps, "games": games, "seconds": time.perf_counter() - t0, "crashed": crashed}), flush=True)
 
 
-def _run_pyref_workers(n, seconds):
-    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--pyref-worker", str(seconds)],
+def _run_pyref_workers(n, seconds, kind="runner"):
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--pyref-worker", str(seconds), "--pyref-kind", kind],
                               stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=REPO)
              for _ in range(n)]
     try:
@@ -186,7 +224,14 @@ def _run_pyref_workers(n, seconds):
     return sum(r["steps"] for r in res), sum(r["games"] for r in res), wall, sum(r["crashed"] for r in res)
 
 
-def python_reference_leg(seconds):
+PYREF_WHAT = {
+    "runner": "unmodified azulnet GameRunner (default rules: random first player, Lid pool), RandomAgent on both seats (BASELINE.json configs[0])",
+    "selfplay": "unmodified azulnet NNRunner.run_episode, random-init Agent against a random-init Agent opponent (scripts/run_batch.py; configs[3] on the CPU)",
+    "train": "unmodified azulnet NNRunner.train(batch_size=10, batches=1) per iteration, Agent vs RandomAgent (scripts/training.py; configs[4] on the CPU)",
+}
+
+
+def python_reference_leg(seconds, kind="runner"):
     """the reference CPU game_runner on this host, os.cpu_count() single-threaded processes for
     `seconds` of wall time after warm-up, plus the single-core figure (one process alone)."""
     if seconds <= 0:
@@ -195,22 +240,41 @@ def python_reference_leg(seconds):
         return {"unavailable": "baseline/_ref not present (build() copies it from /root/reference when that exists)"}
     cores = os.cpu_count() or 1
     try:
-        s1, g1, w1, _ = _run_pyref_workers(1, min(5.0, seconds))
-        s, g, w, crashed = _run_pyref_workers(cores, seconds)
+        s1, g1, w1, _ = _run_pyref_workers(1, min(5.0, seconds), kind)
+        s, g, w, crashed = _run_pyref_workers(cores, seconds, kind)
     except Exception as e:            # never let the reported baseline take the GPU numbers down
         return {"unavailable": "python reference leg failed: %s" % e}
     return {"value": s / w, "unit": UNIT, "games_per_sec": g / w, "cores": cores, "cpu_model": cpu_model_name(),
             "kind": "reference", "single_core_value": s1 / w1, "single_core_games_per_sec": g1 / w1,
             "env_steps": s, "games": g, "wall_s": w, "episodes_crashed": crashed,
-            "sample": "unmodified azulnet GameRunner (default rules: random first player, Lid pool), RandomAgent on both "
-                      "seats, %d single-threaded processes x %.0f s wall after warm-up; %d games, %d env steps "
-                      "(BASELINE.json configs[0])" % (cores, w, g, s)}
+            "sample": "%s; %d single-threaded processes x %.0f s wall after warm-up; %d games, %d env steps" % (
+                PYREF_WHAT[kind], cores, w, g, s)}
+
+
+def run_reference_python(args, kind):
+    """--impl reference for the modes whose path includes the MLP (policy, train): there is no C port of those; the arm is
+    the unmodified Python reference itself on all host cores."""
+    py = python_reference_leg(max(args.pyref_seconds, 5.0), kind)
+    cfg = workload_config(args, args.gpus)
+    cfg["workload"] = PYREF_WHAT[kind]
+    cfg.pop("env_steps_per_game_per_launch", None)
+    if py is None or "unavailable" in py:
+        print(json.dumps({"impl": "reference", "unavailable": (py or {}).get("unavailable", "python reference leg disabled")}))
+        return
+    line = {"impl": "reference", "metric": METRIC, "value": py["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * py["wall_s"] / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (torch CPU) / python int", "data": "synthetic", "config": cfg,
+            "cpu_baseline": dict(py), "games_per_sec": py["games_per_sec"],
+            "e2e": {"value": py["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                                   # rank 0 alone runs the CPU arm
+    if args.mode in ("policy", "train"):
+        return run_reference_python(args, "selfplay" if args.mode == "policy" else "train")
     threads = os.cpu_count() or 1
     pool = 1 if args.pool == "lid" else 0
     from oracle import oracle as O
@@ -737,6 +801,11 @@ def run_b200(args):
             py = python_reference_leg(args.pyref_seconds)
             if py is not None:
                 line["cpu_baseline"]["python_reference"] = py
+            if "extra" in line and args.pyref_seconds > 0:
+                # the same reference, on the paths of configs[3] / configs[4] (shorter legs: the rate settles within seconds)
+                short = min(args.pyref_seconds, 10.0)
+                line["extra"]["policy"]["cpu_python_reference"] = python_reference_leg(short, "selfplay")
+                line["extra"]["train"]["cpu_python_reference"] = python_reference_leg(short, "train")
         print(json.dumps(line))
     ctx.close()
 
@@ -744,7 +813,7 @@ def run_b200(args):
 def main():
     args = parse_args()
     if args.pyref_worker is not None:
-        return pyref_worker(args.pyref_worker)
+        return pyref_worker(args.pyref_worker, args.pyref_kind)
     if not args.games:
         args.games = {"policy": 131072, "train": 16384, "step": 1 << 22, "config3": 262144}.get(args.mode, 65536)
     if args.impl == "reference":
