@@ -15,6 +15,8 @@ SYMBOLS = [
     "azb_opponent_random", "azb_policy_packed_bytes", "azb_policy_pack_weights", "azb_policy_step",
     "azb_observe_bf16", "azb_a2c_loss_grad", "azb_policy_rollout", "azb_discounted_returns",
     "azb_update_workspace_bytes", "azb_a2c_update_gradients",
+    "azb_v_state_words", "azb_v_record_size", "azb_v_n_actions", "azb_v_reset", "azb_v_legal_mask", "azb_v_step",
+    "azb_v_rollout_random", "azb_v_import_state", "azb_v_export_state",
 ]
 
 
@@ -66,6 +68,15 @@ def load():
     L.azb_update_workspace_bytes.argtypes = [i64]
     L.azb_update_workspace_bytes.restype = i64
     L.azb_a2c_update_gradients.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, f32, f32, f32] + [vp] * 13
+    L.azb_v_state_words.argtypes = [i32, i32]
+    L.azb_v_record_size.argtypes = [i32, i32]
+    L.azb_v_n_actions.argtypes = [i32]
+    L.azb_v_reset.argtypes = [vp, i32, vp, vp, vp]
+    L.azb_v_legal_mask.argtypes = [vp, i32, vp, vp, vp]
+    L.azb_v_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.azb_v_rollout_random.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.azb_v_import_state.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.azb_v_export_state.argtypes = [vp, i32, vp, vp, vp]
     if L.azb_abi_version() != ABI_VERSION:
         raise AzbError("libazb.so ABI %d != binding ABI %d: rebuild" % (L.azb_abi_version(), ABI_VERSION))
     _lib = L

@@ -118,6 +118,7 @@ struct Game {
     uint32_t pat[P], wall[P], scf[P], sta[P], stb[P];
 
     static constexpr int WORDS = 7 + 5 * P;
+    static constexpr int PLAYERS = P;
 
     AZB_M void load(const uint32_t* __restrict__ s, int64_t stride, int64_t g)
     {
@@ -242,12 +243,12 @@ AZB_HD void apply_move(Game<P>& g, uint32_t action)
     if (POOL == POOL_LID) g.lid += to_floor << (6u * c);              // azul.py:156-157,160-161
 }
 
-// azul.py:177-181
-template <int P>
-AZB_HD void next_player(Game<P>& g)
+// azul.py:177-181 (GT: Game<P>, or the factory-count variant's GameV<P,F>, which shares the per-player words)
+template <class GT>
+AZB_HD void next_player(GT& g)
 {
     const uint32_t c = g.current_player();
-    g.set_current_player(c < (uint32_t)P ? c + 1u : 1u);
+    g.set_current_player(c < (uint32_t)GT::PLAYERS ? c + 1u : 1u);
 }
 
 // azul.py:182-183 -- every display and all six centre slots (token included) are empty
@@ -258,12 +259,12 @@ AZB_HD bool is_end_of_round(const Game<P>& g)
 }
 
 // azul.py:184-191 -- some wall row of some player holds all five colours
-template <int P>
-AZB_HD bool is_end_of_game(const Game<P>& g)
+template <class GT>
+AZB_HD bool is_end_of_game(const GT& g)
 {
     uint32_t any = 0;
 #pragma unroll
-    for (int p = 0; p < P; p++) {
+    for (int p = 0; p < GT::PLAYERS; p++) {
         const uint32_t w = g.wall[p];
         uint32_t t = w & (w >> 1);
         t &= t >> 2;
@@ -276,8 +277,8 @@ AZB_HD bool is_end_of_game(const Game<P>& g)
 // ---- count_score (azul.py:192-295) for one player ----
 // Adjacency runs on a column-space copy of the wall (column = (colour + row) mod 5,
 // azul.py:194-196) with ctz/clz run-length counts instead of the reference's four walks.
-template <int P, int POOL>
-AZB_HD void score_player(Game<P>& g, const int pl)
+template <int POOL, class GT>
+AZB_HD void score_player_g(GT& g, const int pl)
 {
     uint32_t scf = g.scf[pl], pat = g.pat[pl], wall = g.wall[pl], sta = g.sta[pl], stb = g.stb[pl];
     // count_floor, azul.py:200-210: 0,-1,-2,-4,-6,-8,-11,-14
@@ -334,11 +335,16 @@ AZB_HD void score_player(Game<P>& g, const int pl)
 }
 
 template <int P, int POOL>
-AZB_HD void count_score(Game<P>& g)
+AZB_HD void score_player(Game<P>& g, const int pl) { score_player_g<POOL>(g, pl); }
+
+template <int POOL, class GT>
+AZB_HD void count_score_g(GT& g)
 {
 #pragma unroll
-    for (int p = 0; p < P; p++) score_player<P, POOL>(g, p);
+    for (int p = 0; p < GT::PLAYERS; p++) score_player_g<POOL>(g, p);
 }
+template <int P, int POOL>
+AZB_HD void count_score(Game<P>& g) { count_score_g<POOL>(g); }
 
 // one more tile of colour c on source position b = d + 6c: bit-sliced increment
 AZB_HD void plane_inc(uint32_t& pl0, uint32_t& pl1, uint32_t& pl2, uint32_t b)
@@ -378,8 +384,8 @@ struct BoxRegs {
 
 // Lid pool, one draw (azul.py:79-89): pour the lid into an empty box, pick colour c when the
 // point r in [0,total) falls in its cumulative count.  Returns colour or -1 when no tile is left.
-template <int P>
-AZB_HD int lid_draw(Game<P>& g, BoxRegs& B, uint32_t& x)
+template <class GT>
+AZB_HD int lid_draw(GT& g, BoxRegs& B, uint32_t& x)
 {
     if (B.total == 0u) {                                          // :81-83
         B.unpack(g.lid);
@@ -683,13 +689,13 @@ AZB_HD void export_record(const Game<P>& g, Wr wr)
 // 15 sum of all seats' scores.  Sink::add(index, value) receives the increments.
 // `fin` selects the games of the calling group that just ended; Sink::add_group may aggregate the
 // increments of all calling lanes (the kernels reduce them with one REDUX per counter and warp).
-template <int P, typename Sink>
-AZB_HD void tally_finished(const Game<P>& g, Sink& sink, bool fin = true)
+template <class GT, typename Sink>
+AZB_HD void tally_finished(const GT& g, Sink& sink, bool fin = true)
 {
     const uint32_t s0 = g.scf[0] & 0xFFFFu, s1 = g.scf[1] & 0xFFFFu, f = fin ? 1u : 0u;
     uint32_t all = 0;
 #pragma unroll
-    for (int p = 0; p < P; p++) all += g.scf[p] & 0xFFFFu;
+    for (int p = 0; p < GT::PLAYERS; p++) all += g.scf[p] & 0xFFFFu;
     sink.add_group(1, f);
     sink.add_group(3, f * s0);
     sink.add_group(4, f * s1);

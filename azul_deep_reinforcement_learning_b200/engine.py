@@ -284,6 +284,85 @@ class BatchedAzul:
         return out
 
 
+class BatchedAzulByPlayers:
+    """``n_games`` games under the opt-in rule "factory count by player count" (the reference's
+    azul.py:72 TODO): ``factories`` = 2 * players + 1 displays (7 / 9 for 3 / 4 players; ``factories=5`` runs the reference's
+    rule through the same kernels), 30 * (factories + 1) actions, legal mask = int64 ``[6, n_games]`` (word p bit
+    d + S*c, S = factories + 1), actions uint16 (0xFFFF = skip).  The default engine (:class:`BatchedAzul`) is untouched."""
+
+    def __init__(self, n_games, players, tile_pool=TILE_POOL_RANDOM, first_player=1, seed=0, device=0, game_id_base=0,
+                 factories=None, reset=True):
+        if not torch.cuda.is_available():
+            raise _lib.AzbError("no CUDA device: the engine has no CPU path")
+        self.lib = _lib.load()
+        self.factories = int(2 * players + 1 if factories is None else factories)
+        self.n_games, self.players, self.tile_pool, self.first_player = int(n_games), players, tile_pool, first_player
+        self.seed, self.game_id_base = int(seed), int(game_id_base)
+        self.device = torch.device("cuda", device)
+        self.W = _lib.check(self.lib.azb_v_state_words(players, self.factories))
+        self.U = _lib.check(self.lib.azb_v_record_size(players, self.factories))
+        self.n_actions = self.lib.azb_v_n_actions(self.factories)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.azb_create(ctypes.byref(h), device, self.n_games, players, tile_pool, first_player,
+                                      self.seed & (2 ** 64 - 1), self.game_id_base))
+        self._h = h
+        self.state = torch.zeros((self.W, self.n_games), dtype=torch.int32, device=self.device)
+        self.counters = torch.zeros(N_COUNTERS, dtype=torch.int64, device=self.device)
+        if reset:
+            self.reset()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.lib.azb_destroy(h)
+            self._h = None
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, which=None):
+        if which is not None:
+            which = which.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.azb_v_reset(self._h, self.factories, _ptr(self.state), _ptr(which), self._stream()))
+
+    def legal_mask(self):
+        out = torch.empty((MASK_WORDS, self.n_games), dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.azb_v_legal_mask(self._h, self.factories, _ptr(self.state), _ptr(out), self._stream()))
+        return out
+
+    def step(self, action, draws=None):
+        """One ``Azul.step`` per game (action int16 / uint16 tensor, 0xFFFF = skip).  Returns dict(mask, done, status)."""
+        action = action.to(device=self.device).to(torch.int32).to(torch.uint16 if hasattr(torch, "uint16") else torch.int16).contiguous()
+        if draws is not None:
+            draws = draws.to(device=self.device, dtype=torch.int8).contiguous()
+            assert draws.numel() == 4 * self.factories * self.n_games
+        mask = torch.empty((MASK_WORDS, self.n_games), dtype=torch.int64, device=self.device)
+        done = torch.empty(self.n_games, dtype=torch.uint8, device=self.device)
+        status = torch.empty(self.n_games, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.azb_v_step(self._h, self.factories, _ptr(self.state), _ptr(action), _ptr(draws), _ptr(mask),
+                                      _ptr(done), _ptr(status), self._stream()))
+        return {"mask": mask, "done": done, "status": status}
+
+    def rollout_random(self, k_steps):
+        _lib.check(self.lib.azb_v_rollout_random(self._h, self.factories, _ptr(self.state), int(k_steps), _ptr(self.counters),
+                                                self._stream()))
+
+    def import_records(self, records):
+        rec = torch.as_tensor(np.ascontiguousarray(records, dtype=np.int32)).to(self.device)
+        assert rec.shape == (self.n_games, self.U), rec.shape
+        ok = torch.empty(self.n_games, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.azb_v_import_state(self._h, self.factories, _ptr(rec), _ptr(self.state), _ptr(ok), self._stream()))
+        return ok
+
+    def export_records(self):
+        rec = torch.empty((self.n_games, self.U), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.azb_v_export_state(self._h, self.factories, _ptr(self.state), _ptr(rec), self._stream()))
+        return rec
+
+    def read_counters(self):
+        return dict(zip(COUNTER_NAMES, (int(x) for x in self.counters.cpu().numpy())))
+
+
 class PackedPolicy:
     """The ``ActorCritic`` parameters (model.py:17-21) in the fp16 shared-memory image of the policy kernel."""
 

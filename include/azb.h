@@ -243,6 +243,26 @@ int azb_a2c_update_gradients(azb_t* h, const uint32_t* state_rec, int64_t capaci
                              float* grad_b2a, float* grad_w1c, float* grad_b1c, float* grad_w2c, float* grad_b2c, double* sums,
                              float* logits_out, float* value_out, void* stream);
 
+/* ---- opt-in rule variant: factory count by player count (the reference's azul.py:72 TODO) --------
+ * The reference always builds five factory displays (azul.py:19).  With `factories` = 2 * players + 1 (7 for three
+ * players, 9 for four, as in the board game) a round draws 4 * factories tiles and the action space grows to
+ * 30 * (factories + 1) = 240 / 300: action a = d + S*c + 5*S*p with S = factories + 1 sources (game_runner.py:102-103 with
+ * 6 -> S), legal mask = six 64-bit words (word p bit d + S*c), actions are uint16 (0xFFFF = skip), draws int8
+ * [G][4 * factories], records int32 [G][azb_v_record_size] (the default record with `factories` display rows in front),
+ * state uint32 [azb_v_state_words][G].  The handle comes from azb_create; `factories` = 5 runs the reference's rule
+ * through the same code (it reproduces the default engine bit for bit: tests).  Everything else -- scoring, floor, lid,
+ * Philox schedule (display i draws from word i resp. words 2i, 2i + 1), status bits, counters -- is as in the default path. */
+int azb_v_state_words(int players, int factories);
+int azb_v_record_size(int players, int factories);
+int azb_v_n_actions(int factories);
+int azb_v_reset(azb_t* h, int factories, uint32_t* state, const uint8_t* which, void* stream);
+int azb_v_legal_mask(azb_t* h, int factories, const uint32_t* state, uint64_t* mask6, void* stream);
+int azb_v_step(azb_t* h, int factories, uint32_t* state, const uint16_t* action, const int8_t* draws, uint64_t* mask6_out,
+               uint8_t* done_out, uint8_t* status_out, void* stream);
+int azb_v_rollout_random(azb_t* h, int factories, uint32_t* state, int k_steps, unsigned long long* counters, void* stream);
+int azb_v_import_state(azb_t* h, int factories, const int32_t* records, uint32_t* state, uint8_t* ok_out, void* stream);
+int azb_v_export_state(azb_t* h, int factories, const uint32_t* state, int32_t* records, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

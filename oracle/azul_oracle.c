@@ -24,9 +24,18 @@
 #include <pthread.h>
 
 #define MAXP 4
+#define MAXF 9
+
+/* Number of factory displays.  The reference always uses 5 (azul.py:19, tests/test_azul.py:13-15; its azul.py:72 is a
+ * TODO); the opt-in variant of the engine ("factory count by player count", SURVEY §8f rank 4: 5 / 7 / 9 displays for
+ * 2 / 3 / 4 players as in the board game) is checked against this same file with g_F set through ao_set_factories().
+ * With g_F = 5 every function below is the reference-pinned default.  Process-global: test infrastructure only. */
+static int g_F = 5;
+void ao_set_factories(int f) { g_F = (f == 7 || f == 9) ? f : 5; }
+int ao_get_factories(void) { return g_F; }
 
 typedef struct {
-    int32_t displays[5][5];          /* azul.py:19 */
+    int32_t displays[MAXF][5];       /* azul.py:19 */
     int32_t center[6];               /* azul.py:20 */
     int32_t pattern_lines[MAXP][5][5];/* azul.py:21-22 */
     int32_t walls[MAXP][5][5];       /* azul.py:23-24, indexed [row][COLOUR] */
@@ -52,13 +61,13 @@ enum { PURPOSE_ACTION = 0, PURPOSE_REFILL = 1, PURPOSE_FIRST = 2, PURPOSE_RESET_
 
 /* ------------------------------------------------------------------ record <-> struct ---- */
 
-int ao_record_size(int players) { return 48 + 58 * players; }
+int ao_record_size(int players) { return 48 + 58 * players + 5 * (g_F - 5); }
 
 static void from_record(ao_game *g, const int32_t *r, int P)
 {
     memset(g, 0, sizeof(*g));
     const int32_t *p = r;
-    memcpy(g->displays, p, 25 * 4); p += 25;
+    memcpy(g->displays, p, 5 * g_F * 4); p += 5 * g_F;
     memcpy(g->center, p, 6 * 4); p += 6;
     for (int i = 0; i < P; i++) { memcpy(g->pattern_lines[i], p, 25 * 4); p += 25; }
     for (int i = 0; i < P; i++) { memcpy(g->walls[i], p, 25 * 4); p += 25; }
@@ -80,7 +89,7 @@ static void from_record(ao_game *g, const int32_t *r, int P)
 static void to_record(const ao_game *g, int32_t *r, int P)
 {
     int32_t *p = r;
-    memcpy(p, g->displays, 25 * 4); p += 25;
+    memcpy(p, g->displays, 5 * g_F * 4); p += 5 * g_F;
     memcpy(p, g->center, 6 * 4); p += 6;
     for (int i = 0; i < P; i++) { memcpy(p, g->pattern_lines[i], 25 * 4); p += 25; }
     for (int i = 0; i < P; i++) { memcpy(p, g->walls[i], 25 * 4); p += 25; }
@@ -156,7 +165,7 @@ static void new_round_injected(ao_game *g, int pool, const int8_t *draws)
     for (int c = 0; c < 5; c++) g->center[c] = 0;                      /* :71 */
     g->center[5] = 1;
     memset(g->displays, 0, sizeof(g->displays));                       /* :73 */
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < g_F; i++)
         for (int j = 0; j < 4; j++) {
             int c = draws[i * 4 + j];
             if (c < 0) continue;                                       /* spec: slot left empty */
@@ -181,12 +190,12 @@ static void new_round_injected(ao_game *g, int pool, const int8_t *draws)
  * counts, azul.py:85-89), lid poured into the box when the box is empty (azul.py:81-83). */
 static void new_round_philox(ao_game *g, int pool, uint64_t seed, uint32_t gid, uint32_t purpose)
 {
-    uint32_t R[12];
-    int calls = pool == POOL_LID ? 3 : 2;
+    uint32_t R[20];
+    int calls = pool == POOL_LID ? (2 * g_F + 3) / 4 : (g_F + 3) / 4;       /* 3 / 2 calls for the reference's 5 displays */
     for (int j = 0; j < calls; j++) draw_words(seed, gid, g->total_steps, purpose, (uint32_t)j, R + 4 * j);
-    int8_t draws[20];
+    int8_t draws[4 * MAXF];
     if (pool == POOL_RANDOM) {
-        for (int i = 0; i < 5; i++) {
+        for (int i = 0; i < g_F; i++) {
             uint32_t x = R[i];
             for (int j = 0; j < 4; j++) { draws[i * 4 + j] = (int8_t)mulhi32(x, 5); x *= 5u; }
         }
@@ -196,7 +205,7 @@ static void new_round_philox(ao_game *g, int pool, uint64_t seed, uint32_t gid, 
     /* Lid: the colour depends on the evolving box, so interleave with the bookkeeping */
     int32_t box[5], lid[5];
     memcpy(box, g->box, sizeof(box)); memcpy(lid, g->lid, sizeof(lid));
-    for (int i = 0; i < 5; i++) {
+    for (int i = 0; i < g_F; i++) {
         uint32_t x = 0;
         for (int j = 0; j < 4; j++) {
             if ((j & 1) == 0) x = R[2 * i + (j >> 1)];
@@ -280,7 +289,7 @@ static void next_player(ao_game *g)
 /* azul.py:182-183 -- all six centre slots count, token included */
 static int is_end_of_round(const ao_game *g)
 {
-    for (int i = 0; i < 5; i++) for (int c = 0; c < 5; c++) if (g->displays[i][c]) return 0;
+    for (int i = 0; i < g_F; i++) for (int c = 0; c < 5; c++) if (g->displays[i][c]) return 0;
     for (int c = 0; c < 6; c++) if (g->center[c]) return 0;
     return 1;
 }
@@ -372,14 +381,22 @@ static void count_score(ao_game *g, int pool)
     }
 }
 
-/* game_runner.py:113-117 with index = d + 6c + 30p (game_runner.py:102-103) -> six 30-bit words */
+/* game_runner.py:113-117 with index = d + S*c + 5*S*p, S = displays + 1 sources (game_runner.py:102-103: S = 6) ->
+ * six words of 5*S bits, word p bit (d + S*c) */
+static void legal_mask64(const ao_game *g, uint64_t mask[6])
+{
+    const int S = g_F + 1;
+    for (int p = 0; p < 6; p++) mask[p] = 0;
+    for (int i = 0; i < 30 * S; i++) {
+        int d = i % S, c = (i / S) % 5, p = i / (5 * S);                                /* :107-111 */
+        if (is_legal_move(g, d, c, p)) mask[p] |= 1ull << (d + S * c);
+    }
+}
 static void legal_mask(const ao_game *g, uint32_t mask[6])
 {
-    for (int p = 0; p < 6; p++) mask[p] = 0;
-    for (int i = 0; i < 180; i++) {
-        int d = i % 6, c = (i / 6) % 5, p = i / 30;                                     /* :107-111 */
-        if (is_legal_move(g, d, c, p)) mask[p] |= 1u << (d + 6 * c);
-    }
+    uint64_t m[6];
+    legal_mask64(g, m);
+    for (int p = 0; p < 6; p++) mask[p] = (uint32_t)m[p];
 }
 
 /* azul.py:296-313.  draws == NULL -> Philox schedule.  Returns 0, or -1 IllegalMove / -2 GameEnded
@@ -387,7 +404,7 @@ static void legal_mask(const ao_game *g, uint32_t mask[6])
 static int step(ao_game *g, int pool, int d, int c, int p, const int8_t *draws, uint64_t seed, uint32_t gid)
 {
     if (g->end_of_game) return -2;
-    if (d < 0 || d > 5 || c < 0 || c > 4 || p < 0 || p > 5) return -1;
+    if (d < 0 || d > g_F || c < 0 || c > 4 || p < 0 || p > 5) return -1;
     if (!is_legal_move(g, d, c, p)) return -1;
     move(g, pool, d, c, p);
     g->total_steps += 1;
@@ -420,11 +437,12 @@ static void reset_philox(ao_game *g, int P, int pool, int first_rule, uint64_t s
  * except the 30 straight-to-floor ones (p = 0) which get 0.01 -> integer weights 100 : 1.
  * r = mulhi(word, total) picks a point in the cumulative weight; heavy actions (words 1..5 in
  * ascending action index) come first, then the floor actions of word 0. */
-static int random_action(const uint32_t mask[6], uint32_t word)
+static int random_action64(const uint64_t mask[6], uint32_t word)
 {
+    const int S = g_F + 1;
     int n_hi = 0;
-    for (int p = 1; p < 6; p++) n_hi += __builtin_popcount(mask[p]);
-    int n_lo = __builtin_popcount(mask[0]);
+    for (int p = 1; p < 6; p++) n_hi += __builtin_popcountll(mask[p]);
+    int n_lo = __builtin_popcountll(mask[0]);
     uint32_t total = 100u * (uint32_t)n_hi + (uint32_t)n_lo;
     if (total == 0) return -1;
     uint32_t r = mulhi32(word, total);
@@ -432,9 +450,15 @@ static int random_action(const uint32_t mask[6], uint32_t word)
     if (r < 100u * (uint32_t)n_hi) { k = (int)(r / 100u); p0 = 1; p1 = 6; }
     else { k = (int)(r - 100u * (uint32_t)n_hi); p0 = 0; p1 = 1; }
     for (int p = p0; p < p1; p++)
-        for (int b = 0; b < 30; b++)
-            if (mask[p] >> b & 1) { if (k == 0) return 30 * p + b; k--; }
+        for (int b = 0; b < 5 * S; b++)
+            if (mask[p] >> b & 1) { if (k == 0) return 5 * S * p + b; k--; }
     return -1;
+}
+static int random_action(const uint32_t mask[6], uint32_t word)
+{
+    uint64_t m[6];
+    for (int p = 0; p < 6; p++) m[p] = mask[p];
+    return random_action64(m, word);
 }
 
 /* ------------------------------------------------------------------ exported entry points - */
@@ -513,12 +537,20 @@ void ao_legal_mask(const int32_t *rec, int players, uint32_t *mask6)
     legal_mask(&g, mask6);
 }
 
+/* the same with 64-bit words: needed for 7 / 9 displays (40 / 50 bits per word) */
+void ao_legal_mask64(const int32_t *rec, int players, uint64_t *mask6)
+{
+    ao_game g; from_record(&g, rec, players);
+    legal_mask64(&g, mask6);
+}
+
 int ao_step(int32_t *rec, int players, int pool, int action, const int8_t *draws, uint64_t seed, uint32_t gid)
 {
     ao_game g; from_record(&g, rec, players);
     int rc;
-    if (action < 0 || action >= 180) rc = g.end_of_game ? -2 : -1;
-    else rc = step(&g, pool, action % 6, (action / 6) % 5, action / 30, draws, seed, gid);
+    const int S = g_F + 1;
+    if (action < 0 || action >= 30 * S) rc = g.end_of_game ? -2 : -1;
+    else rc = step(&g, pool, action % S, (action / S) % 5, action / (5 * S), draws, seed, gid);
     if (rc == 0) to_record(&g, rec, players);
     return rc;
 }
@@ -608,20 +640,21 @@ void ao_statistics(const int32_t *rec, int players, int32_t *out)
 static void rollout_one(ao_game *g, int P, int pool, int first_rule, uint64_t seed, uint32_t gid,
                         int k_steps, int64_t *cnt)
 {
+    const int S = g_F + 1;
     for (int i = 0; i < k_steps; i++) {
-        uint32_t mask[6];
+        uint64_t mask[6];
         if (g->end_of_game) { reset_philox(g, P, pool, first_rule, seed, gid); cnt[2]++; }
-        legal_mask(g, mask);
+        legal_mask64(g, mask);
         if ((mask[0] | mask[1] | mask[2] | mask[3] | mask[4] | mask[5]) == 0) {
             cnt[6]++;
             reset_philox(g, P, pool, first_rule, seed, gid); cnt[2]++;
-            legal_mask(g, mask);
+            legal_mask64(g, mask);
         }
         uint32_t w[4];
         draw_words(seed, gid, g->total_steps >> 2, PURPOSE_ACTION, 0, w);
-        int a = random_action(mask, w[g->total_steps & 3]);
+        int a = random_action64(mask, w[g->total_steps & 3]);
         int turn_before = g->turn_counter, bag_before = g->status & ST_BAG_EMPTY;
-        step(g, pool, a % 6, (a / 6) % 5, a / 30, NULL, seed, gid);
+        step(g, pool, a % S, (a / S) % 5, a / (5 * S), NULL, seed, gid);
         cnt[0]++;
         if (g->turn_counter != turn_before) cnt[2]++;
         if (!bag_before && (g->status & ST_BAG_EMPTY)) cnt[7]++;

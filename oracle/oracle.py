@@ -48,6 +48,8 @@ def lib():
         L.ao_random_action.argtypes = [u32p, U32]
         L.ao_opponent_random.argtypes = [i32p, I, I, U64, U32, I, u32p]
         L.ao_philox4x32_10.argtypes = [u32p, u32p, u32p]
+        L.ao_set_factories.argtypes = [I]
+        L.ao_legal_mask64.argtypes = [i32p, I, ctypes.POINTER(ctypes.c_uint64)]
         L.ao_observe.argtypes = [i32p, I, I, i32p]
         L.ao_runner_continues.argtypes = [i32p, I, I]
         L.ao_statistics.argtypes = [i32p, I, i32p]
@@ -55,7 +57,7 @@ def lib():
         L.ao_rollout_random_mt.argtypes = [i32p, ctypes.c_int64, I, I, I, U64, U32, I, i64p, I]
         for f in ("ao_init", "ao_new_round", "ao_reset_philox", "ao_move", "ao_next_player", "ao_count_score",
                   "ao_score_preview", "ao_legal_mask", "ao_philox4x32_10", "ao_rollout_random",
-                  "ao_rollout_random_mt", "ao_observe", "ao_statistics"):
+                  "ao_rollout_random_mt", "ao_observe", "ao_statistics", "ao_set_factories", "ao_legal_mask64"):
             getattr(L, f).restype = None
         _lib = L
     return _lib
@@ -132,6 +134,27 @@ class Game:
         dd = _draws(draws)
         return lib().ao_step(_rec(self.rec), self.players, self.tile_pool, int(action),
                              dd[1] if dd else None, seed, gid)
+
+
+class factories:
+    """``with factories(7): ...`` -- run the oracle with 7 / 9 factory displays (the opt-in "factory count by player
+    count" variant); the reference itself always uses 5 (azul.py:19), which is restored on exit."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def __enter__(self):
+        lib().ao_set_factories(self.f)
+        return self
+
+    def __exit__(self, *a):
+        lib().ao_set_factories(5)
+
+
+def legal_mask64(rec, players):
+    m = np.zeros(6, dtype=np.uint64)
+    lib().ao_legal_mask64(_rec(np.ascontiguousarray(rec, dtype=np.int32)), players, _p(m, ctypes.c_uint64))
+    return m
 
 
 def observe(rec, players, perspective=0):

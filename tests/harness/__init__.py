@@ -68,3 +68,45 @@ def opponent(rec, players, pool, seed, gid, require_two=True):
     rc = lib().hh_opponent(rec.ctypes.data, players, pool, seed, gid, int(require_two), mask.ctypes.data, diff.ctypes.data)
     assert rc == 0
     return int(diff[0]), mask
+
+
+# ---- the "factory count by player count" variant (csrc/azb_variant.cuh) ------------------------------------------
+_VSO = os.path.join(_HERE, "_build", "libvariant_host.so")
+_VHDR = os.path.join(os.path.dirname(_HDR), "azb_variant.cuh")
+_vlib = None
+
+
+def vlib():
+    global _vlib
+    if _vlib is None:
+        src = os.path.join(_HERE, "variant_host.cpp")
+        newest = max(os.path.getmtime(src), os.path.getmtime(_HDR), os.path.getmtime(_VHDR))
+        if not os.path.exists(_VSO) or os.path.getmtime(_VSO) < newest:
+            os.makedirs(os.path.dirname(_VSO), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _VSO, src])
+        L = ctypes.CDLL(_VSO)
+        L.vh_op.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                            ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+        L.vh_rollout.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+        L.vh_random_action.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]
+        _vlib = L
+    return _vlib
+
+
+V_OP_MASK, V_OP_STEP, V_OP_RESET, V_OP_ROUNDTRIP = 0, 1, 6, 100
+
+
+def v_op(rec, players, factories, pool, code, a=0, draws=None, seed=0, gid=0, first_rule=1):
+    assert rec.dtype == np.int32 and rec.flags.c_contiguous
+    d = None if draws is None else np.ascontiguousarray(draws, dtype=np.int8)
+    mask = np.zeros(6, np.uint64)
+    rc = vlib().vh_op(rec.ctypes.data, players, factories, pool, code, int(a), None if d is None else d.ctypes.data, seed, gid,
+                      first_rule, mask.ctypes.data)
+    return rc, mask
+
+
+def v_rollout(recs, players, factories, pool, first_rule, seed, gid0, k):
+    cnt = np.zeros(16, np.int64)
+    assert vlib().vh_rollout(recs.ctypes.data, recs.shape[0], players, factories, pool, first_rule, seed, gid0, k, cnt.ctypes.data) == 0
+    return cnt
