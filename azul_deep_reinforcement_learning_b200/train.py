@@ -125,7 +125,7 @@ class SelfPlayTrainer:
         torch.manual_seed(seed)                              # identical initial weights on every rank
         self.net = ActorCritic(136, 180).to(self.device)
         self.params = list(self.net.parameters())
-        self.opt = torch.optim.Adam(self.params, lr=learning_rate, fused=True)       # agent.py:37 (one fused kernel)
+        self.opt = torch.optim.Adam(self.params, lr=learning_rate, fused=True, capturable=True)   # agent.py:37 (one fused kernel; graph-capturable)
         self.runner = BatchedGameRunner(games_per_rank, rules=rules, seed=seed, device=device,
                                         game_id_base=parallel.shard(rank, games_per_rank), record_obs=True)
         self.packed = PackedPolicy(self.runner.engine, self.net)
@@ -147,6 +147,7 @@ class SelfPlayTrainer:
         self._host_stats = torch.zeros((2, STAT_FIELDS), dtype=torch.float64).pin_memory()
         self._pending = []                                   # (slot, event) of statistics on their way to the host
         self._slot = 0
+        self._graph = None
         self.history = []
 
     # ---- rollout ---------------------------------------------------------------------------
@@ -167,7 +168,8 @@ class SelfPlayTrainer:
     def load_parameters(self, state_dict):
         """Replace the network parameters (e.g. a checkpoint or a reference ``ac_net.state_dict()``); Adam restarts."""
         self.net.load_state_dict({k: v.to(self.device) for k, v in state_dict.items()})
-        self.opt = torch.optim.Adam(self.params, lr=self.opt.param_groups[0]["lr"], fused=True)
+        self.opt = torch.optim.Adam(self.params, lr=self.opt.param_groups[0]["lr"], fused=True, capturable=True)
+        self._graph = None
 
     # ---- gradients -------------------------------------------------------------------------
     def accumulate_gradients(self, obs, masks, action, qval, chunk=1 << 18):
@@ -220,7 +222,43 @@ class SelfPlayTrainer:
 
     # ---- update ----------------------------------------------------------------------------
     def update(self, batch, defer_stats=False):
-        """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch.
+        """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch (see :meth:`_update_device`);
+        then the statistics start their way to the host."""
+        self._push_stats(self._update_device(batch))
+        return None if defer_stats else self.fetch_stats()
+
+    def _push_stats(self, stats):
+        slot = self._slot
+        self._slot ^= 1
+        self._host_stats[slot].copy_(stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((slot, ev))
+
+    # ---- the whole batch as one CUDA graph ----------------------------------------------------
+    def enable_step_graph(self, warmup=2):
+        """Capture rollout + update (every launch of a batch, collectives and the fused Adam step included) in ONE CUDA
+        graph: a batch is then a single graph launch (the ~60 small launches of a batch otherwise leave the GPU idle for a
+        fifth of the step).  Only for the persistent rollout + tensor-core update (no host decision inside a batch)."""
+        assert self.rollout_kind == "persistent" and self.update_kind == "tensor"
+        for _ in range(warmup):
+            self.update(self.rollout())
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_stats = self._update_device(self.rollout())
+        return self
+
+    def step(self, defer_stats=False):
+        """One training batch: rollout + update (one graph launch when :meth:`enable_step_graph` was called)."""
+        if getattr(self, "_graph", None) is not None:
+            self._graph.replay()
+            self._push_stats(self._graph_stats)
+            return None if defer_stats else self.fetch_stats()
+        return self.update(self.rollout(), defer_stats)
+
+    def _update_device(self, batch):
+        """``Agent.update`` (agent.py:39-62) on every recorded agent decision of the batch; returns the device statistics.
 
         Gradients are accumulated as SUMS over the local decisions in the flat fp32 buffer; one fp32 all-reduce carries
         them and a tiny float64 one the decision count and the batch statistics; every rank then divides by the global
@@ -262,13 +300,7 @@ class SelfPlayTrainer:
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)                  # C2: 18 float64 counters
         self.tc.flat.mul_((1.0 / stats[0].clamp_min(1.0)).float())
         self.opt.step()
-        slot = self._slot
-        self._slot ^= 1
-        self._host_stats[slot].copy_(stats, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self._pending.append((slot, ev))
-        return None if defer_stats else self.fetch_stats()
+        return stats
 
     def fetch_stats(self):
         """Statistics of the oldest update whose numbers have not been read yet (waits for that copy only)."""
@@ -306,11 +338,12 @@ class SelfPlayTrainer:
             self.net.load_state_dict({k: v.to(self.device) for k, v in obj["ac_net"].items()})
             if "optimizer" in obj:
                 self.opt.load_state_dict(obj["optimizer"])
+            self._graph = None                               # a captured batch refers to the old optimiser state
             return int(obj.get("batch", 0))
         self.load_parameters(load_ac_net(path).state_dict())
         return 0
 
-    def train(self, batches=1000, net_name=None, log=print, start_batch=0, checkpoint_every=1000):
+    def train(self, batches=1000, net_name=None, log=print, start_batch=0, checkpoint_every=1000, graph=True):
         """Batches ``start_batch + 1 .. batches``.  With ``net_name``: one CSV row per batch in ``<net_name>.csv``
         (appended to when resuming) and ``<net_name>.pt`` every ``checkpoint_every`` batches and at the end.  The host
         never waits for the batch it just launched: a batch's statistics are read (and logged) while the next one runs."""
@@ -339,9 +372,12 @@ class SelfPlayTrainer:
                     b, st["games_per_sec"], st["reward"], st["player_score"], st["opponent_score"],
                     100 * st["win_percent"], st["ac_loss"]))
 
+        can_graph = graph and self.rollout_kind == "persistent" and self.update_kind == "tensor"
         for b in range(start_batch, batches):
+            if can_graph and self._graph is None and b >= start_batch + 2:
+                self.enable_step_graph(warmup=0)             # the first two batches ran launch by launch (lazy initialisation)
             t0 = time.perf_counter()
-            self.update(self.rollout(), defer_stats=True)
+            self.step(defer_stats=True)
             marks.append((b + 1, t0))
             if len(marks) > 1:                               # the previous batch's numbers are on the host by now
                 finish(*marks.pop(0))

@@ -71,6 +71,7 @@ def parse_args():
     ap.add_argument("--presteps", type=int, default=203,
                     help="--mode step: random-agent env steps before the timed step (0 = fresh games: no round can end)")
     ap.add_argument("--policy-k", type=int, default=64, help="policy: decisions per game per launch of the persistent self-play kernel")
+    ap.add_argument("--no-graph", action="store_true", help="train: run the batch launch by launch instead of as one CUDA graph")
     ap.add_argument("--pyref-worker", type=float, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--pyref-kind", default="runner", choices=["runner", "selfplay", "train"], help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -695,55 +696,67 @@ def measure_policy(args, ctx, games, steps, warmup):
 
 def measure_train(args, ctx, games, steps, warmup):
     """BASELINE.json configs[4]: the scripts/training.py-equivalent loop -- GPU self-play rollouts of `games` episodes
-    per rank against the random opponent + one A2C update with a flat NCCL gradient all-reduce per bench step."""
+    per rank against the random opponent + one A2C update with a flat NCCL gradient all-reduce per bench step.  The
+    timed region runs the product's training step (SelfPlayTrainer.step: the whole batch as one CUDA graph); a few
+    launch-by-launch batches before it give the rollout / update split."""
     torch = ctx.torch
     from azul_deep_reinforcement_learning_b200.train import SelfPlayTrainer
     tr = SelfPlayTrainer(games, seed=args.seed & 0x7FFFFFFF, device=ctx.local, rank=ctx.rank, world=ctx.world)
     steps_word = lambda: int(tr.runner.engine.state[6].to(torch.int64).sum())   # noqa: E731  env steps executed so far
     for _ in range(warmup):
         tr.update(tr.rollout())
-    ctx.barrier()
-    sampler = ctx.clocks()
-    if ctx.rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env_steps, n_games, trans, upd_ms, roll_ms, sync_ms = 0, 0, 0.0, [], [], []
-    ctx.barrier()
-    ev0.record()
-    for _ in range(steps):
+    upd_ms, roll_ms, sync_ms, trans = [], [], [], 0.0
+    for _ in range(3):                               # launch by launch, synchronised: where the time goes
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        s0 = steps_word()
         batch = tr.rollout()
-        env_steps += steps_word() - s0           # (rollout resets keep the per-slot step counters running)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         st = tr.update(batch)
         torch.cuda.synchronize()
         upd_ms.append(1e3 * (time.perf_counter() - t1)); roll_ms.append(1e3 * (t1 - t0))
-        sync_ms.append(1e3 * st.get("update_sync_s", 0.0))
-        n_games += games; trans = st["transitions"]
+        sync_ms.append(1e3 * st.get("update_sync_s", 0.0)); trans = st["transitions"]
+    graph = not args.no_graph
+    if graph:
+        tr.enable_step_graph(warmup=1)
+    ctx.barrier()
+    sampler = ctx.clocks()
+    if ctx.rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0 = steps_word()
+    ctx.barrier()
+    ev0.record()
+    for _ in range(steps):
+        tr.step(defer_stats=True)
     ev1.record()
     ctx.barrier()
     clocks = sampler.stop() if ctx.rank == 0 else None
+    last = None
+    for _ in range(steps):
+        last = tr.fetch_stats()                      # every batch's statistics reached the host
+    env_steps, n_games = steps_word() - s0, games * steps
     dev_ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
     tot = torch.tensor([float(env_steps), float(n_games)], dtype=torch.float64, device=ctx.dev)
     ctx.parallel.reduce_counters(tot)
     cfg = workload_config(args, ctx.world, games=games, players=2)
     cfg["workload"] = ("self-play A2C training: %d episodes per GPU per batch vs the random opponent (persistent fused policy "
-                       "kernel rollouts), discounted returns, Agent.update loss, Adam, flat NCCL gradient all-reduce "
-                       "(BASELINE.json configs[4])" % games)
+                       "kernel rollouts), discounted returns, Agent.update loss and gradients on the tensor cores, fused Adam, flat "
+                       "NCCL gradient all-reduce; %s (BASELINE.json configs[4])" % (
+                           games, "one CUDA graph per batch" if graph else "launch by launch"))
     cfg.pop("env_steps_per_game_per_launch", None)
     cfg["l2"] = "n/a (multi-kernel training step; working set is re-generated every batch)"
     value = float(tot[0]) / (dev_ms * 1e-3)
-    return {"value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms / steps,
+    return {"value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": steps, "warmup": warmup + 3, "ms_per_step": dev_ms / steps,
             "dtype": "fp16-operand tensor-core MLP (rollout and update), fp32 accumulation / u32 rules", "config": cfg,
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 32,
-                    "note": "a training batch is end to end by construction: statistics are read back to the host every batch"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 18,
+                    "note": "a training batch is end to end by construction: its statistics are copied to pinned host memory every batch"},
             "gpu_launches": None, "clocks": clocks,
             "games_per_sec": float(tot[1]) / (dev_ms * 1e-3), "agent_decisions_per_batch": trans,
             "rollout_ms": statistics.median(roll_ms), "update_ms": statistics.median(upd_ms),
-            "allreduce_and_stats_ms": statistics.median(sync_ms),
-            "step_ms": [round(a + b, 2) for a, b in zip(roll_ms, upd_ms)]}
+            "allreduce_and_stats_ms": statistics.median(sync_ms), "cuda_graph": graph,
+            "launch_by_launch_step_ms": [round(a + b, 2) for a, b in zip(roll_ms, upd_ms)],
+            "last_batch": {k: last[k] for k in ("reward", "ac_loss", "win_percent", "unfinished")} if last else None}
 
 
 def finish_line(args, m, extra_keys=()):
@@ -788,7 +801,7 @@ def run_b200(args):
             m = measure_policy(args, ctx, 131072, es, 3)
             extra["policy"] = {k: m[k] for k in brief + ("decisions_per_sec", "accuracy", "dtype") if k in m}
             m = measure_train(args, ctx, 16384, max(3, min(args.steps, 8)), 3)
-            extra["train"] = {k: m[k] for k in brief + ("agent_decisions_per_batch", "rollout_ms", "update_ms", "allreduce_and_stats_ms", "step_ms", "dtype") if k in m}
+            extra["train"] = {k: m[k] for k in brief + ("agent_decisions_per_batch", "rollout_ms", "update_ms", "allreduce_and_stats_ms", "launch_by_launch_step_ms", "cuda_graph", "last_batch", "dtype") if k in m}
             line["extra"] = extra
     if ctx.rank == 0:
         if ctx.world == 1 and not args.no_cpu_baseline and mode == "random":
