@@ -138,9 +138,25 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 
 // games waiting in a warp's queue that trigger a pass: fuller passes cost fewer instructions, earlier passes patch lines that
 // are still in L2 (measured 16 / 20 / 24 / 28 / 32: 201 / 191 / 183 / 186 / 196 us for 4.2 M two-player games)
-constexpr int STEP_DRAIN_AT = 24;
-constexpr int STEP_QCAP = 48;           // a row that would overflow the queue drains it first
-constexpr int STEP_WARPS = 2;           // warps per block (fine-grained shared-memory occupancy)
+// (the AZB_STEP_* macros exist for tuning sweeps: tools/sweep_step.sh builds variants of the library with -D)
+#ifndef AZB_STEP_DRAIN_AT
+#define AZB_STEP_DRAIN_AT 24
+#endif
+#ifndef AZB_STEP_QCAP
+#define AZB_STEP_QCAP 48
+#endif
+#ifndef AZB_STEP_WARPS
+#define AZB_STEP_WARPS 2
+#endif
+#ifndef AZB_STEP_MINBLOCKS
+#define AZB_STEP_MINBLOCKS 8
+#endif
+#ifndef AZB_STEP_STAGES_P2
+#define AZB_STEP_STAGES_P2 4
+#endif
+constexpr int STEP_DRAIN_AT = AZB_STEP_DRAIN_AT;
+constexpr int STEP_QCAP = AZB_STEP_QCAP;           // a row that would overflow the queue drains it first
+constexpr int STEP_WARPS = AZB_STEP_WARPS;         // warps per block (fine-grained shared-memory occupancy)
 
 template <int P, int STAGES>
 struct StepSmem {
@@ -220,7 +236,7 @@ __device__ __forceinline__ void row_flush(const uint32_t* tile, uint32_t* __rest
 }
 
 template <int P, int POOL, int STAGES>
-__global__ void __launch_bounds__(32 * STEP_WARPS, 8) k_step(Launch L, const uint8_t* __restrict__ action,
+__global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(Launch L, const uint8_t* __restrict__ action,
                                                            const int8_t* __restrict__ draws, StepOut O, int aligned)
 {
     using S = StepSmem<P, STAGES>;
@@ -652,7 +668,7 @@ template <int P, int POOL>
 static int launch_step(const azb_t* h, const Launch& L, const uint8_t* action, const int8_t* draws, const StepOut& O,
                        int aligned, cudaStream_t stream)
 {
-    constexpr int STAGES = P == 2 ? 4 : 3;       // 2 / 3 / 4 / 5 stages: 183 / 192 / 183 / 198 us for 4.2 M two-player games
+    constexpr int STAGES = P == 2 ? AZB_STEP_STAGES_P2 : 3;       // 2 / 3 / 4 / 5 stages: 183 / 192 / 183 / 198 us for 4.2 M two-player games
     auto kern = k_step<P, POOL, STAGES>;
     const size_t smem = StepSmem<P, STAGES>::bytes(STEP_WARPS);
     static thread_local int per_sm_cached[64] = {0};      // function attributes are per device

@@ -487,15 +487,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             const bool ended_before = gm.ended();
             const bool stuck = acts && status == (uint32_t)ST_STUCK;
             uint32_t flags = 0u;
+            bool stepped = false;
             if (A.apply_step && n_valid > 0 && !ended_before) {
                 apply_move<2, POOL>(gm, action);                          // azul.py:304
                 gm.steps += 1u;
                 if (is_end_of_round(gm)) flags = FLAG_ROUND_OVER;         // azul.py:306 -> finishing phase
                 else next_player(gm);                                     // azul.py:313
-                if (valid && A.apply_step == 2) sink.add(0, 1);
+                stepped = valid && A.apply_step == 2;
             } else if (A.apply_step == 2 && acts && (ended_before || stuck)) {
                 flags = FLAG_FRESH_GAME;                                  // GameRunner.reset, game_runner.py:76-80
                 if (valid && stuck) sink.add(6, 1);
+            }
+            {   // env steps executed by this warp's 32 games: one shared-memory atomic per warp (part 0 = whole warps)
+                const uint32_t n_stepped = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, stepped));
+                if ((tid & 31) == 0) sink.add(0, n_stepped);
             }
             gm.misc |= flags;
             if (valid && A.apply_step) gm.store(A.state, A.n, g);
@@ -521,6 +526,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         // round the move may have ended, let the random opponent play until seat 1 is to move with >= 2 legal actions (or the
         // game is over), take the reward from a score preview, and close the decision's record
         bool alive = false;
+        // (spreading a tile's 128 games over all 16 warps, 8 lanes each, was measured slower: 1.07 vs 0.97 ms per rollout of
+        // 16,384 episodes -- the state loads lose their coalescing and every warp still walks the union of its games' paths)
         for (int64_t j = part; j < my_tiles; j += PARTS) {
             const int64_t g = ((int64_t)blockIdx.x + j * gridDim.x) * TILE_M + row;
             if (g >= A.n) continue;

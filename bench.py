@@ -161,7 +161,6 @@ def pyref_worker(seconds, kind="runner"):
         gr = GameRunner(opponent=Agent()) if kind == "selfplay" else GameRunner()
         runner = NNRunner(learner, gr)
         counted = {"steps": 0}
-        orig_step = gr.game.__class__.step
 
         def episode(seed):
             import numpy
