@@ -99,6 +99,15 @@ def allreduce_gradients_and_stats(params, stats):
     return stats
 
 
+def allreduce_flat_and_stats(flat, stats):
+    """What the trainer does per update, in place: C1 = ONE fp32 all-reduce of the flat gradient buffer (82,081 sums), C2 =
+    one float64 all-reduce of the statistics vector.  No-op for a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return flat, stats
+
+
 def global_count(n_local, device):
     t = torch.tensor([float(n_local)], dtype=torch.float64, device=device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -295,9 +304,7 @@ class SelfPlayTrainer:
         one = torch.ones(1, dtype=torch.float64, device=self.device)
         wins = (batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum().reshape(1)
         stats = torch.cat([n_local, sums, reward_total, one * G, batch["stats"].sum(dim=0), wins, unfinished + 1e9 * overflow])
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.tc.flat, op=dist.ReduceOp.SUM)          # C1: 82,081 fp32 gradient sums
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM)                  # C2: 18 float64 counters
+        allreduce_flat_and_stats(self.tc.flat, stats)                    # C1: 82,081 fp32 gradient sums, C2: 18 float64 counters
         self.tc.flat.mul_((1.0 / stats[0].clamp_min(1.0)).float())
         self.opt.step()
         return stats

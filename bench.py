@@ -750,7 +750,9 @@ def measure_train(args, ctx, games, steps, warmup):
             "dtype": "fp16-operand tensor-core MLP (rollout and update), fp32 accumulation / u32 rules", "config": cfg,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 18,
                     "note": "a training batch is end to end by construction: its statistics are copied to pinned host memory every batch"},
-            "gpu_launches": None, "clocks": clocks,
+            # this library's kernels per batch: pack weights, reset, opponent loop (reset), persistent policy rollout,
+            # returns, statistics, update forward/backward, update dW (plus torch fills / reductions / fused Adam / NCCL)
+            "gpu_launches": 8 * steps, "clocks": clocks,
             "games_per_sec": float(tot[1]) / (dev_ms * 1e-3), "agent_decisions_per_batch": trans,
             "rollout_ms": statistics.median(roll_ms), "update_ms": statistics.median(upd_ms),
             "allreduce_and_stats_ms": statistics.median(sync_ms), "cuda_graph": graph,

@@ -139,6 +139,38 @@ def test_two_rank_gradient_allreduce_matches_global_batch(tmp_path):
                 assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-6), name
 
 
+def _flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    from azul_deep_reinforcement_learning_b200.train import allreduce_flat_and_stats
+    dist.init_process_group("gloo")
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(82081, generator=g)
+    stats = torch.tensor([10.0 + rank, 1.5 * (rank + 1)], dtype=torch.float64)
+    allreduce_flat_and_stats(flat, stats)
+    if rank == 0:
+        out.put((flat.clone(), stats.clone()))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_and_stats_allreduce_two_ranks_gloo():
+    """The trainer's collectives (one flat fp32 gradient all-reduce + one float64 statistics all-reduce) on two gloo ranks."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flat, stats = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = sum(torch.randn(82081, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
+    assert torch.allclose(flat, want) and flat.dtype == torch.float32
+    assert stats.tolist() == [21.0, 4.5]
+
+
 def test_saved_networks_load_back_through_agent(tmp_path):
     """Every format the package (or the reference, nn_runner.py:83-84 / agent.py:36) writes loads back through
     ``Agent(base_net_file=...)``: pickled module (.mx), bare state_dict (.pt), trainer checkpoint dict (.pt)."""
