@@ -278,9 +278,9 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     pool = 1 if args.pool == "lid" else 0
     from oracle import oracle as O
-    # bounded sample per step so the whole run ends within minutes: ~1.5 s of CPU work per step
+    # bounded sample per step so the whole run ends within minutes: ~0.5 s of CPU work per step
     rate, _, _, _ = cpu_rollout_rate(args, 1.0, threads)
-    n = int(max(threads, min(args.games, rate * 1.5 / args.k_steps)))
+    n = int(max(threads, min(args.games, rate * 0.5 / args.k_steps)))
     recs = O.fresh_records(n, args.players, pool, 0, args.seed, 0)
     for _ in range(args.warmup):
         O.rollout_random(recs, args.players, pool, 0, args.seed, 0, args.k_steps, threads=threads)
