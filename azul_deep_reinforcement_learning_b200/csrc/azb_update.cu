@@ -48,6 +48,7 @@ struct FwdArgs {
     const float* __restrict__ qval;           // [cap] discounted returns
     const uint32_t* __restrict__ n_dec;       // [1] device-side decision count (clamped to cap), or null: n_fixed
     int64_t n_fixed;
+    int64_t row0, rows_max;                   // this launch handles decisions [row0, row0 + rows_max) (workspace-sized chunks)
     const unsigned char* __restrict__ packed; // weight image (azb_policy_pack_weights)
     float actor_c, critic_c, entropy_c;
     unsigned char* __restrict__ xt;           // operand tiles for k_update_dw, [tiles][...]
@@ -113,8 +114,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
     const uint32_t w1_addr = smem_u32(smem + OFF_W1), w2_addr = smem_u32(smem + OFF_W2), a_addr = smem_u32(t1);
-    int64_t n = A.n_dec ? (int64_t)*A.n_dec : A.n_fixed;
-    n = n < A.cap ? n : A.cap;
+    int64_t n_all = A.n_dec ? (int64_t)*A.n_dec : A.n_fixed;
+    n_all = n_all < A.cap ? n_all : A.cap;
+    int64_t n = n_all - A.row0;                              // decisions of this chunk
+    n = n < 0 ? 0 : (n < A.rows_max ? n : A.rows_max);
     const int64_t tiles = (n + TILE_M - 1) / TILE_M;
     const int col0 = part * PART_COLS;
     uint32_t phase = 0;
@@ -125,13 +128,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
     Game<2> nxt;
     if ((int64_t)blockIdx.x < tiles) {
         const int64_t g0 = (int64_t)blockIdx.x * TILE_M + row;
-        nxt.load(A.state_rec, A.cap, g0 < n ? g0 : n - 1);
+        nxt.load(A.state_rec, A.cap, A.row0 + (g0 < n ? g0 : n - 1));
     }
     mbar_wait(bar_w, 0);
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t g = tile * TILE_M + row;
-        const bool valid = g < n;
-        const int64_t gl = valid ? g : n - 1;
+        const bool valid = tile * TILE_M + row < n;
+        const int64_t g = A.row0 + tile * TILE_M + row;         // absolute decision index
+        const int64_t gl = valid ? g : A.row0 + n - 1;
         unsigned char* g_x = A.xt + tile * X_TILE_BYTES;
         unsigned char* g_ha = A.ha + tile * H_TILE_BYTES;
         unsigned char* g_dl = A.dl + tile * H_TILE_BYTES;
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
         if (part == 0) gb2c += dv;
         if (tile + gridDim.x < tiles) {                    // in flight during epilogue 3
             const int64_t g2 = (tile + gridDim.x) * TILE_M + row;
-            nxt.load(A.state_rec, A.cap, g2 < n ? g2 : n - 1);
+            nxt.load(A.state_rec, A.cap, A.row0 + (g2 < n ? g2 : n - 1));
         }
         mbar_wait(bar3, phase);
         tc_fence_after();
@@ -463,7 +466,7 @@ struct DwGemm {
 struct DwArgs {
     DwGemm gemm[3];                              // CTA b works on gemm[b % 3]: the three products run side by side
     const uint32_t* __restrict__ n_dec;
-    int64_t n_fixed, cap;
+    int64_t n_fixed, cap, row0, rows_max;
 };
 
 constexpr int DW_THREADS = 256;
@@ -497,7 +500,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_update_dw(DwArgs A)
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     int64_t n = A.n_dec ? (int64_t)*A.n_dec : A.n_fixed;
-    n = n < A.cap ? n : A.cap;
+    n = (n < A.cap ? n : A.cap) - A.row0;
+    n = n < 0 ? 0 : (n < A.rows_max ? n : A.rows_max);
     const int64_t tiles = (n + TILE_M - 1) / TILE_M;
     // CTA b: product b % 3, and among that product's CTAs number b / 3 of (gridDim.x - role + 2) / 3
     const int role = (int)(blockIdx.x % 3u), rank = (int)(blockIdx.x / 3u), ranks = ((int)gridDim.x - role + 2) / 3;
@@ -586,10 +590,22 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_update_dw(DwArgs A)
 
 extern "C" {
 
+// the kernels work through the decisions in chunks of at most UPDATE_CHUNK so that the workspace stays bounded (1.9 GB)
+// however large the record capacity is
+static int64_t UPDATE_CHUNK = (int64_t)1 << 20;
+
+int azb_update_set_chunk_rows(int64_t rows)
+{
+    if (rows < pol::TILE_M || rows % pol::TILE_M) return azb_fail(AZB_E_INVALID, "chunk rows must be a positive multiple of 128%s");
+    UPDATE_CHUNK = rows;
+    return 0;
+}
+
 int64_t azb_update_workspace_bytes(int64_t capacity)
 {
-    const int64_t tiles = (capacity + pol::TILE_M - 1) / pol::TILE_M;
-    return tiles * (int64_t)(upd::X_TILE_BYTES + 4 * upd::H_TILE_BYTES) + upd::H_TILE_BYTES;      // + slack for the M-tile overrun of the last tile's bulk copy source
+    const int64_t rows = capacity < UPDATE_CHUNK ? capacity : UPDATE_CHUNK;
+    const int64_t tiles = (rows + pol::TILE_M - 1) / pol::TILE_M;
+    return tiles * (int64_t)(upd::X_TILE_BYTES + 4 * upd::H_TILE_BYTES);
 }
 
 int azb_a2c_update_gradients(azb_t* h, const uint32_t* state_rec, int64_t capacity, const uint8_t* action, const float* qval,
@@ -605,24 +621,21 @@ int azb_a2c_update_gradients(azb_t* h, const uint32_t* state_rec, int64_t capaci
     if (capacity < 1 || (!n_dec && (n_fixed < 0 || n_fixed > capacity))) return azb_fail(AZB_E_INVALID, "bad decision count / capacity%s");
     if (h->players != 2) return azb_fail(AZB_E_INVALID, "the policy network is defined for 2 players (136 inputs, agent.py:29)%s");
     if (!n_dec && n_fixed == 0) return 0;
-    const int64_t tiles_cap = (capacity + pol::TILE_M - 1) / pol::TILE_M;
+    const int64_t chunk_rows = capacity < UPDATE_CHUNK ? capacity : UPDATE_CHUNK;
+    const int64_t tiles_cap = (chunk_rows + pol::TILE_M - 1) / pol::TILE_M;
     unsigned char* ws = (unsigned char*)workspace;
     upd::FwdArgs F;
     F.state_rec = state_rec; F.cap = capacity; F.action = action; F.qval = qval; F.n_dec = n_dec; F.n_fixed = n_fixed;
     F.packed = (const unsigned char*)packed; F.actor_c = actor_coeff; F.critic_c = critic_coeff; F.entropy_c = entropy_coeff;
-    // [A tile | B tile] pairs are NOT interleaved in HBM: five arrays of tiles
+    // five arrays of operand tiles (one chunk's worth)
     F.dl = ws;
     F.ha = F.dl + tiles_cap * upd::H_TILE_BYTES;
     F.dha = F.ha + tiles_cap * upd::H_TILE_BYTES;
     F.dhc = F.dha + tiles_cap * upd::H_TILE_BYTES;
     F.xt = F.dhc + tiles_cap * upd::H_TILE_BYTES;
     F.grad_w2c = grad_w2c; F.grad_b2c = grad_b2c; F.sums = sums; F.logits_out = logits_out; F.value_out = value_out;
-    const int64_t tiles_max = n_dec ? tiles_cap : (n_fixed + pol::TILE_M - 1) / pol::TILE_M;
-    const int grid = (int)(tiles_max < h->sm_count ? tiles_max : h->sm_count);
     cudaStream_t st = (cudaStream_t)stream;
     AZB_CUDA(cudaFuncSetAttribute(upd::k_update_fwd_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES));
-    upd::k_update_fwd_bwd<<<grid, pol::THREADS, pol::SMEM_BYTES, st>>>(F);
-    CHECK_LAUNCH();
     const int dw_smem = upd::DW_STAGES * upd::DW_STAGE_BYTES;
     AZB_CUDA(cudaFuncSetAttribute(upd::k_update_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     upd::DwArgs D;
@@ -634,8 +647,19 @@ int azb_a2c_update_gradients(azb_t* h, const uint32_t* state_rec, int64_t capaci
     // grad W1c | b1c = dHc^T [X | 1]
     D.gemm[2] = upd::DwGemm{F.dhc, F.xt, upd::X_TILE_BYTES, 144, grad_w1c, pol::OBS, pol::OBS, grad_b1c, pol::BIAS_K1, 1};
     const int dw_grid = h->sm_count < 3 ? 3 : h->sm_count;       // every product needs at least one CTA
-    upd::k_update_dw<<<dw_grid, upd::DW_THREADS, dw_smem, st>>>(D);
-    CHECK_LAUNCH();
+    // with a device-side count every chunk of the capacity is launched (a chunk past the count exits at once)
+    const int64_t rows_total = n_dec ? capacity : n_fixed;
+    for (int64_t row0 = 0; row0 < rows_total; row0 += chunk_rows) {
+        const int64_t rows = rows_total - row0 < chunk_rows ? rows_total - row0 : chunk_rows;
+        const int64_t tiles_max = (rows + pol::TILE_M - 1) / pol::TILE_M;
+        const int grid = (int)(tiles_max < h->sm_count ? tiles_max : h->sm_count);
+        F.row0 = row0; F.rows_max = rows;
+        upd::k_update_fwd_bwd<<<grid, pol::THREADS, pol::SMEM_BYTES, st>>>(F);
+        CHECK_LAUNCH();
+        D.row0 = row0; D.rows_max = rows;
+        upd::k_update_dw<<<dw_grid, upd::DW_THREADS, dw_smem, st>>>(D);
+        CHECK_LAUNCH();
+    }
     return 0;
 }
 

@@ -237,6 +237,10 @@ int azb_a2c_loss_grad(azb_t* h, int64_t n, const float* logits, const float* val
  * scratch of azb_update_workspace_bytes(capacity) bytes.  logits_out float [n][180] / value_out float [n] (optional): the
  * recomputed network outputs. */
 int64_t azb_update_workspace_bytes(int64_t capacity);
+/* The update works through the decisions in chunks so that the workspace stays bounded however large `capacity` is
+ * (default 2^20 decisions = 1.9 GB); process-wide tuning / test hook: rows must be a positive multiple of 128 and be set
+ * before azb_update_workspace_bytes is asked for the size. */
+int azb_update_set_chunk_rows(int64_t rows);
 int azb_a2c_update_gradients(azb_t* h, const uint32_t* state_rec, int64_t capacity, const uint8_t* action, const float* qval,
                              const uint32_t* n_dec, int64_t n_fixed, const void* packed, float actor_coeff, float critic_coeff,
                              float entropy_coeff, void* workspace, float* grad_w1a, float* grad_b1a, float* grad_w2a,

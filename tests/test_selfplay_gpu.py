@@ -362,3 +362,35 @@ def test_tensor_core_update_gradients_match_autograd(games, scale):
     upd.run(packed, recs.state_rec, recs.action_rec, recs.qval, n_fixed=n, coeffs=coeffs, zero=False)
     torch.cuda.synchronize()
     assert float((upd.flat - 2 * flat1).abs().max()) <= 2e-3 * float(flat1.abs().max())
+
+
+def test_tensor_core_update_in_chunks_equals_one_pass():
+    """azb_a2c_update_gradients works through the records in workspace-sized chunks: 1,024-decision chunks give the same
+    gradient sums (up to the order of the fp32 atomic additions) as one pass."""
+    from azul_deep_reinforcement_learning_b200 import _lib
+    from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
+    from azul_deep_reinforcement_learning_b200.engine import PackedPolicy, UpdateGradients
+    from azul_deep_reinforcement_learning_b200.selfplay import BatchedGameRunner, PersistentEpisodes
+    torch.manual_seed(9)
+    net = ActorCritic(136, 180).cuda()
+    gr = BatchedGameRunner(300, seed=12)
+    packed = PackedPolicy(gr.engine, net)
+    recs = PersistentEpisodes(gr, packed, max_decisions=160).run(gamma=0.99)
+    n = int(recs.meta[0])
+    one = UpdateGradients(gr.engine, recs.cap)
+    one.run(packed, recs.state_rec, recs.action_rec, recs.qval, n_dec=recs.meta[:1])
+    lib = _lib.load()
+    try:
+        _lib.check(lib.azb_update_set_chunk_rows(1024))
+        many = UpdateGradients(gr.engine, recs.cap)
+        assert many.workspace.numel() < one.workspace.numel() // 8
+        many.run(packed, recs.state_rec, recs.action_rec, recs.qval, n_dec=recs.meta[:1])
+        fixed = UpdateGradients(gr.engine, recs.cap)
+        fixed.run(packed, recs.state_rec, recs.action_rec, recs.qval, n_fixed=n)
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.azb_update_set_chunk_rows(1 << 20))
+    scale = float(one.flat.abs().max())
+    assert n > 5 * 1024 and float((many.flat - one.flat).abs().max()) <= 1e-4 * scale
+    assert float((fixed.flat - one.flat).abs().max()) <= 1e-4 * scale
+    assert float(((many.sums - one.sums).abs() / one.sums.abs().clamp_min(1.0)).max()) < 1e-9
