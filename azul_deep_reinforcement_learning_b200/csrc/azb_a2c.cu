@@ -130,14 +130,22 @@ __global__ void k_returns(int64_t n, int k, double gamma, const int16_t* __restr
     if (steps_used && (int)*steps_used < k) k = (int)*steps_used;      // decision iterations the rollout actually ran
     double q = 0.0, total = 0.0;
     if (g < n) {
-        for (int t = k - 1; t >= 0; t--) {
-            const int64_t i = (int64_t)t * n + g;
-            if (!(flags_rec[i] & 1)) continue;
-            const double r = (double)reward_rec[i];
-            q = r + gamma * q;
-            total += r;
-            const int32_t slot = slot_rec[i];
-            if (slot >= 0) qval[slot] = (float)q;
+        // backwards in groups of four: the twelve loads of a group are independent of the recurrence and in flight together
+        for (int t1 = k; t1 > 0; t1 -= 4) {
+            uint8_t f[4]; int16_t r[4]; int32_t sl[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int t = t1 - 1 - j;
+                const int64_t i = (int64_t)(t < 0 ? 0 : t) * n + g;
+                f[j] = t >= 0 ? flags_rec[i] : (uint8_t)0; r[j] = reward_rec[i]; sl[j] = slot_rec[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!(f[j] & 1)) continue;
+                q = (double)r[j] + gamma * q;
+                total += (double)r[j];
+                if (sl[j] >= 0) qval[sl[j]] = (float)q;
+            }
         }
     }
     if (reward_sum) {                                   // sum of the episode rewards (Agent.update's "reward" statistic, agent.py:58)
@@ -147,7 +155,62 @@ __global__ void k_returns(int64_t n, int k, double gamma, const int16_t* __restr
     }
 }
 
+// The statistics vector of one training batch in one pass over the games (what Agent.update / GameRunner's statistics
+// report, agent.py:58-59, game_runner.py:10-22, azul.py:314-315): out[18] (double, zeroed by the caller) =
+//   0 decision count (clamped to the record capacity), 1-3 the three loss sums, 4 sum of rewards, 5 games,
+//   6-15 sums of Azul.get_statistics' ten raw values over the games, 16 games seat 1 won, 17 games not finished
+//   (+ 1e9 when the decision records overflowed their capacity).
+__global__ void k_train_stats(const uint32_t* __restrict__ s, int64_t n, const uint32_t* __restrict__ n_dec, int64_t rec_cap,
+                              const double* __restrict__ loss_sums, const double* __restrict__ reward_sum, double* __restrict__ out)
+{
+    __shared__ double part[12][8];
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) v[i] = 0.0;
+    if (g < n) {                                                        // 2-player layout: MISC word 3, per player 7 + 5p .. 11 + 5p
+        const uint32_t misc = s[3 * n + g], scf0 = s[9 * n + g], scf1 = s[14 * n + g], sta0 = s[10 * n + g], sta1 = s[15 * n + g], stb0 = s[11 * n + g];
+        const double s0 = (double)(scf0 & 0xFFFFu), s1 = (double)(scf1 & 0xFFFFu);
+        v[0] = s0; v[1] = s1; v[2] = (double)((misc >> 16) & 0xFFFu); v[3] = (double)(sta0 & 0xFFFu);
+        v[4] = (double)((sta0 & 0xFFFu) + (sta1 & 0xFFFu)); v[5] = (double)((sta0 >> 12) & 0xFFFFu); v[6] = (double)(sta0 >> 28);
+        v[7] = (double)(stb0 & 255u); v[8] = (double)((stb0 >> 16) & 255u); v[9] = (double)((stb0 >> 8) & 255u);
+        v[10] = s0 > s1 ? 1.0 : 0.0; v[11] = ((misc >> 12) & 1u) ? 0.0 : 1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
+        if ((threadIdx.x & 31) == 0) part[i][threadIdx.x >> 5] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += part[threadIdx.x][w];
+        if (t != 0.0) atomicAdd(out + 6 + threadIdx.x, t);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t nd = (int64_t)*n_dec;
+        out[0] = (double)(nd < rec_cap ? nd : rec_cap);
+        out[1] = loss_sums[0]; out[2] = loss_sums[1]; out[3] = loss_sums[2];
+        out[4] = reward_sum[0]; out[5] = (double)n;
+        if (nd > rec_cap) atomicAdd(out + 17, 1e9);
+    }
+}
+
 }  // namespace a2c
+
+extern "C" int azb_train_stats(azb_t* h, const uint32_t* state, const uint32_t* n_dec, int64_t rec_cap, const double* loss_sums,
+                               const double* reward_sum, double* out18, void* stream)
+{
+    CHECK_HANDLE(h);
+    if (!state || !n_dec || !loss_sums || !reward_sum || !out18) return azb_fail(AZB_E_INVALID, "null buffer%s");
+    if (h->players != 2) return azb_fail(AZB_E_INVALID, "training statistics are defined for the 2-player GameRunner%s");
+    AZB_CUDA(cudaMemsetAsync(out18, 0, 18 * sizeof(double), (cudaStream_t)stream));
+    a2c::k_train_stats<<<(unsigned)((h->n_games + 255) / 256), 256, 0, (cudaStream_t)stream>>>(state, h->n_games, n_dec, rec_cap,
+                                                                                              loss_sums, reward_sum, out18);
+    CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int azb_discounted_returns(azb_t* h, int k_decisions, double gamma, const int16_t* reward_rec,
                                       const uint8_t* flags_rec, const int32_t* slot_rec, float* qval, double* reward_sum,

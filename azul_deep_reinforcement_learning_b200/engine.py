@@ -448,6 +448,13 @@ def runner_rollout(engine, packed, records, player_score, mode=0, out=None):
         None, engine._stream()))
 
 
+def train_stats(engine, records, loss_sums, out):
+    """The 18 batch statistics (``azb_train_stats``) into ``out`` (float64 [18]) in one launch."""
+    _lib.check(engine.lib.azb_train_stats(engine._h, _ptr(engine.state), _ptr(records.meta), records.cap, _ptr(loss_sums),
+                                         _ptr(records.reward_sum), _ptr(out), engine._stream()))
+    return out
+
+
 def discounted_returns_records(engine, records, gamma):
     """nn_runner.py:72-75 on the decision records: fills ``records.qval`` (compact) and ``records.reward_sum``."""
     r = records

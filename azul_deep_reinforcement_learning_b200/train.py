@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 from . import parallel
 from .azulnet.model import ActorCritic
-from .engine import PackedPolicy, UpdateGradients
+from .engine import PackedPolicy, UpdateGradients, train_stats
 from .selfplay import BatchedGameRunner, GraphedEpisodes, PersistentEpisodes, discounted_returns, run_episodes
 
 ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF = 1.0, 0.5, 0.1          # agent.py:47-49
@@ -164,8 +164,7 @@ class SelfPlayTrainer:
         with torch.no_grad():
             self.packed.update(self.net)
             if self.episodes is not None:
-                recs = self.episodes.run(self.gamma)
-                return {"records": recs, "stats": self.runner.engine.stats().to(torch.float64)}
+                return {"records": self.episodes.run(self.gamma)}
             if self.graphed is not None:
                 batch = self.graphed.run(max_decisions=self.max_decisions)
             else:
@@ -277,7 +276,6 @@ class SelfPlayTrainer:
         G = self.runner.n_games
         if "records" in batch:                        # compact decision records of the persistent rollout
             recs = batch["records"]
-            n_local = recs.meta[:1].double()
             if self.update_kind == "tensor":
                 self.tc.run(self.packed, recs.state_rec, recs.action_rec, recs.qval, n_dec=recs.meta[:1],
                             coeffs=(ACTOR_COEFF, CRITIC_COEFF, ENTROPY_COEFF))
@@ -287,9 +285,7 @@ class SelfPlayTrainer:
                 obs = recs.view.observe_bf16(-1)[:n]
                 masks = recs.view.legal_mask().t()[:n]
                 sums = self.accumulate_gradients(obs, masks, recs.action_rec[:n].long(), recs.qval[:n])
-            reward_total = recs.reward_sum.reshape(1)
-            unfinished = (G - ((recs.flags_rec >> 1) & 1).sum()).double().reshape(1)
-            overflow = (recs.meta[:1] > recs.cap).double()
+            stats = train_stats(self.runner.engine, recs, sums, torch.empty(STAT_FIELDS, dtype=torch.float64, device=self.device))
         else:
             act = batch["active"]
             T = act.shape[0]
@@ -300,10 +296,9 @@ class SelfPlayTrainer:
             sums = self.accumulate_gradients(obs, masks, batch["action"].reshape(-1)[sel], batch["qval"].reshape(-1)[sel])
             reward_total = batch["reward"].double().mul(act).sum().reshape(1)
             unfinished = torch.full((1,), float(batch["unfinished"]), dtype=torch.float64, device=self.device)
-            overflow = torch.zeros(1, dtype=torch.float64, device=self.device)
-        one = torch.ones(1, dtype=torch.float64, device=self.device)
-        wins = (batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum().reshape(1)
-        stats = torch.cat([n_local, sums, reward_total, one * G, batch["stats"].sum(dim=0), wins, unfinished + 1e9 * overflow])
+            one = torch.ones(1, dtype=torch.float64, device=self.device)
+            wins = (batch["stats"][:, 0] > batch["stats"][:, 1]).double().sum().reshape(1)
+            stats = torch.cat([n_local, sums, reward_total, one * G, batch["stats"].sum(dim=0), wins, unfinished])
         allreduce_flat_and_stats(self.tc.flat, stats)                    # C1: 82,081 fp32 gradient sums, C2: 18 float64 counters
         self.tc.flat.mul_((1.0 / stats[0].clamp_min(1.0)).float())
         self.opt.step()

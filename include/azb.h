@@ -208,6 +208,14 @@ int azb_policy_rollout(azb_t* h, uint32_t* state, const void* packed, int mode, 
 int azb_discounted_returns(azb_t* h, int k_decisions, double gamma, const int16_t* reward_rec, const uint8_t* flags_rec,
                            const int32_t* slot_rec, float* qval, double* reward_sum, const uint32_t* steps_used, void* stream);
 
+/* The statistics of one training batch in one launch (what Agent.update and GameRunner's GameStatistics report,
+ * agent.py:58-59, game_runner.py:10-22, azul.py:314-315), from the final packed states of the batch's games and the
+ * device-side results of the rollout / update: out18 double [18] = decision count (clamped to rec_cap), the three loss
+ * sums, sum of rewards, games, the sums of Azul.get_statistics' ten raw values (azb_stats order), games seat 1 won, games
+ * not finished (+ 1e9 when n_dec > rec_cap: the decision records overflowed).  Sums, so that ranks can all-reduce them. */
+int azb_train_stats(azb_t* h, const uint32_t* state, const uint32_t* n_dec, int64_t rec_cap, const double* loss_sums,
+                    const double* reward_sum, double* out18, void* stream);
+
 /* ---- a19: the loss of Agent.update and its gradient at the network outputs --------------------
  * For n recorded agent decisions (device arrays): logits float [n][180] (raw actor outputs), value float [n],
  * mask_rows uint32 [n][6] (the legal-mask words of each decision), action int64 [n], qval float [n]
