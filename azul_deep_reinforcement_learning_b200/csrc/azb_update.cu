@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
     const int col0 = part * PART_COLS;
     uint32_t phase = 0;
     double acc_a = 0.0, acc_c = 0.0, acc_e = 0.0;            // loss sums (part 0 threads)
-    float gw2c_lo = 0.0f, gw2c_hi = 0.0f, gb2c = 0.0f;       // lane l of a warp: critic columns col0 + l and col0 + 32 + l (l < 16)
+    float gw2c[3] = {0.0f, 0.0f, 0.0f}, gb2c = 0.0f;          // lane l of a warp: critic columns col0 + 16 c + (l & 15), c = 0..2
 
     // the packed state of a tile's decisions is loaded one tile ahead (before the previous tile's last epilogue)
     Game<2> nxt;
@@ -357,7 +357,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
             umma_commit(bar3);
         }
         // ---- meanwhile, the critic: dHc = dv w2c (Hc > 0) -> HBM;  grad w2c += dv relu(Hc_pre);  grad b2c += dv ----
-        float gsum_lo = 0.0f, gsum_hi = 0.0f;
 #pragma unroll
         for (int c = 0; c < PART_COLS / 16; c++) {
             const int c0 = col0 + 16 * c;
@@ -379,15 +378,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
                 o.z = pack_f16(d[8 * qq + 4], d[8 * qq + 5]); o.w = pack_f16(d[8 * qq + 6], d[8 * qq + 7]);
                 *reinterpret_cast<uint4*>(g_dhc + hbm_off((c0 >> 3) + qq, row, K2_CHUNKS)) = o;
             }
-            // column sums over the warp's 32 rows: lane l keeps columns l (c = 0, 1) and 32 + l (c = 2)
+            // column sums over the warp's 32 rows by a transposing butterfly: at distance s every lane hands the half of its
+            // values that its partner keeps (16 shuffles per 16 columns instead of 80); lane l ends up with column l & 15
+            float t[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const float t = warp_sum(dv * fmaxf(v[i], 0.0f));
-                if (c < 2) gsum_lo = (lane == 16 * c + i) ? t : gsum_lo;
-                else gsum_hi = (lane == i) ? t : gsum_hi;
+            for (int i = 0; i < 16; i++) t[i] = dv * fmaxf(v[i], 0.0f);
+#pragma unroll
+            for (int sft = 8; sft >= 1; sft >>= 1) {
+                const bool up = (lane & sft) != 0;
+#pragma unroll
+                for (int i = 0; i < sft; i++) {
+                    const float send = up ? t[i] : t[i + sft];
+                    const float keep = up ? t[i + sft] : t[i];
+                    t[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, sft);
+                }
             }
+            gw2c[c] += t[0] + __shfl_xor_sync(0xFFFFFFFFu, t[0], 16);
         }
-        gw2c_lo += gsum_lo; gw2c_hi += gsum_hi;
         if (part == 0) gb2c += dv;
         if (tile + gridDim.x < tiles) {                    // in flight during epilogue 3
             const int64_t g2 = (tile + gridDim.x) * TILE_M + row;
@@ -420,11 +427,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
 
     // ---- kernel end: the critic's second layer gradient and the loss sums ----
     {
-        // lane l of every warp holds the sums of critic columns col0 + l (and col0 + 32 + l for l < 16) over its rows
-        const int j_lo = col0 + lane, j_hi = col0 + 32 + lane;
-        const int u_lo = critic_unit(j_lo), u_hi = lane < 16 ? critic_unit(j_hi) : -1;
-        if (u_lo >= 0 && gw2c_lo != 0.0f) atomicAdd(A.grad_w2c + u_lo, gw2c_lo);
-        if (u_hi >= 0 && gw2c_hi != 0.0f) atomicAdd(A.grad_w2c + u_hi, gw2c_hi);
+        // lanes 0..15 of every warp hold the sums of critic columns col0 + 16 c + lane over the warp's rows
+        if (lane < 16) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int u = critic_unit(col0 + 16 * c + lane);
+                if (u >= 0 && gw2c[c] != 0.0f) atomicAdd(A.grad_w2c + u, gw2c[c]);
+            }
+        }
         const float b = warp_sum(gb2c);
         if (lane == 0 && b != 0.0f) atomicAdd(A.grad_b2c, b);
         double a0 = acc_a, a1 = acc_c, a2 = acc_e;
