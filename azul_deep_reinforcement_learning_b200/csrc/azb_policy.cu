@@ -215,13 +215,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         Game<2> gm = nxt;
         const bool has_next = tile + gridDim.x < tiles;
 
-        // ---- the observation tile (layer-1 A operand) is already in shared memory ----
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-
-        // ---- layer 1 on the tensor cores ----
-        if (tid == 0) {
+        // ---- layer 1 on the tensor cores.  For the first tile of a decision round the observation was built by all four
+        // parts in the prologue: one block barrier, then thread 0 issues.  For every later tile parts 1..3 built it during
+        // the previous tile's last epilogue and thread 128 issued the MMAs right there (see the end of the loop body): the
+        // MMAs start while part 0 still plays the previous tile's moves (+1.4 % decisions/s; building the observation even
+        // earlier -- right after layer 2, by all four parts -- and issuing before epilogue 2c was measured and is no faster) ----
+        auto issue_layer1 = [&]() {
             tc_fence_after();
 #pragma unroll 1
             for (int s = 0; s < K1 / 16; s++) {
@@ -232,6 +231,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 umma(tmem_base + N1A, ad, bd_c, instr_desc(N1C), s > 0);
             }
             umma_commit(bar1);
+        };
+        if (tile == (int64_t)blockIdx.x) {
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) issue_layer1();
         }
         if (has_next) {                                    // in flight while the epilogues run
             const int64_t g2 = (tile + gridDim.x) * TILE_M + row;
@@ -511,6 +516,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         }
         else if (has_next) {
             build_obs_tile_3(nxt, a_tile, row, part);      // writes [0, OBS_TILE_BYTES): the scratch above it stays intact
+            // Layer 1 of the NEXT tile starts now, while part 0 still publishes and plays this tile's moves: nobody reads
+            // TMEM any more (every thread passed the barrier after epilogue 2b behind a tcgen05 fence; part 0 works from
+            // registers and the scratch behind the observation tile), and the observation's writers are exactly the 384
+            // threads of parts 1..3, which meet at a named barrier of their own.
+            fence_async_smem();
+            asm volatile("bar.sync 1, %0;" ::"n"(THREADS - TILE_M) : "memory");
+            if (tid == TILE_M) issue_layer1();
         }
         // all TMEM reads and scratch reads of this tile are complete before the next tile overwrites them
         __syncthreads();
