@@ -35,10 +35,26 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile libazb.so if missing or stale; returns its path."""
-    if force or needs_build():
-        cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-        subprocess.check_call(cmd)
+    """Compile libazb.so if missing or stale; returns its path.  Each translation unit is compiled to an object file
+    under csrc/_obj (only when it or a header changed), all of them in parallel, then linked."""
+    if not (force or needs_build()):
+        return LIB_PATH
+    nvcc = find_nvcc()
+    obj_dir = os.path.join(CSRC, "_obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    newest_header = max(os.path.getmtime(h) for h in HEADERS)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 

@@ -188,6 +188,32 @@ AZB_HD void legal_mask(const Game<P>& g, uint32_t m[6])
     }
 }
 
+// The destination half of the legal mask as one word per player: bit 5r + c = colour c may still go to pattern line r
+// (the line is empty or holds c, and wall[r][c] is clear; azul.py:171-175).  The rollout keeps these words in registers:
+// a move into line r leaves exactly {c} open there, scoring rebuilds them (rollout_steps).
+template <int P>
+AZB_HD uint32_t open_rows(const Game<P>& g, int pl)
+{
+    const uint32_t pat = g.pat[pl], wall = g.wall[pl];
+    uint32_t o = 0;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, col = (pat >> (6 * r)) & 7u;
+        o |= ((cnt ? (1u << col) : 31u) & ~(wall >> (5 * r)) & 31u) << (5 * r);
+    }
+    return o;
+}
+// legal_mask from the open-rows words (same result as legal_mask(g, m) when open[p] == open_rows(g, p))
+template <int P>
+AZB_HD void legal_mask_open(const Game<P>& g, const uint32_t (&open)[P], uint32_t m[6])
+{
+    const uint32_t src = (g.pl0 | g.pl1 | g.pl2 | spread5to6(g.misc & 31u)) & PLANE_MASK;
+    const uint32_t o = g.sel(open, g.seat());
+    m[0] = src;
+#pragma unroll
+    for (int r = 0; r < 5; r++) m[r + 1] = src & (spread5to6((o >> (5 * r)) & 31u) * 63u);
+}
+
 // floors[] += n capped at 7 (azul.py:119-123)
 AZB_HD uint32_t floor_add(uint32_t scf, uint32_t n)
 {
@@ -197,8 +223,8 @@ AZB_HD uint32_t floor_add(uint32_t scf, uint32_t n)
 }
 
 // ---- move (azul.py:118-161); no legality check, like the reference ----
-template <int P, int POOL>
-AZB_HD void apply_move(Game<P>& g, uint32_t action)
+template <int P, int POOL, bool TRACK>
+AZB_HD void apply_move_impl(Game<P>& g, uint32_t action, uint32_t* open)
 {
     // Branch-free: a warp holds 32 different games, so "display or centre" and "pattern line or floor"
     // are selects, not branches.  A centre take is the display case with an empty "rest".
@@ -241,7 +267,17 @@ AZB_HD void apply_move(Game<P>& g, uint32_t action)
     g.put(g.pat, s, to_row ? newpat : pat);
     g.put(g.scf, s, floor_add(g.sel(g.scf, s), tok + to_floor));     // azul.py:119-123 (cap 7)
     if (POOL == POOL_LID) g.lid += to_floor << (6u * c);              // azul.py:156-157,160-161
+    if (TRACK) {                                                      // open rows of the mover: line p-1 now takes only c
+        const uint32_t sh5 = to_row ? 5u * (p - 1u) : 0u;
+#pragma unroll
+        for (int q = 0; q < P; q++) {
+            const uint32_t o = open[q];
+            open[q] = (to_row && s == q) ? ((o & ~(31u << sh5)) | (1u << (sh5 + c))) : o;
+        }
+    }
 }
+template <int P, int POOL>
+AZB_HD void apply_move(Game<P>& g, uint32_t action) { apply_move_impl<P, POOL, false>(g, action, nullptr); }
 
 // azul.py:177-181 (GT: Game<P>, or the factory-count variant's GameV<P,F>, which shares the per-player words)
 template <class GT>
@@ -371,34 +407,55 @@ AZB_HD void new_round_header(Game<P>& g)
 }
 
 // Lid pool: the box for the duration of a refill, held as the four cumulative counts the draw compares against
-// (e0 = box[0], e1 = box[0] + box[1], ...) and the total, so a draw updates its thresholds in place.
+// (e0 = box[0], e1 = box[0] + box[1], ...) packed as the four bytes of ONE register, each with its bit 7 set, and the
+// total.  A draw compares its point with all four thresholds in one subtraction (byte j of E - (r + 1) * 0x01010101
+// keeps bit 7 exactly when e_j > r; no byte borrows because 128 + e_j - r - 1 stays in [0, 255]) and lowers the
+// thresholds above the point in one more.  A real game holds 100 tiles, so a cumulative count fits 7 bits; a
+// box with more than 127 tiles (only reachable from an imported record that no game can produce) is flagged
+// ST_BAD_IMPORT by the caller and clamped.
 struct BoxRegs {
-    uint32_t e0, e1, e2, e3, total;
-    AZB_M void unpack(uint32_t w)
+    uint32_t E, total;
+    // returns false when the counts do not fit (more than 127 tiles)
+    AZB_M bool unpack(uint32_t w)
     {
-        e0 = w & 63u; e1 = e0 + ((w >> 6) & 63u); e2 = e1 + ((w >> 12) & 63u); e3 = e2 + ((w >> 18) & 63u);
+        const uint32_t e0 = w & 63u, e1 = e0 + ((w >> 6) & 63u), e2 = e1 + ((w >> 12) & 63u), e3 = e2 + ((w >> 18) & 63u);
         total = e3 + ((w >> 24) & 63u);
+        const bool fits = total <= 127u;
+        const uint32_t c0 = e0 < 127u ? e0 : 127u, c1 = e1 < 127u ? e1 : 127u, c2 = e2 < 127u ? e2 : 127u, c3 = e3 < 127u ? e3 : 127u;
+        total = fits ? total : 127u;
+        E = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24) | 0x80808080u;
+        return fits;
     }
-    AZB_M uint32_t pack() const { return e0 | ((e1 - e0) << 6) | ((e2 - e1) << 12) | ((e3 - e2) << 18) | ((total - e3) << 24); }
+    AZB_M uint32_t pack() const
+    {
+        const uint32_t e0 = E & 127u, e1 = (E >> 8) & 127u, e2 = (E >> 16) & 127u, e3 = (E >> 24) & 127u;
+        return e0 | ((e1 - e0) << 6) | ((e2 - e1) << 12) | ((e3 - e2) << 18) | ((total - e3) << 24);
+    }
 };
 
-// Lid pool, one draw (azul.py:79-89): pour the lid into an empty box, pick colour c when the
-// point r in [0,total) falls in its cumulative count.  Returns colour or -1 when no tile is left.
+// one draw from a non-empty box (azul.py:87-89): colour c <=> e(c-1) <= r < e(c) for the point r = mulhi(x, total);
+// taking one tile of c lowers every threshold from e(c) on.  Returns the colour.
+AZB_HD uint32_t lid_draw_fast(BoxRegs& B, uint32_t& x)
+{
+    const uint64_t prod = (uint64_t)x * B.total;                  // one wide multiply: the point and the next x
+    const uint32_t r = (uint32_t)(prod >> 32);
+    x = (uint32_t)prod;
+    const uint32_t above = ((B.E - (r + 1u) * 0x01010101u) >> 7) & 0x01010101u;    // byte j = 1 when e_j > r
+    B.E -= above;
+    B.total -= 1u;
+    return 4u - ((above * 0x01010101u) >> 24);
+}
+
+// Lid pool, one draw (azul.py:79-89): pour the lid into an empty box first.  Returns colour or -1 when no tile is left.
 template <class GT>
 AZB_HD int lid_draw(GT& g, BoxRegs& B, uint32_t& x)
 {
     if (B.total == 0u) {                                          // :81-83
-        B.unpack(g.lid);
+        if (!B.unpack(g.lid)) g.add_status(ST_BAD_IMPORT);
         g.lid = 0u;
         if (B.total == 0u) { g.add_status(ST_BAG_EMPTY); return -1; }   // :86 TODO in the reference
     }
-    const uint32_t r = mulhi(x, B.total);
-    x *= B.total;
-    // colour c <=> e(c-1) <= r < e(c); taking one tile of c lowers every threshold from e(c) on (:89)
-    const uint32_t g0 = r >= B.e0 ? 1u : 0u, g1 = r >= B.e1 ? 1u : 0u, g2 = r >= B.e2 ? 1u : 0u, g3 = r >= B.e3 ? 1u : 0u;
-    B.e0 += g0 - 1u; B.e1 += g1 - 1u; B.e2 += g2 - 1u; B.e3 += g3 - 1u;
-    B.total -= 1u;
-    return (int)(g0 + g1 + g2 + g3);
+    return (int)lid_draw_fast(B, x);
 }
 
 // azul.py:64-89 with the Philox draw schedule (DESIGN.md "RNG schedule"): call j of
@@ -411,7 +468,7 @@ AZB_HD void new_round_philox(Game<P>& g, const Philox& rng, uint32_t gid, uint32
     new_round_header(g);
     constexpr uint32_t CALLS = POOL == POOL_LID ? 3u : 2u;
     BoxRegs B;
-    if (POOL == POOL_LID) B.unpack(g.box);
+    if (POOL == POOL_LID) { if (!B.unpack(g.box)) g.add_status(ST_BAD_IMPORT); }
     AZB_ROLLED
     for (uint32_t j = 0; j < CALLS; j++) {
         uint32_t w[4];
@@ -431,14 +488,22 @@ AZB_HD void new_round_philox(Game<P>& g, const Philox& rng, uint32_t gid, uint32
             }
         } else {
             const uint32_t nh = j == 2u ? 2u : 4u;                // half-displays: words 2i, 2i+1 of display i
-            AZB_ROLLED
-            for (uint32_t q = 0; q < nh; q++) {
-                uint32_t x = q == 0u ? w[0] : q == 1u ? w[1] : q == 2u ? w[2] : w[3];
-                const uint32_t d = 2u * j + (q >> 1) + 1u;
 #pragma unroll
-                for (int t = 0; t < 2; t++) {
-                    const int c = lid_draw(g, B, x);
-                    if (c >= 0) plane_inc(g.pl0, g.pl1, g.pl2, d + 6u * (uint32_t)c);
+            for (uint32_t q = 0; q < 4u; q++) {
+                if (q < nh) {
+                    uint32_t x = w[q];
+                    const uint32_t d = 2u * j + (q >> 1) + 1u;
+                    if (B.total >= 2u) {                          // no refill inside this pair: two unchecked draws
+                        const uint32_t c0 = lid_draw_fast(B, x), c1 = lid_draw_fast(B, x);
+                        plane_inc(g.pl0, g.pl1, g.pl2, d + 6u * c0);
+                        plane_inc(g.pl0, g.pl1, g.pl2, d + 6u * c1);
+                    } else {
+                        AZB_ROLLED
+                        for (int t = 0; t < 2; t++) {
+                            const int c = lid_draw(g, B, x);
+                            if (c >= 0) plane_inc(g.pl0, g.pl1, g.pl2, d + 6u * (uint32_t)c);
+                        }
+                    }
                 }
             }
         }
@@ -757,15 +822,18 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
     // 0 playing, 1 round over: waits for score + refill, 2 waits for a fresh game (stuck / ended on entry)
     int phase = (remaining > 0 && g.ended()) ? 2 : 0;
     words.prefetch(rng, gid, g.steps);
+    uint32_t open[P];                                                 // open_rows of every player, kept current
+#pragma unroll
+    for (int p = 0; p < P; p++) open[p] = open_rows(g, p);
     for (;;) {
         if (remaining > 0 && phase == 0) {
             uint32_t m[6];
-            legal_mask(g, m);
+            legal_mask_open(g, open, m);
             if (m[0] == 0u) {                                         // words 1..5 are subsets of word 0 (the floor takes any source)
                 sink.add(6, 1);                                       // stuck round: abort the game
                 phase = 2;
             } else {
-                apply_move<P, POOL>(g, random_action(m, words.get(rng, gid, g.steps)));   // azul.py:304
+                apply_move_impl<P, POOL, true>(g, random_action(m, words.get(rng, gid, g.steps)), open);   // azul.py:304
                 g.steps += 1u;
                 remaining--;
                 if (is_end_of_round(g)) phase = 1;                    // azul.py:306
@@ -802,6 +870,8 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 const uint32_t bag_before = g.status() & ST_BAG_EMPTY;
                 new_round_philox<P, POOL>(g, rng, gid, purpose);      // azul.py:311 / game_runner.py:80
                 if (!bag_before && (g.status() & ST_BAG_EMPTY)) sink.add(7, 1);
+#pragma unroll
+                for (int p = 0; p < P; p++) open[p] = open_rows(g, p);   // scoring emptied lines and filled the wall
                 words.prefetch(rng, gid, g.steps);                    // the whole warp is here: words for the next round
             }
         } else if (n_movable == 0) {

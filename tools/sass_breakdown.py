@@ -46,7 +46,7 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     # the page holds one section per profiled launch ("Kernel Name" row, header row, one row per instruction):
     # take the first section of the wanted kernel
-    want = re.sub(r"I?L?i(\d+)E?", "", kname).split("I")[0].lstrip("_Z0123456789")
+    want = re.sub(r"I?L?i(\d+)E?", "", kname).split("I")[0].lstrip("_Z0123456789").rstrip("E")
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
     sec = next(((a, b) for a, b in zip(starts, starts[1:]) if want in rows[a][1] and b - a - 2 == len(lines)), None)
     assert sec, ("no section of %d instructions for %s" % (len(lines), want), [(rows[a][1][:40], b - a - 2) for a, b in zip(starts, starts[1:])])
@@ -55,7 +55,7 @@ def main():
     data = rows[sec[0] + 2:sec[1]]
     assert len(data) == len(lines), (len(data), len(lines), "rebuild the library at the profiled commit")
     src = {}
-    for fn in os.listdir(CSRC):
+    for fn in (f for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))):
         src[fn] = open(os.path.join(CSRC, fn)).read().splitlines()
 
     def func_of(f, ln):
