@@ -58,7 +58,7 @@ __global__ void k_legal_mask(const uint32_t* __restrict__ s, int64_t n, uint32_t
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g >= n) return;
     Game<P> gm;
-    gm.pl0 = s[g]; gm.pl1 = s[n + g]; gm.pl2 = s[2 * n + g]; gm.misc = s[3 * n + g];
+    gm.pl0 = s[g]; gm.pl1 = s[n + g]; gm.pl2 = s[2 * n + g]; gm.set_misc_word(s[3 * n + g]);
     const int seat = gm.seat();
 #pragma unroll
     for (int p = 0; p < P; p++) { gm.pat[p] = 0; gm.wall[p] = 0; }
@@ -384,8 +384,8 @@ struct BlockSink {
 // reads 32 consecutive banks.  A round that outlasts them falls back to computing a block in place.
 constexpr int ROUND_WORDS = 16;          // 12 / 16 / 20 words: 3.61 / 3.70 / 3.67e10 env steps/s (rounds last ~10.5 steps; longer ones fall back)
 struct RoundWords {
-    uint32_t* base;          // &buf[threadIdx.x]
-    uint32_t stride;         // blockDim.x
+    uint32_t base;           // shared-window byte address of buf[threadIdx.x] (a generic pointer costs an address conversion per read)
+    uint32_t stride;         // 4 * blockDim.x
     uint32_t first_block;
     uint32_t w[4];
     uint32_t block;
@@ -396,15 +396,20 @@ struct RoundWords {
         for (uint32_t j = 0; j < ROUND_WORDS / 4; j++) {
             uint32_t r[4];
             rng(gid, first_block + j, PURPOSE_ACTION, 0u, r);
-            base[(4 * j + 0) * stride] = r[0]; base[(4 * j + 1) * stride] = r[1];
-            base[(4 * j + 2) * stride] = r[2]; base[(4 * j + 3) * stride] = r[3];
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (4 * j + i) * stride), "r"(r[i]) : "memory");
         }
         block = 0xFFFFFFFFu;
     }
     __device__ __forceinline__ uint32_t get(const Philox& rng, uint32_t gid, uint32_t T)
     {
         const uint32_t idx = T - 4u * first_block;
-        if (idx < (uint32_t)ROUND_WORDS) return base[idx * stride];
+        if (idx < (uint32_t)ROUND_WORDS) {
+            uint32_t v;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(base + idx * stride) : "memory");
+            return v;
+        }
         if (block != (T >> 2)) { block = T >> 2; rng(gid, block, PURPOSE_ACTION, 0u, w); }
         const uint32_t i = T & 3u;
         return i == 0u ? w[0] : i == 1u ? w[1] : i == 2u ? w[2] : w[3];
@@ -427,8 +432,8 @@ __global__ void k_rollout_random(Launch L, int k_steps, int defer, uint32_t* __r
     const Philox rng{L.k0, L.k1};
     BlockSink sink{cnt};
     RoundWords words;
-    words.base = round_words + threadIdx.x;
-    words.stride = blockDim.x;
+    words.base = (uint32_t)__cvta_generic_to_shared(round_words + threadIdx.x);
+    words.stride = 4u * blockDim.x;
     rollout_steps<P, POOL>(gm, rng, L.gid0 + (uint32_t)gl, L.first_rule, k_steps, sink, WarpLanes{}, valid, defer, words);
     if (valid) {
         gm.store(L.state, L.n, g);
@@ -496,7 +501,7 @@ __device__ __forceinline__ void observe_row(const Game<P>& gm, int perspective, 
     for (int c = 0; c < 5; c++) {
         const uint32_t b = (uint32_t)(6 * c);
         obs_store(o, 25 + c, (float)(((gm.pl0 >> b) & 1u) | (((gm.pl1 >> b) & 1u) << 1) | (((gm.pl2 >> b) & 1u) << 2) |
-                            (((gm.misc >> c) & 1u) << 3)));
+                            (((gm.pl3 >> b) & 1u) << 3)));
     }
     obs_store(o, 30, (float)((gm.misc >> 5) & 1u));
     // order = [perspective] + ascending others (game_runner.py:57)

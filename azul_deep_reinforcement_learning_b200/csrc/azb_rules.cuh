@@ -114,7 +114,9 @@ struct Philox {
 // ---- the game in registers ----------------------------------------------------------------
 template <int P>
 struct Game {
-    uint32_t pl0, pl1, pl2, misc, box, lid, steps;
+    // In registers the fourth plane of the centre counts is held spread like the other planes (pl3: bit 6c = bit 3 of the
+    // centre's count of colour c) and MISC[4:0] is zero; load / store convert from / to the packed word.
+    uint32_t pl0, pl1, pl2, pl3, misc, box, lid, steps;
     uint32_t pat[P], wall[P], scf[P], sta[P], stb[P];
 
     static constexpr int WORDS = 7 + 5 * P;
@@ -123,7 +125,7 @@ struct Game {
     AZB_M void load(const uint32_t* __restrict__ s, int64_t stride, int64_t g)
     {
         pl0 = s[0 * stride + g]; pl1 = s[1 * stride + g]; pl2 = s[2 * stride + g];
-        misc = s[3 * stride + g]; box = s[4 * stride + g]; lid = s[5 * stride + g];
+        set_misc_word(s[3 * stride + g]); box = s[4 * stride + g]; lid = s[5 * stride + g];
         steps = s[6 * stride + g];
 #pragma unroll
         for (int p = 0; p < P; p++) {
@@ -135,7 +137,7 @@ struct Game {
     AZB_M void store(uint32_t* __restrict__ s, int64_t stride, int64_t g) const
     {
         s[0 * stride + g] = pl0; s[1 * stride + g] = pl1; s[2 * stride + g] = pl2;
-        s[3 * stride + g] = misc; s[4 * stride + g] = box; s[5 * stride + g] = lid;
+        s[3 * stride + g] = misc_word(); s[4 * stride + g] = box; s[5 * stride + g] = lid;
         s[6 * stride + g] = steps;
 #pragma unroll
         for (int p = 0; p < P; p++) {
@@ -144,6 +146,11 @@ struct Game {
             s[(11 + 5 * p) * stride + g] = stb[p];
         }
     }
+
+    // the packed MISC word <-> misc + pl3
+    AZB_M void set_misc_word(uint32_t w) { misc = w & ~31u; pl3 = ((w & 31u) * 0x00108421u) & 0x01041041u; }
+    AZB_M uint32_t misc_word() const { return misc | ((((pl3 & 0x01041041u) * 0x00108421u) >> 20) & 31u); }
+    AZB_M uint32_t sources() const { return pl0 | pl1 | pl2 | pl3; }    // bit d + 6c: source d holds colour c
 
     AZB_M uint32_t current_player() const { return (misc >> 6) & 7u; }
     AZB_M uint32_t next_first_player() const { return (misc >> 9) & 7u; }
@@ -176,7 +183,7 @@ struct Game {
 template <int P>
 AZB_HD void legal_mask(const Game<P>& g, uint32_t m[6])
 {
-    const uint32_t src = (g.pl0 | g.pl1 | g.pl2 | spread5to6(g.misc & 31u)) & PLANE_MASK;
+    const uint32_t src = g.sources();
     const int s = g.seat();
     const uint32_t pat = g.sel(g.pat, s), wall = g.sel(g.wall, s);
     m[0] = src;
@@ -188,9 +195,10 @@ AZB_HD void legal_mask(const Game<P>& g, uint32_t m[6])
     }
 }
 
-// The destination half of the legal mask as one word per player: bit 5r + c = colour c may still go to pattern line r
-// (the line is empty or holds c, and wall[r][c] is clear; azul.py:171-175).  The rollout keeps these words in registers:
-// a move into line r leaves exactly {c} open there, scoring rebuilds them (rollout_steps).
+// The destination half of the legal mask as one word per player: bit 6c + r = colour c may still go to pattern line r
+// (the line is empty or holds c, and wall[r][c] is clear; azul.py:171-175), so that (open >> r) & M6 is line r's colour
+// set already spread to the source planes' stride.  The rollout keeps these words in registers: a move into line r
+// leaves exactly {c} open there, scoring rebuilds them (rollout_steps).
 template <int P>
 AZB_HD uint32_t open_rows(const Game<P>& g, int pl)
 {
@@ -199,7 +207,7 @@ AZB_HD uint32_t open_rows(const Game<P>& g, int pl)
 #pragma unroll
     for (int r = 0; r < 5; r++) {
         const uint32_t cnt = (pat >> (6 * r + 3)) & 7u, col = (pat >> (6 * r)) & 7u;
-        o |= ((cnt ? (1u << col) : 31u) & ~(wall >> (5 * r)) & 31u) << (5 * r);
+        o |= spread5to6((cnt ? (1u << col) : 31u) & ~(wall >> (5 * r)) & 31u) << r;
     }
     return o;
 }
@@ -207,11 +215,11 @@ AZB_HD uint32_t open_rows(const Game<P>& g, int pl)
 template <int P>
 AZB_HD void legal_mask_open(const Game<P>& g, const uint32_t (&open)[P], uint32_t m[6])
 {
-    const uint32_t src = (g.pl0 | g.pl1 | g.pl2 | spread5to6(g.misc & 31u)) & PLANE_MASK;
+    const uint32_t src = g.sources();
     const uint32_t o = g.sel(open, g.seat());
     m[0] = src;
 #pragma unroll
-    for (int r = 0; r < 5; r++) m[r + 1] = src & (spread5to6((o >> (5 * r)) & 31u) * 63u);
+    for (int r = 0; r < 5; r++) m[r + 1] = src & (((o >> r) & M6) * 63u);
 }
 
 // floors[] += n capped at 7 (azul.py:119-123)
@@ -223,61 +231,71 @@ AZB_HD uint32_t floor_add(uint32_t scf, uint32_t n)
 }
 
 // ---- move (azul.py:118-161); no legality check, like the reference ----
+// p = destination (0 floor, 1..5 pattern line), b = d + 6c = the bit of (source d, colour c) in the planes.
+// Branch-free: a warp holds 32 different games, so "display or centre" and "pattern line or floor" are selects, not
+// branches.  A centre take is the display case with an empty "rest".  Written for the sm_100a integer pipes: bit logic
+// and shifts share one half-rate pipe, multiply-adds run on the other, so sums and left shifts by a common amount are
+// phrased as multiply-adds where that is free.
 template <int P, int POOL, bool TRACK>
-AZB_HD void apply_move_impl(Game<P>& g, uint32_t action, uint32_t* open)
+AZB_HD void apply_move_core(Game<P>& g, uint32_t p, uint32_t b, uint32_t* open)
 {
-    // Branch-free: a warp holds 32 different games, so "display or centre" and "pattern line or floor"
-    // are selects, not branches.  A centre take is the display case with an empty "rest".
-    const uint32_t p = action / 30u, b = action - 30u * p, c = b / 6u, d = b - 6u * c;
+    const uint32_t c = (b * 43u) >> 8, c6 = 6u * c, d = b - c6;       // b < 30: b / 6 == (b * 43) >> 8
     const int s = g.seat();
-    const bool from_display = d != 0u;
-    const uint32_t cbit = 1u << (6u * c);
-    uint32_t n = ((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2) |
-                 (from_display ? 0u : ((g.misc >> c) & 1u) << 3);
+    const bool centre = d == 0u;
+    const uint32_t cbit = 1u << c6;
+    // tiles taken (pl3 only has bits at d = 0)
+    const uint32_t n = ((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2) | (((g.pl3 >> b) & 1u) << 3);
     // azul.py:125-133: the chosen colour leaves, the rest of display d joins the centre -- a bit-sliced
     // 4-bit ripple add over all five colours at once.  azul.py:134-138: from the centre only colour c leaves.
-    const uint32_t rest = from_display ? (M6 & ~cbit) : 0u;
+    const uint32_t others = M6 & ~cbit;
+    const uint32_t rest = centre ? 0u : others, keepc = centre ? others : M6;
     const uint32_t r0 = (g.pl0 >> d) & rest, r1 = (g.pl1 >> d) & rest, r2 = (g.pl2 >> d) & rest;
-    const uint32_t c0 = g.pl0 & M6, c1 = g.pl1 & M6, c2 = g.pl2 & M6, c3 = spread5to6(g.misc & 31u);
-    const uint32_t keepc = from_display ? M6 : (M6 & ~cbit);
-    const uint32_t s0 = c0 ^ r0, k0 = c0 & r0;
-    const uint32_t s1 = c1 ^ r1 ^ k0, k1 = (c1 & r1) | (k0 & (c1 ^ r1));
-    const uint32_t s2 = c2 ^ r2 ^ k1, k2 = (c2 & r2) | (k1 & (c2 ^ r2));
-    const uint32_t s3 = c3 ^ k2;
-    const uint32_t clear = ~((M6 << d) | M6);           // the emptied display (or nothing more, d = 0) and the old centre
-    g.pl0 = (g.pl0 & clear) | (s0 & keepc);
-    g.pl1 = (g.pl1 & clear) | (s1 & keepc);
-    g.pl2 = (g.pl2 & clear) | (s2 & keepc);
-    uint32_t misc = (g.misc & ~31u) | gather6to5(s3 & keepc);
-    // azul.py:139-143: the first-player token goes with the first centre take, onto the floor first
-    const uint32_t tok = from_display ? 0u : (misc >> 5) & 1u;
-    misc &= ~(tok << 5);
-    misc = tok ? ((misc & ~(7u << 9)) | (((misc >> 6) & 7u) << 9)) : misc;
-    g.misc = misc;
+    const uint32_t k0 = g.pl0 & r0;
+    const uint32_t k1 = (g.pl1 & r1) | (k0 & (g.pl1 ^ r1));
+    const uint32_t k2 = (g.pl2 & r2) | (k1 & (g.pl2 ^ r2));
+    const uint32_t clear = ~((M6 << d) | M6);            // the emptied display (or nothing more, d = 0) and the old centre
+    g.pl0 = (g.pl0 & clear) | ((g.pl0 ^ r0) & keepc);
+    g.pl1 = (g.pl1 & clear) | ((g.pl1 ^ r1 ^ k0) & keepc);
+    g.pl2 = (g.pl2 & clear) | ((g.pl2 ^ r2 ^ k1) & keepc);
+    g.pl3 = (g.pl3 ^ k2) & keepc;
+    // azul.py:139-143: the first-player token goes with the first centre take, onto the floor first;
+    // next_first_player [11:9] := current_player [8:6]
+    const uint32_t t32 = centre ? (g.misc & 32u) : 0u;
+    const uint32_t nf_mask = t32 * 112u;                 // 0xE00 when the token moves
+    const uint32_t misc = g.misc ^ t32;
+    g.misc = (misc & ~nf_mask) | ((misc << 3) & nf_mask);
     // azul.py:145-161: fill row p-1 up to its capacity p, the rest (everything when p = 0) falls to the floor
     const bool to_row = p != 0u;
     const uint32_t pat = g.sel(g.pat, s);
-    const uint32_t sh = to_row ? 6u * (p - 1u) : 0u;
+    const uint32_t sh = to_row ? 6u * p - 6u : 0u;
     const uint32_t cnt = (pat >> (sh + 3u)) & 7u;
-    const uint32_t room = to_row ? p - cnt : 0u;        // p >= cnt always
-    const uint32_t placed = n < room ? n : room;
+    const uint32_t room = p - cnt;                       // p >= cnt when to_row
+    const uint32_t placed = to_row ? (n < room ? n : room) : 0u;
     const uint32_t to_floor = n - placed;
-    const uint32_t newcnt = cnt + placed;
-    const uint32_t newpat = (pat & ~(63u << sh)) | ((newcnt ? (c | (newcnt << 3)) : 0u) << sh);
+    const uint32_t pw = 1u << sh;
+    // to_row: cnt + placed >= 1 (a tile was placed, or the line was already full), so the colour is always written
+    const uint32_t newpat = (pat & ~(63u * pw)) | (((cnt + placed) * 8u + c) * pw);
     g.put(g.pat, s, to_row ? newpat : pat);
-    g.put(g.scf, s, floor_add(g.sel(g.scf, s), tok + to_floor));     // azul.py:119-123 (cap 7)
-    if (POOL == POOL_LID) g.lid += to_floor << (6u * c);              // azul.py:156-157,160-161
+    // floors[] += n capped at 7 (azul.py:119-123): both candidates share the score bits, so min() compares the floor fields
+    const uint32_t scf = g.sel(g.scf, s);
+    const uint32_t added = ((t32 >> 5) + to_floor) * 65536u + scf, capped = scf | (7u << 16);
+    g.put(g.scf, s, added < capped ? added : capped);
+    if (POOL == POOL_LID) g.lid += to_floor * cbit;                   // azul.py:156-157,160-161
     if (TRACK) {                                                      // open rows of the mover: line p-1 now takes only c
-        const uint32_t sh5 = to_row ? 5u * (p - 1u) : 0u;
+        const uint32_t pr = 1u << (to_row ? p - 1u : 0u);
 #pragma unroll
         for (int q = 0; q < P; q++) {
             const uint32_t o = open[q];
-            open[q] = (to_row && s == q) ? ((o & ~(31u << sh5)) | (1u << (sh5 + c))) : o;
+            open[q] = (to_row && s == q) ? ((o & ~(M6 * pr)) | (cbit * pr)) : o;
         }
     }
 }
 template <int P, int POOL>
-AZB_HD void apply_move(Game<P>& g, uint32_t action) { apply_move_impl<P, POOL, false>(g, action, nullptr); }
+AZB_HD void apply_move(Game<P>& g, uint32_t action)
+{
+    const uint32_t p = action / 30u;
+    apply_move_core<P, POOL, false>(g, p, action - 30u * p, nullptr);
+}
 
 // azul.py:177-181 (GT: Game<P>, or the factory-count variant's GameV<P,F>, which shares the per-player words)
 template <class GT>
@@ -291,7 +309,7 @@ AZB_HD void next_player(GT& g)
 template <int P>
 AZB_HD bool is_end_of_round(const Game<P>& g)
 {
-    return ((g.pl0 | g.pl1 | g.pl2) & PLANE_MASK) == 0u && (g.misc & 63u) == 0u;
+    return (g.sources() | (g.misc & 32u)) == 0u;
 }
 
 // azul.py:184-191 -- some wall row of some player holds all five colours
@@ -402,8 +420,8 @@ AZB_HD void new_round_header(Game<P>& g)
     for (int p = 0; p < P; p++) g.sta[p] += (s == p) ? 1u : 0u;   // :67 first_player_stats
     g.misc = (g.misc & ~(0xFFFu << 16)) | (((g.turn_counter() + 1u) & 0xFFFu) << 16);   // :68
     g.set_next_first_player(0u);                                  // :69
-    g.misc = (g.misc & ~31u) | 32u;                               // :71 centre empty + token
-    g.pl0 = g.pl1 = g.pl2 = 0u;                                   // :73
+    g.misc |= 32u;                                                // :71 centre empty + token
+    g.pl0 = g.pl1 = g.pl2 = g.pl3 = 0u;                           // :73
 }
 
 // Lid pool: the box for the duration of a refill, held as the four cumulative counts the draw compares against
@@ -535,7 +553,7 @@ AZB_HD void new_round_injected(Game<P>& g, DrawFn draw)
 template <int P, int POOL>
 AZB_HD void init_game(Game<P>& g, uint32_t first_player)
 {
-    g.pl0 = g.pl1 = g.pl2 = 0u;
+    g.pl0 = g.pl1 = g.pl2 = g.pl3 = 0u;
     g.misc = first_player << 9;
     g.box = (POOL == POOL_LID) ? (20u | 20u << 6 | 20u << 12 | 20u << 18 | 20u << 24) : 0u;
     g.lid = 0u;
@@ -591,7 +609,7 @@ AZB_HD bool move_is_legal(const Game<P>& g, uint32_t action)
     // branch-free: a warp tests 32 different games
     const uint32_t a = action < 180u ? action : 0u;
     const uint32_t p = a / 30u, b = a - 30u * p, c = b / 6u;
-    const uint32_t src = (g.pl0 | g.pl1 | g.pl2 | spread5to6(g.misc & 31u)) & PLANE_MASK;
+    const uint32_t src = g.sources();
     const int s = g.seat();
     const uint32_t pat = g.sel(g.pat, s), wall = g.sel(g.wall, s);
     const uint32_t r = p ? p - 1u : 0u, cnt = (pat >> (6u * r + 3u)) & 7u, col = (pat >> (6u * r)) & 7u;
@@ -614,8 +632,9 @@ AZB_HD uint32_t select_bit(uint32_t m, uint32_t k)
 
 // The integer random agent (game_runner.py:87-97): legal floor actions (p = 0) weigh 1, every
 // other legal action 100; the point r = mulhi(word, total) walks words 1..5 first, then word 0.
-// Returns 180 when no action is legal.  Branch-free up to the final bit select.
-AZB_HD uint32_t random_action(const uint32_t m[6], uint32_t word)
+// Yields the action as destination p and plane bit b (action = 30 p + b); false when no action is legal.
+// Branch-free up to the final bit select.
+AZB_HD bool random_action_pb(const uint32_t m[6], uint32_t word, uint32_t& p, uint32_t& b)
 {
     const uint32_t n1 = (uint32_t)popc(m[1]), n2 = (uint32_t)popc(m[2]), n3 = (uint32_t)popc(m[3]),
                    n4 = (uint32_t)popc(m[4]), n5 = (uint32_t)popc(m[5]), n0 = (uint32_t)popc(m[0]);
@@ -625,18 +644,24 @@ AZB_HD uint32_t random_action(const uint32_t m[6], uint32_t word)
     const bool heavy = r < 100u * n_hi;
     const uint32_t kh = r / 100u;                        // rank among the heavy actions
     // word i + 1 holds the kh-th heavy action: the thresholds are monotone, so four predicated overwrites pick the
-    // word and the rank before it (an `i == k ? ... :` chain compiles to a divergent switch)
+    // word, its destination and the rank before it (an `i == k ? ... :` chain compiles to a divergent switch)
     const bool g1 = kh >= e1, g2 = kh >= e2, g3 = kh >= e3, g4 = kh >= e4;
-    const uint32_t i = (uint32_t)g1 + (uint32_t)g2 + (uint32_t)g3 + (uint32_t)g4;
-    uint32_t before = 0u, wh = m[1];
-    before = g1 ? e1 : before; wh = g1 ? m[2] : wh;
-    before = g2 ? e2 : before; wh = g2 ? m[3] : wh;
-    before = g3 ? e3 : before; wh = g3 ? m[4] : wh;
-    before = g4 ? e4 : before; wh = g4 ? m[5] : wh;
+    uint32_t before = 0u, wh = m[1], ph = 1u;
+    before = g1 ? e1 : before; wh = g1 ? m[2] : wh; ph = g1 ? 2u : ph;
+    before = g2 ? e2 : before; wh = g2 ? m[3] : wh; ph = g2 ? 3u : ph;
+    before = g3 ? e3 : before; wh = g3 ? m[4] : wh; ph = g3 ? 4u : ph;
+    before = g4 ? e4 : before; wh = g4 ? m[5] : wh; ph = g4 ? 5u : ph;
     const uint32_t w = heavy ? wh : m[0];
     const uint32_t k = heavy ? kh - before : r - 100u * n_hi;
-    const uint32_t base = heavy ? 30u * (i + 1u) : 0u;
-    return total == 0u ? 180u : base + select_bit(w, k);
+    p = heavy ? ph : 0u;
+    b = select_bit(w, k);
+    return total != 0u;
+}
+// the same as an action index; 180 when no action is legal
+AZB_HD uint32_t random_action(const uint32_t m[6], uint32_t word)
+{
+    uint32_t p, b;
+    return random_action_pb(m, word, p, b) ? 30u * p + b : 180u;
 }
 
 // ---- unpacked record <-> packed game (kernel K7; record layout in layout.py) -----------------
@@ -646,7 +671,7 @@ template <int P, typename Rd>
 AZB_HD bool import_record(Game<P>& g, Rd rd)
 {
     bool ok = true;
-    g.pl0 = g.pl1 = g.pl2 = 0u; g.misc = 0u; g.box = g.lid = 0u;
+    g.pl0 = g.pl1 = g.pl2 = g.pl3 = 0u; g.misc = 0u; g.box = g.lid = 0u;
     for (int i = 0; i < 5; i++)
         for (int c = 0; c < 5; c++) {
             const int32_t n = rd(i * 5 + c);
@@ -659,7 +684,7 @@ AZB_HD bool import_record(Game<P>& g, Rd rd)
         ok &= (n >= 0 && n <= 15);
         const uint32_t b = (uint32_t)(6 * c), v = (uint32_t)n;
         g.pl0 |= (v & 1u) << b; g.pl1 |= ((v >> 1) & 1u) << b; g.pl2 |= ((v >> 2) & 1u) << b;
-        g.misc |= ((v >> 3) & 1u) << c;
+        g.pl3 |= ((v >> 3) & 1u) << b;
     }
     { const int32_t t = rd(30); ok &= (t == 0 || t == 1); g.misc |= (uint32_t)(t & 1) << 5; }
     const int o_pat = 31, o_wall = 31 + 25 * P, o_fl = 31 + 50 * P, o_sc = 31 + 51 * P, o_s = 31 + 52 * P;
@@ -712,7 +737,7 @@ AZB_HD void export_record(const Game<P>& g, Wr wr)
     for (int c = 0; c < 5; c++) {
         const uint32_t b = (uint32_t)(6 * c);
         wr(25 + c, (int32_t)(((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2) |
-                             (((g.misc >> c) & 1u) << 3)));
+                             (((g.pl3 >> b) & 1u) << 3)));
     }
     wr(30, (int32_t)((g.misc >> 5) & 1u));
     const int o_pat = 31, o_wall = 31 + 25 * P, o_fl = 31 + 50 * P, o_sc = 31 + 51 * P, o_s = 31 + 52 * P;
@@ -833,7 +858,9 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 sink.add(6, 1);                                       // stuck round: abort the game
                 phase = 2;
             } else {
-                apply_move_impl<P, POOL, true>(g, random_action(m, words.get(rng, gid, g.steps)), open);   // azul.py:304
+                uint32_t mp, mb;
+                random_action_pb(m, words.get(rng, gid, g.steps), mp, mb);   // m[0] != 0: an action exists
+                apply_move_core<P, POOL, true>(g, mp, mb, open);          // azul.py:304
                 g.steps += 1u;
                 remaining--;
                 if (is_end_of_round(g)) phase = 1;                    // azul.py:306

@@ -175,7 +175,7 @@ __device__ __forceinline__ float obs_value(const Game<2>& g, uint32_t pat_me, ui
     } else if constexpr (IDX < 30) {                  // centre colour counts
         constexpr int c = IDX - 25, b = 6 * c;
         return small_int_to_float(((g.pl0 >> b) & 1u) | (((g.pl1 >> b) & 1u) << 1) | (((g.pl2 >> b) & 1u) << 2) |
-                                  (((g.misc >> c) & 1u) << 3));
+                                  (((g.pl3 >> b) & 1u) << 3));
     } else if constexpr (IDX == 30) {                 // first-player token
         return (g.misc & 32u) ? 1.0f : 0.0f;
     } else if constexpr (IDX < 81) {                  // pattern lines, mine then the opponent's
