@@ -305,8 +305,13 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
         }
         bool round_over = false, moved = false;
         uint32_t status = 0;
+#ifdef AZB_STEP_NOCOMPUTE      // tuning only: the memory path of k_step without the rules
+        if (false) {
+            if (gm.ended()) {
+#else
         if (valid && a != AZB_ACTION_SKIP) {
             if (gm.ended()) {
+#endif
                 status = ST_ENDED;                                        // azul.py:298-299
             } else {
                 if (!move_is_legal(gm, a)) {
@@ -320,12 +325,19 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
                 }
             }
         }
+#ifdef AZB_STEP_NOCOMPUTE
+        moved = valid;
+#endif
         if (fast) {
             // whole lines through the tile; the lanes whose round ended write their interim state and outputs here
             // and the final ones in drain() -- later in program order of this warp, ordered by __syncwarp
             const bool any_moved = __any_sync(0xFFFFFFFFu, moved);
             uint32_t m[6];
+#ifdef AZB_STEP_NOCOMPUTE
+            for (int p = 0; p < 6; p++) m[p] = gm.pl0 + a + p;
+#else
             legal_mask(gm, m);
+#endif
             if (!round_over && !gm.ended() && m[0] == 0u /* words 1..5 are subsets of word 0 */ && gm.current_player() != 0u)
                 status |= ST_STUCK;
             if (any_moved) gm.store(tile, 32, lane);
