@@ -143,7 +143,7 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 #define AZB_STEP_DRAIN_AT 24
 #endif
 #ifndef AZB_STEP_QCAP
-#define AZB_STEP_QCAP 48
+#define AZB_STEP_QCAP 56
 #endif
 #ifndef AZB_STEP_WARPS
 #define AZB_STEP_WARPS 2
@@ -237,142 +237,170 @@ __device__ __forceinline__ void row_flush(const uint32_t* tile, uint32_t* __rest
 
 template <int P, int POOL, int STAGES>
 __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(Launch L, const uint8_t* __restrict__ action,
-                                                           const int8_t* __restrict__ draws, StepOut O, int aligned)
+                                                           const int8_t* __restrict__ draws, StepOut O, int aligned,
+                                                           unsigned int* __restrict__ sched)
 {
     using S = StepSmem<P, STAGES>;
     constexpr int W = S::W, QCAP = STEP_QCAP;
+    static_assert(QCAP >= STEP_DRAIN_AT - 1 + 32, "a row must fit behind a queue that is just below the drain threshold");
     extern __shared__ __align__(16) uint32_t step_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* q = step_smem + (size_t)warp * S::WORDS_PER_WARP;
     uint32_t* tiles = q + S::QUEUE;
     uint32_t* mask_tile = tiles + STAGES * S::TILE;
     const int64_t n_rows = (L.n + 31) / 32;
-    const int64_t warps_total = (int64_t)gridDim.x * STEP_WARPS;
     const Philox rng{L.k0, L.k1};
     int waiting = 0;                                        // warp-uniform: entries in this warp's queue
     const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
-
-    auto drain = [&](int count) {                           // finish `count` (<= 32) games from the tail of the queue
-        if (lane < count) {
-            Game<P> h;
-            uint32_t gidx, st;
-            queue_get<P, QCAP>(q, waiting - count + lane, h, gidx, st);
-            count_score<P, POOL>(h);                                      // azul.py:307
-            if (is_end_of_game(h)) {                                      // azul.py:308-309
-                h.misc |= 1u << 12;
-            } else if (draws) {                                           // azul.py:311
-                const int8_t* d = draws + 20 * (int64_t)gidx;
-                new_round_injected<P, POOL>(h, [&](int k) { return (int)d[k]; });
-            } else {
-                new_round_philox<P, POOL>(h, rng, L.gid0 + gidx, PURPOSE_REFILL);
-            }
-            step_finish<P, POOL>(L, O, h, (int64_t)gidx, st, true, pol_first);
-        }
-        waiting -= count;
-        __syncwarp();
-    };
-    auto row_is_fast = [&](int64_t r) { return aligned && r * 32 + 32 <= L.n; };
     const int64_t lane_off = (int64_t)(lane >> 3) * L.n + 4 * (lane & 7), n4 = 4 * L.n;
 
-    const int64_t row0 = (int64_t)blockIdx.x * STEP_WARPS + warp;
-    // prologue: rows 0 .. STAGES-2 of this warp in flight
+    // Rows are claimed from a device-wide counter (sched[0]), not assigned by stride: a warp's time depends on how many of
+    // its games end their round, and with a fixed assignment the slowest warp set the kernel's tail.  Results do not
+    // depend on which warp steps a game.  The last warp to leave resets the counters for the next launch.
+    auto claim = [&]() -> int64_t {
+        unsigned int r = 0;
+        if (lane == 0) r = atomicAdd(&sched[0], 1u);
+        return (int64_t)__shfl_sync(0xFFFFFFFFu, r, 0);
+    };
+    auto row_is_fast = [&](int64_t r) { return aligned && r * 32 + 32 <= L.n; };
+    // the ring: ring_row[k] = row whose tile is (being) loaded into stage k; rows >= n_rows mean "none"
+    int64_t ring_row[STAGES];
+#pragma unroll
+    for (int k = 0; k < STAGES; k++) ring_row[k] = n_rows;
+    // prologue: STAGES-1 rows of this warp in flight
 #pragma unroll
     for (int k = 0; k < STAGES - 1; k++) {
-        const int64_t r = row0 + k * warps_total;
+        const int64_t r = claim();
+        ring_row[k] = r;
         if (r < n_rows) row_fetch<W>(tiles + k * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4, pol_first);
         cp_async_commit();
     }
     int stage = 0;
-    for (int64_t row = row0; row < n_rows; row += warps_total) {
-        const int64_t g = row * 32 + lane;
-        const bool valid = g < L.n;
-        const bool fast = row_is_fast(row);
-        uint32_t* tile = tiles + stage * S::TILE;
-        {   // refill the tile consumed by the previous iteration; every lane is past its reads of it
+    for (;;) {
+        // the row consumed now (compile-time ring indices: the ring lives in registers)
+        int64_t row = ring_row[0];
+#pragma unroll
+        for (int k = 1; k < STAGES; k++) row = stage == k ? ring_row[k] : row;
+        const bool have_row = row < n_rows;
+        if (have_row) {
+            const int64_t g = row * 32 + lane;
+            const bool valid = g < L.n;
+            const bool fast = row_is_fast(row);
+            uint32_t* tile = tiles + stage * S::TILE;
+            {   // refill the tile consumed by the previous iteration; every lane is past its reads of it
+                __syncwarp();
+                const int64_t r = claim();
+                const int st_fill = stage == 0 ? STAGES - 1 : stage - 1;
+#pragma unroll
+                for (int k = 0; k < STAGES; k++) ring_row[k] = st_fill == k ? r : ring_row[k];
+                if (r < n_rows) row_fetch<W>(tiles + st_fill * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4, pol_first);
+                cp_async_commit();
+            }
+            cp_async_wait<STAGES - 1>();
             __syncwarp();
-            const int64_t r = row + (STAGES - 1) * warps_total;
-            const int st_fill = stage == 0 ? STAGES - 1 : stage - 1;
-            if (r < n_rows) row_fetch<W>(tiles + st_fill * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4, pol_first);
-            cp_async_commit();
-        }
-        cp_async_wait<STAGES - 1>();
-        __syncwarp();
-        Game<P> gm;
-        uint32_t a = AZB_ACTION_SKIP;
-        if (valid) {
-            gm.load(tile, 32, lane);
-            a = fast ? reinterpret_cast<const uint8_t*>(tile + W * 32)[lane] : action[g];
-        }
-        bool round_over = false, moved = false;
-        uint32_t status = 0;
+            Game<P> gm;
+            uint32_t a = AZB_ACTION_SKIP;
+            if (valid) {
+                gm.load(tile, 32, lane);
+                a = fast ? reinterpret_cast<const uint8_t*>(tile + W * 32)[lane] : action[g];
+            }
+            bool round_over = false, moved = false;
+            uint32_t status = 0;
 #ifdef AZB_STEP_NOCOMPUTE      // tuning only: the memory path of k_step without the rules
-        if (false) {
-            if (gm.ended()) {
+            if (false) {
+                if (gm.ended()) {
 #else
-        if (valid && a != AZB_ACTION_SKIP) {
-            if (gm.ended()) {
+            if (valid && a != AZB_ACTION_SKIP) {
+                if (gm.ended()) {
 #endif
-                status = ST_ENDED;                                        // azul.py:298-299
-            } else {
-                if (!move_is_legal(gm, a)) {
-                    status = ST_ILLEGAL;                                  // azul.py:301-302
+                    status = ST_ENDED;                                        // azul.py:298-299
                 } else {
-                    apply_move<P, POOL>(gm, a);                           // azul.py:304
-                    gm.steps += 1u;
-                    moved = true;
-                    round_over = is_end_of_round(gm);                     // azul.py:306
-                    if (!round_over) next_player(gm);                     // azul.py:313
+                    if (!move_is_legal(gm, a)) {
+                        status = ST_ILLEGAL;                                  // azul.py:301-302
+                    } else {
+                        apply_move<P, POOL>(gm, a);                           // azul.py:304
+                        gm.steps += 1u;
+                        moved = true;
+                        round_over = is_end_of_round(gm);                     // azul.py:306
+                        if (!round_over) next_player(gm);                     // azul.py:313
+                    }
                 }
             }
-        }
 #ifdef AZB_STEP_NOCOMPUTE
-        moved = valid;
+            moved = valid;
 #endif
-        if (fast) {
-            // whole lines through the tile; the lanes whose round ended write their interim state and outputs here
-            // and the final ones in drain() -- later in program order of this warp, ordered by __syncwarp
-            const bool any_moved = __any_sync(0xFFFFFFFFu, moved);
-            uint32_t m[6];
+            if (fast) {
+                // whole lines through the tile; the lanes whose round ended write their interim state and outputs here
+                // and the final ones in the drain -- later in program order of this warp, ordered by __syncwarp
+                const bool any_moved = __any_sync(0xFFFFFFFFu, moved);
+                uint32_t m[6];
 #ifdef AZB_STEP_NOCOMPUTE
-            for (int p = 0; p < 6; p++) m[p] = gm.pl0 + a + p;
+                for (int p = 0; p < 6; p++) m[p] = gm.pl0 + a + p;
 #else
-            legal_mask(gm, m);
+                legal_mask(gm, m);
 #endif
-            if (!round_over && !gm.ended() && m[0] == 0u /* words 1..5 are subsets of word 0 */ && gm.current_player() != 0u)
-                status |= ST_STUCK;
-            if (any_moved) gm.store(tile, 32, lane);
-            if (O.mask6) {
+                if (!round_over && !gm.ended() && m[0] == 0u /* words 1..5 are subsets of word 0 */ && gm.current_player() != 0u)
+                    status |= ST_STUCK;
+                if (any_moved) gm.store(tile, 32, lane);
+                if (O.mask6) {
 #pragma unroll
-                for (int p = 0; p < 6; p++) mask_tile[32 * p + lane] = m[p];
-            }
-            __syncwarp();
-            if (any_moved) row_flush<W>(tile, L.state, row * 32, lane, lane_off, n4, pol_last);
-            if (O.mask6) row_flush<6>(mask_tile, O.mask6, row * 32, lane, lane_off, n4, pol_last);
-            if (!round_over) {
-                if (O.preview) {
-                    Game<P> cp = gm;
-                    count_score<P, POOL>(cp);
-#pragma unroll
-                    for (int p = 0; p < P; p++) O.preview[p * L.n + g] = (int16_t)(cp.scf[p] & 0xFFFFu);
+                    for (int p = 0; p < 6; p++) mask_tile[32 * p + lane] = m[p];
                 }
-                if (O.done) O.done[g] = gm.ended() ? 1 : 0;
-                if (O.status) O.status[g] = (uint8_t)(status | gm.status());
+                __syncwarp();
+                if (any_moved) row_flush<W>(tile, L.state, row * 32, lane, lane_off, n4, pol_last);
+                if (O.mask6) row_flush<6>(mask_tile, O.mask6, row * 32, lane, lane_off, n4, pol_last);
+                if (!round_over) {
+                    if (O.preview) {
+                        Game<P> cp = gm;
+                        count_score<P, POOL>(cp);
+#pragma unroll
+                        for (int p = 0; p < P; p++) O.preview[p * L.n + g] = (int16_t)(cp.scf[p] & 0xFFFFu);
+                    }
+                    if (O.done) O.done[g] = gm.ended() ? 1 : 0;
+                    if (O.status) O.status[g] = (uint8_t)(status | gm.status());
+                }
+            } else if (valid && !round_over) {
+                step_finish<P, POOL>(L, O, gm, g, status, moved);
             }
-        } else if (valid && !round_over) {
-            step_finish<P, POOL>(L, O, gm, g, status, moved);
+            const uint32_t over = __ballot_sync(0xFFFFFFFFu, round_over);
+            if (over) {                                                       // waiting < STEP_DRAIN_AT here: the row fits
+                if (round_over) queue_put<P, QCAP>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
+                waiting += __popc(over);
+                __syncwarp();
+            }
+            stage = stage + 1 == STAGES ? 0 : stage + 1;
         }
-        const uint32_t over = __ballot_sync(0xFFFFFFFFu, round_over);
-        if (over) {
-            if (waiting + __popc(over) > QCAP) drain(waiting);            // waiting < STEP_DRAIN_AT here
-            if (round_over) queue_put<P, QCAP>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
-            waiting += __popc(over);
+        // ONE drain site (the pass is ~2 k instructions; three inlined copies did not fit the instruction cache):
+        // a pass runs once STEP_DRAIN_AT games wait, and for whatever is left when the rows have run out
+        if (waiting >= STEP_DRAIN_AT || (!have_row && waiting > 0)) {
+            const int count = waiting < 32 ? waiting : 32;                    // finish `count` games from the tail of the queue
+            if (lane < count) {
+                Game<P> h;
+                uint32_t gidx, st;
+                queue_get<P, QCAP>(q, waiting - count + lane, h, gidx, st);
+                count_score<P, POOL>(h);                                      // azul.py:307
+                if (is_end_of_game(h)) {                                      // azul.py:308-309
+                    h.misc |= 1u << 12;
+                } else if (draws) {                                           // azul.py:311
+                    const int8_t* d = draws + 20 * (int64_t)gidx;
+                    new_round_injected<P, POOL>(h, [&](int k) { return (int)d[k]; });
+                } else {
+                    new_round_philox<P, POOL>(h, rng, L.gid0 + gidx, PURPOSE_REFILL);
+                }
+                step_finish<P, POOL>(L, O, h, (int64_t)gidx, st, true, pol_first);
+            }
+            waiting -= count;
             __syncwarp();
-            if (waiting >= STEP_DRAIN_AT) drain(waiting < 32 ? waiting : 32);
+        } else if (!have_row) {
+            break;
         }
-        stage = stage + 1 == STAGES ? 0 : stage + 1;
     }
     cp_async_wait<0>();
-    if (waiting > 0) drain(waiting);
+    if (lane == 0) {
+        const unsigned int warps_total = gridDim.x * STEP_WARPS;
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == warps_total - 1u) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+    }
 }
 
 // K1+K2+K3+K6 fused: k_steps random-agent env steps per game in one launch
@@ -701,7 +729,7 @@ static int launch_step(const azb_t* h, const Launch& L, const uint8_t* action, c
     int64_t blocks = (rows + STEP_WARPS - 1) / STEP_WARPS;
     const int64_t resident = (int64_t)h->sm_count * per_sm;
     if (blocks > resident) blocks = resident;
-    kern<<<dim3((unsigned)blocks), 32 * STEP_WARPS, smem, stream>>>(L, action, draws, O, aligned);
+    kern<<<dim3((unsigned)blocks), 32 * STEP_WARPS, smem, stream>>>(L, action, draws, O, aligned, h->sched);
     return 0;
 }
 
@@ -735,12 +763,17 @@ int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_p
     h->device = device; h->n_games = n_games; h->players = players; h->tile_pool = tile_pool;
     h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->block_threads_set = 0; h->defer = 32;
     AZB_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    // row counter + exit counter of azb_step's dynamic row schedule (reset by the kernel itself after every launch)
+    e = cudaMalloc(&h->sched, 64);
+    if (e == cudaSuccess) e = cudaMemset(h->sched, 0, 64);
+    if (e != cudaSuccess) { delete h; return azb_fail(AZB_E_CUDA, "scheduler counters: %s", cudaGetErrorString(e)); }
     *out = h;
     return 0;
 }
 
 int azb_destroy(azb_t* h)
 {
+    if (h && h->sched) { cudaSetDevice(h->device); cudaFree(h->sched); }
     delete h;
     return 0;
 }

@@ -18,6 +18,7 @@ struct azb_handle {
     int block_threads_set; // azb_set_block_threads was called: no automatic choice for the rollout kernel
     int defer;             // rollout: games of a warp that must be waiting before the end-of-round pass runs
     int sm_count;
+    unsigned int* sched;   // device: azb_step's row counter and exit counter (one azb_step launch per handle at a time)
 };
 
 int azb_fail(int code, const char* fmt, const char* detail = "");
