@@ -403,6 +403,104 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
     }
 }
 
+// ---- k_step_plain: the same step with plain coalesced loads / stores and occupancy instead of staging ----
+// One game per lane, rows claimed from the device-wide counter, every state word read and written with one 128-byte
+// line per warp instruction straight from / to global memory (a streaming kernel of this access pattern reaches 0.93 of
+// the measured HBM peak: tools/microbench/stream.cu; the cp.async tile ring of k_step 0.77 without any rules work).
+// Latency is hidden by resident warps: the register budget is capped so that 32 (2 players) / 24 / 20 warps fit an SM, and
+// shared memory only holds the warp-private queues of finished rounds.
+#ifndef AZB_STEP_PLAIN
+#define AZB_STEP_PLAIN 0
+#endif
+#ifndef AZB_PLAIN_WARPS
+#define AZB_PLAIN_WARPS 4
+#endif
+constexpr int PLAIN_WARPS = AZB_PLAIN_WARPS;
+template <int P> struct PlainCfg { static constexpr int MINBLOCKS = P == 2 ? 32 / PLAIN_WARPS : P == 3 ? 24 / PLAIN_WARPS : 20 / PLAIN_WARPS; };
+
+template <int P, int POOL>
+__global__ void __launch_bounds__(32 * PLAIN_WARPS, PlainCfg<P>::MINBLOCKS) k_step_plain(Launch L, const uint8_t* __restrict__ action,
+                                                                    const int8_t* __restrict__ draws, StepOut O,
+                                                                    unsigned int* __restrict__ sched)
+{
+    constexpr int W = 7 + 5 * P, QCAP = STEP_QCAP;
+    static_assert(QCAP >= STEP_DRAIN_AT - 1 + 32, "a row must fit behind a queue that is just below the drain threshold");
+    extern __shared__ __align__(16) uint32_t step_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* q = step_smem + (size_t)warp * ((W + 2) * QCAP);
+    const int64_t n_rows = (L.n + 31) / 32;
+    const Philox rng{L.k0, L.k1};
+    int waiting = 0;                                        // warp-uniform: entries in this warp's queue
+    const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+    for (;;) {
+        unsigned int claimed = 0;
+        if (lane == 0) claimed = atomicAdd(&sched[0], 1u);
+        const int64_t row = (int64_t)__shfl_sync(0xFFFFFFFFu, claimed, 0);
+        const bool have_row = row < n_rows;
+        if (have_row) {
+            const int64_t g = row * 32 + lane;
+            const bool valid = g < L.n;
+            Game<P> gm;
+            uint32_t a = AZB_ACTION_SKIP;
+            if (valid) {
+                gm.load(L.state, L.n, g);
+                a = action[g];
+            }
+            bool round_over = false, moved = false;
+            uint32_t status = 0;
+            if (valid && a != AZB_ACTION_SKIP) {
+                if (gm.ended()) {
+                    status = ST_ENDED;                                        // azul.py:298-299
+                } else if (!move_is_legal(gm, a)) {
+                    status = ST_ILLEGAL;                                      // azul.py:301-302
+                } else {
+                    apply_move<P, POOL>(gm, a);                               // azul.py:304
+                    gm.steps += 1u;
+                    moved = true;
+                    round_over = is_end_of_round(gm);                         // azul.py:306
+                    if (!round_over) next_player(gm);                         // azul.py:313
+                }
+            }
+            // the lanes whose round ended write nothing here: the drain writes their final state and outputs, into lines
+            // that the other lanes' stores (L2 evict_last) keep resident until then
+            if (valid && !round_over) step_finish<P, POOL>(L, O, gm, g, status, moved, pol_last);
+            const uint32_t over = __ballot_sync(0xFFFFFFFFu, round_over);
+            if (over) {                                                       // waiting < STEP_DRAIN_AT here: the row fits
+                if (round_over) queue_put<P, QCAP>(q, waiting + __popc(over & ((1u << lane) - 1u)), gm, (uint32_t)g, status);
+                waiting += __popc(over);
+                __syncwarp();
+            }
+        }
+        if (waiting >= STEP_DRAIN_AT || (!have_row && waiting > 0)) {
+            const int count = waiting < 32 ? waiting : 32;                    // finish `count` games from the tail of the queue
+            if (lane < count) {
+                Game<P> h;
+                uint32_t gidx, st;
+                queue_get<P, QCAP>(q, waiting - count + lane, h, gidx, st);
+                count_score<P, POOL>(h);                                      // azul.py:307
+                if (is_end_of_game(h)) {                                      // azul.py:308-309
+                    h.misc |= 1u << 12;
+                } else if (draws) {                                           // azul.py:311
+                    const int8_t* d = draws + 20 * (int64_t)gidx;
+                    new_round_injected<P, POOL>(h, [&](int k) { return (int)d[k]; });
+                } else {
+                    new_round_philox<P, POOL>(h, rng, L.gid0 + gidx, PURPOSE_REFILL);
+                }
+                step_finish<P, POOL>(L, O, h, (int64_t)gidx, st, true, pol_first);
+            }
+            waiting -= count;
+            __syncwarp();
+        } else if (!have_row) {
+            break;
+        }
+    }
+    if (lane == 0) {
+        const unsigned int warps_total = gridDim.x * PLAIN_WARPS;
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == warps_total - 1u) { sched[0] = 0u; sched[1] = 0u; __threadfence(); }
+    }
+}
+
 // K1+K2+K3+K6 fused: k_steps random-agent env steps per game in one launch
 struct BlockSink {
     unsigned long long* c;
@@ -713,23 +811,35 @@ template <int P, int POOL>
 static int launch_step(const azb_t* h, const Launch& L, const uint8_t* action, const int8_t* draws, const StepOut& O,
                        int aligned, cudaStream_t stream)
 {
+#if AZB_STEP_PLAIN
+    (void)aligned;
+    auto kern = k_step_plain<P, POOL>;
+    constexpr int WARPS = PLAIN_WARPS;
+    const size_t smem = (size_t)WARPS * (7 + 5 * P + 2) * STEP_QCAP * sizeof(uint32_t);
+#else
     constexpr int STAGES = P == 2 ? AZB_STEP_STAGES_P2 : 3;       // 2 / 3 / 4 / 5 stages: 183 / 192 / 183 / 198 us for 4.2 M two-player games
     auto kern = k_step<P, POOL, STAGES>;
+    constexpr int WARPS = STEP_WARPS;
     const size_t smem = StepSmem<P, STAGES>::bytes(STEP_WARPS);
+#endif
     static thread_local int per_sm_cached[64] = {0};      // function attributes are per device
     int uncached = 0;
     int& per_sm = h->device < 64 ? per_sm_cached[h->device] : uncached;
     if (per_sm == 0) {
         AZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * STEP_WARPS, smem));
+        AZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS, smem));
         if (per_sm < 1) per_sm = 1;
     }
     const int64_t rows = (h->n_games + 31) / 32;
-    int64_t blocks = (rows + STEP_WARPS - 1) / STEP_WARPS;
+    int64_t blocks = (rows + WARPS - 1) / WARPS;
     const int64_t resident = (int64_t)h->sm_count * per_sm;
     if (blocks > resident) blocks = resident;
-    kern<<<dim3((unsigned)blocks), 32 * STEP_WARPS, smem, stream>>>(L, action, draws, O, aligned, h->sched);
+#if AZB_STEP_PLAIN
+    kern<<<dim3((unsigned)blocks), 32 * WARPS, smem, stream>>>(L, action, draws, O, h->sched);
+#else
+    kern<<<dim3((unsigned)blocks), 32 * WARPS, smem, stream>>>(L, action, draws, O, aligned, h->sched);
+#endif
     return 0;
 }
 
