@@ -853,7 +853,8 @@ AZB_HD void export_record(const Game<P>& g, Wr wr)
 // rows, 12 completed columns, 13 completed colours (seat 0), 14 sum first_player_stats seat 0,
 // 15 sum of all seats' scores.  Sink::add(index, value) receives the increments.
 // `fin` selects the games of the calling group that just ended; Sink::add_group may aggregate the
-// increments of all calling lanes (the kernels reduce them with one REDUX per counter and warp).
+// increments of all calling lanes (the rollout kernel keeps them in registers and reduces them with one REDUX per
+// counter and warp every 256 end-of-round passes: Sink::pass_done() is called by the whole group after each pass).
 template <class GT, typename Sink>
 AZB_HD void tally_finished(const GT& g, Sink& sink, bool fin = true)
 {
@@ -977,6 +978,7 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 for (int p = 0; p < P; p++) open[p] = open_rows(g, p);   // scoring emptied lines and filled the wall
                 words.prefetch(rng, gid, g.steps);                    // the whole warp is here: words for the next round
             }
+            sink.pass_done();                                         // every lane of the group is here
         } else if (n_movable == 0) {
             break;
         }
