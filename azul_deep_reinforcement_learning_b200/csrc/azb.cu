@@ -178,13 +178,21 @@ __device__ __forceinline__ void cp_async16(uint32_t* smem_dst, const uint32_t* g
 __device__ __forceinline__ uint64_t l2_policy_evict_last()
 {
     uint64_t p;
+#ifdef AZB_STEP_NOHINT          // tuning only
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#else
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+#endif
     return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
     uint64_t p;
+#ifdef AZB_STEP_NOHINT          // tuning only
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#else
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
     return p;
 }
 __device__ __forceinline__ void cp_async16_hint(uint32_t* smem_dst, const uint32_t* gsrc, uint64_t policy)
@@ -448,8 +456,14 @@ __global__ void __launch_bounds__(32 * PLAIN_WARPS, PlainCfg<P>::MINBLOCKS) k_st
             }
             bool round_over = false, moved = false;
             uint32_t status = 0;
+#ifdef AZB_STEP_NOCOMPUTE
+            moved = valid; gm.steps += a;
+            if (false) {
+                if (gm.ended()) {
+#else
             if (valid && a != AZB_ACTION_SKIP) {
                 if (gm.ended()) {
+#endif
                     status = ST_ENDED;                                        // azul.py:298-299
                 } else if (!move_is_legal(gm, a)) {
                     status = ST_ILLEGAL;                                      // azul.py:301-302

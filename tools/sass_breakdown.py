@@ -48,7 +48,7 @@ def main():
     # take the first section of the wanted kernel
     want = re.sub(r"I?L?i(\d+)E?", "", kname).split("I")[0].lstrip("_Z0123456789").rstrip("E")
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
-    sec = next(((a, b) for a, b in zip(starts, starts[1:]) if want in rows[a][1] and b - a - 2 == len(lines)), None)
+    sec = next(((a, b) for a, b in zip(starts, starts[1:]) if (want in rows[a][1] or want.split("8")[-1] in rows[a][1]) and b - a - 2 == len(lines)), None)
     assert sec, ("no section of %d instructions for %s" % (len(lines), want), [(rows[a][1][:40], b - a - 2) for a, b in zip(starts, starts[1:])])
     hdr = rows[sec[0] + 1]
     idx = {h: i for i, h in enumerate(hdr)}
