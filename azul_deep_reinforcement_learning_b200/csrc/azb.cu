@@ -154,6 +154,11 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 #ifndef AZB_STEP_STAGES_P2
 #define AZB_STEP_STAGES_P2 4
 #endif
+#ifndef AZB_STEP_CLAIM
+#define AZB_STEP_CLAIM 4
+#endif
+constexpr int STEP_CLAIM = AZB_STEP_CLAIM;         // consecutive rows a warp takes from the device-wide counter at a time
+constexpr int STEP_SCHED_WORDS = 16;               // row counter, exit counter
 constexpr int STEP_DRAIN_AT = AZB_STEP_DRAIN_AT;
 constexpr int STEP_QCAP = AZB_STEP_QCAP;           // a row that would overflow the queue drains it first
 constexpr int STEP_WARPS = AZB_STEP_WARPS;         // warps per block (fine-grained shared-memory occupancy)
@@ -265,10 +270,20 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
     // Rows are claimed from a device-wide counter (sched[0]), not assigned by stride: a warp's time depends on how many of
     // its games end their round, and with a fixed assignment the slowest warp set the kernel's tail.  Results do not
     // depend on which warp steps a game.  The last warp to leave resets the counters for the next launch.
+    // One atomic per ROW bounds the kernel (131,072 atomics on one address per launch of 4.2 M games: 0.59 of the HBM peak,
+    // the memory path alone 0.69), so a ticket is STEP_CLAIM consecutive rows: 2 / 4 / 8 rows 0.68 / 0.70 / 0.69 (larger
+    // tickets bring the tail back; the memory path alone reaches 0.87 with 4).  Measured and rejected: tickets that
+    // shrink towards the end (0.67: the single-row tail is atomic-bound again) and one counter per group of 8 blocks
+    // (0.63 - 0.65: a group's blocks share an SM, so nothing balances the SMs any more).
+    int64_t claim_next = 0, claim_end = 0;
     auto claim = [&]() -> int64_t {
-        unsigned int r = 0;
-        if (lane == 0) r = atomicAdd(&sched[0], 1u);
-        return (int64_t)__shfl_sync(0xFFFFFFFFu, r, 0);
+        if (claim_next == claim_end) {
+            unsigned int r = 0;
+            if (lane == 0) r = atomicAdd(&sched[0], (unsigned int)STEP_CLAIM);
+            claim_next = (int64_t)__shfl_sync(0xFFFFFFFFu, r, 0);
+            claim_end = claim_next + STEP_CLAIM;
+        }
+        return claim_next++;
     };
     auto row_is_fast = [&](int64_t r) { return aligned && r * 32 + 32 <= L.n; };
     // the ring: ring_row[k] = row whose tile is (being) loaded into stage k; rows >= n_rows mean "none"
@@ -908,8 +923,8 @@ int azb_create(azb_t** out, int device, int64_t n_games, int players, int tile_p
     h->first_player = first_player; h->seed = seed; h->game_id_base = game_id_base; h->block_threads = 128; h->block_threads_set = 0; h->defer = 32;
     AZB_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     // row counter + exit counter of azb_step's dynamic row schedule (reset by the kernel itself after every launch)
-    e = cudaMalloc(&h->sched, 64);
-    if (e == cudaSuccess) e = cudaMemset(h->sched, 0, 64);
+    e = cudaMalloc(&h->sched, STEP_SCHED_WORDS * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(h->sched, 0, STEP_SCHED_WORDS * sizeof(unsigned int));
     if (e != cudaSuccess) { delete h; return azb_fail(AZB_E_CUDA, "scheduler counters: %s", cudaGetErrorString(e)); }
     *out = h;
     return 0;
