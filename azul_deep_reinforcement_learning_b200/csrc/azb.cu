@@ -275,48 +275,45 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
     // tickets bring the tail back; the memory path alone reaches 0.87 with 4).  Measured and rejected: tickets that
     // shrink towards the end (0.67: the single-row tail is atomic-bound again) and one counter per group of 8 blocks
     // (0.63 - 0.65: a group's blocks share an SM, so nothing balances the SMs any more).
-    int64_t claim_next = 0, claim_end = 0;
-    auto claim = [&]() -> int64_t {
+    const uint32_t n_rows32 = (uint32_t)n_rows, fast_rows = aligned ? (uint32_t)(L.n / 32) : 0u;   // n_games <= 2^31
+    uint32_t claim_next = 0, claim_end = 0;
+    auto claim = [&]() -> uint32_t {
         if (claim_next == claim_end) {
             unsigned int r = 0;
             if (lane == 0) r = atomicAdd(&sched[0], (unsigned int)STEP_CLAIM);
-            claim_next = (int64_t)__shfl_sync(0xFFFFFFFFu, r, 0);
+            claim_next = __shfl_sync(0xFFFFFFFFu, r, 0);
             claim_end = claim_next + STEP_CLAIM;
         }
         return claim_next++;
     };
-    auto row_is_fast = [&](int64_t r) { return aligned && r * 32 + 32 <= L.n; };
-    // the ring: ring_row[k] = row whose tile is (being) loaded into stage k; rows >= n_rows mean "none"
-    int64_t ring_row[STAGES];
-#pragma unroll
-    for (int k = 0; k < STAGES; k++) ring_row[k] = n_rows;
+    // rows in flight, in the order they were claimed = the order they are consumed (rows >= n_rows mean "none");
+    // the row at the head was loaded into tile `stage`
+    uint32_t in_flight[STAGES - 1];
     // prologue: STAGES-1 rows of this warp in flight
 #pragma unroll
     for (int k = 0; k < STAGES - 1; k++) {
-        const int64_t r = claim();
-        ring_row[k] = r;
-        if (r < n_rows) row_fetch<W>(tiles + k * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4, pol_first);
+        const uint32_t r = claim();
+        in_flight[k] = r;
+        if (r < n_rows32) row_fetch<W>(tiles + k * S::TILE, L.state, action, L.n, (int64_t)r * 32, lane, r < fast_rows, lane_off, n4, pol_first);
         cp_async_commit();
     }
     int stage = 0;
     for (;;) {
-        // the row consumed now (compile-time ring indices: the ring lives in registers)
-        int64_t row = ring_row[0];
-#pragma unroll
-        for (int k = 1; k < STAGES; k++) row = stage == k ? ring_row[k] : row;
-        const bool have_row = row < n_rows;
+        const uint32_t row = in_flight[0];
+        const bool have_row = row < n_rows32;
         if (have_row) {
-            const int64_t g = row * 32 + lane;
+            const int64_t g = (int64_t)row * 32 + lane;
             const bool valid = g < L.n;
-            const bool fast = row_is_fast(row);
+            const bool fast = row < fast_rows;
             uint32_t* tile = tiles + stage * S::TILE;
             {   // refill the tile consumed by the previous iteration; every lane is past its reads of it
                 __syncwarp();
-                const int64_t r = claim();
-                const int st_fill = stage == 0 ? STAGES - 1 : stage - 1;
+                const uint32_t r = claim();
 #pragma unroll
-                for (int k = 0; k < STAGES; k++) ring_row[k] = st_fill == k ? r : ring_row[k];
-                if (r < n_rows) row_fetch<W>(tiles + st_fill * S::TILE, L.state, action, L.n, r * 32, lane, row_is_fast(r), lane_off, n4, pol_first);
+                for (int k = 0; k + 1 < STAGES - 1; k++) in_flight[k] = in_flight[k + 1];
+                in_flight[STAGES - 2] = r;
+                const int st_fill = stage == 0 ? STAGES - 1 : stage - 1;
+                if (r < n_rows32) row_fetch<W>(tiles + st_fill * S::TILE, L.state, action, L.n, (int64_t)r * 32, lane, r < fast_rows, lane_off, n4, pol_first);
                 cp_async_commit();
             }
             cp_async_wait<STAGES - 1>();
@@ -354,7 +351,9 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
 #endif
             if (fast) {
                 // whole lines through the tile; the lanes whose round ended write their interim state and outputs here
-                // and the final ones in the drain -- later in program order of this warp, ordered by __syncwarp
+                // and the final ones in the drain -- later in program order of this warp, ordered by __syncwarp.  (Parking only
+                // (game index, status) and letting the drain read the interim state back from L2 was measured: 0.63 against
+                // 0.71 of the HBM peak -- 17 more registers for the loads in flight and an L2 round trip in every pass)
                 const bool any_moved = __any_sync(0xFFFFFFFFu, moved);
                 uint32_t m[6];
 #ifdef AZB_STEP_NOCOMPUTE
@@ -370,8 +369,8 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
                     for (int p = 0; p < 6; p++) mask_tile[32 * p + lane] = m[p];
                 }
                 __syncwarp();
-                if (any_moved) row_flush<W>(tile, L.state, row * 32, lane, lane_off, n4, pol_last);
-                if (O.mask6) row_flush<6>(mask_tile, O.mask6, row * 32, lane, lane_off, n4, pol_last);
+                if (any_moved) row_flush<W>(tile, L.state, (int64_t)row * 32, lane, lane_off, n4, pol_last);
+                if (O.mask6) row_flush<6>(mask_tile, O.mask6, (int64_t)row * 32, lane, lane_off, n4, pol_last);
                 if (!round_over) {
                     if (O.preview) {
                         Game<P> cp = gm;
