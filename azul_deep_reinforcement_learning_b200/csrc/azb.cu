@@ -335,10 +335,9 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
 #endif
                     status = ST_ENDED;                                        // azul.py:298-299
                 } else {
-                    if (!move_is_legal(gm, a)) {
-                        status = ST_ILLEGAL;                                  // azul.py:301-302
+                    if (!move_if_legal<P, POOL>(gm, a)) {                     // azul.py:301-304
+                        status = ST_ILLEGAL;
                     } else {
-                        apply_move<P, POOL>(gm, a);                           // azul.py:304
                         gm.steps += 1u;
                         moved = true;
                         round_over = is_end_of_round(gm);                     // azul.py:306

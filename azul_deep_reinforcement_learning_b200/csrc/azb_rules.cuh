@@ -671,6 +671,23 @@ AZB_HD bool move_is_legal(const Game<P>& g, uint32_t action)
     return (action < 180u) & source_ok & ((p == 0u) | row_ok);                        // the floor takes anything
 }
 
+// is_legal_move + move for one supplied action (Azul.step, azul.py:301-304): returns false and leaves the game untouched
+// when the action is illegal.  One decode of the action and one pick of the mover's words serve both halves.
+template <int P, int POOL>
+AZB_HD bool move_if_legal(Game<P>& g, uint32_t action)
+{
+    const uint32_t a = action < 180u ? action : 0u;
+    const uint32_t p = a / 30u, b = a - 30u * p, c = (b * 43u) >> 8;
+    const int s = g.seat();
+    const uint32_t pat = g.sel(g.pat, s), wall = g.sel(g.wall, s);
+    const uint32_t r = p ? p - 1u : 0u, cnt = (pat >> (6u * r + 3u)) & 7u, col = (pat >> (6u * r)) & 7u;
+    const bool source_ok = (g.sources() >> b) & 1u;                                   // azul.py:164-169
+    const bool row_ok = ((cnt == 0u) | (col == c)) & !((wall >> (5u * r + c)) & 1u);   // azul.py:171-175
+    const bool legal = (action < 180u) & source_ok & ((p == 0u) | row_ok);            // the floor takes anything
+    if (legal) apply_move_core<P, POOL, false>(g, p, b, nullptr);
+    return legal;
+}
+
 // position of the k-th (0-based) set bit of a 30-bit word; k < popc(m).  Binary search on the popcount of the low half,
 // with the comparison taken from a sign bit and the three updates written as multiply-adds (see "pipe placement").
 #if AZB_SELECT_ARITH
