@@ -31,6 +31,26 @@ static int run_op(int32_t* rec, int op, int a, const int8_t* draws, uint64_t see
         if (g.ended()) { rc = -2; break; }
         legal_mask(g, m);
         if (move_is_legal(g, (uint32_t)a) != action_is_legal(m, (uint32_t)a)) return -99;
+        {   // the rollout's register forms agree with the reference forms at every replayed state:
+            // open-rows words -> the same mask; move_if_legal -> the same verdict and the same move
+            uint32_t open[P], mo[6];
+            for (int p = 0; p < P; p++) open[p] = open_rows(g, p);
+            legal_mask_open(g, open, mo);
+            for (int w = 0; w < 6; w++) if (mo[w] != m[w]) return -98;
+            Game<P> h1 = g, h2 = g;
+            const bool legal = move_if_legal<P, POOL>(h1, (uint32_t)a);
+            if (legal != action_is_legal(m, (uint32_t)a)) return -97;
+            if (legal) {
+                apply_move<P, POOL>(h2, (uint32_t)a);
+                const uint32_t pp = (uint32_t)a / 30u;
+                apply_move_core<P, POOL, true>(g, pp, (uint32_t)a - 30u * pp, open);     // on the game itself: undone below
+                uint32_t w1[Game<P>::WORDS], w2[Game<P>::WORDS], w3[Game<P>::WORDS];
+                h1.store(w1, 1, 0); h2.store(w2, 1, 0); g.store(w3, 1, 0);
+                for (int w = 0; w < Game<P>::WORDS; w++) if (w1[w] != w2[w] || w1[w] != w3[w]) return -96;
+                for (int p = 0; p < P; p++) if (open[p] != open_rows(g, p)) return -95;  // the move kept the open words current
+                import_record<P>(g, [&](int i) { return rec[i]; });                      // back to the pre-move state
+            }
+        }
         if (!action_is_legal(m, (uint32_t)a)) { rc = -1; break; }
         if (draws) advance<P, POOL>(g, (uint32_t)a, [&](Game<P>& gg) { new_round_injected<P, POOL>(gg, [&](int k) { return (int)draws[k]; }); });
         else advance<P, POOL>(g, (uint32_t)a, [&](Game<P>& gg) { new_round_philox<P, POOL>(gg, rng, gid, PURPOSE_REFILL); });
@@ -46,7 +66,11 @@ static int run_op(int32_t* rec, int op, int a, const int8_t* draws, uint64_t see
     case 10: {  // single-action legality test against the full mask, all action bytes
         uint32_t m[6];
         legal_mask(g, m);
-        for (uint32_t b = 0; b < 256; b++) rc += move_is_legal(g, b) != action_is_legal(m, b);
+        for (uint32_t b = 0; b < 256; b++) {
+            rc += move_is_legal(g, b) != action_is_legal(m, b);
+            Game<P> h = g;
+            rc += move_if_legal<P, POOL>(h, b) != action_is_legal(m, b);
+        }
         break;
     }
     case 100: break;   // round trip

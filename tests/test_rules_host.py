@@ -126,6 +126,21 @@ def test_packed_score_preview_and_predicates():
         assert H.op(rec, 2, 0, H.OP_EOG)[0] == int(g.is_end_of_game())
 
 
+def test_box_beyond_127_tiles_is_flagged():
+    """The Lid refill keeps the cumulative box counts in 7-bit fields (a game has 100 tiles): a box that no game can
+    produce is flagged with the bad-import status bit instead of drawing from corrupted thresholds."""
+    from azul_deep_reinforcement_learning_b200.layout import STATUS_BAD_IMPORT
+    players, pool, seed, gid0 = 2, 1, 77, 5
+    L = UnpackedLayout(players)
+    recs = O.fresh_records(4, players, pool, 0, seed, gid0)
+    ok = recs.copy()
+    recs[:, L.box:L.box + 5] = 40                  # 200 tiles in the bag
+    H.rollout(recs, players, pool, 0, seed, gid0, 40)
+    H.rollout(ok, players, pool, 0, seed, gid0, 40)
+    assert (recs[:, L.status] & STATUS_BAD_IMPORT).all()
+    assert not (ok[:, L.status] & STATUS_BAD_IMPORT).any()
+
+
 def test_import_rejects_unrepresentable():
     L = UnpackedLayout(2)
     rec = np.zeros(L.size, np.int32); rec[L.n_players] = 2
