@@ -95,7 +95,9 @@ int azb_legal_mask(azb_t* h, const uint32_t* state, uint32_t* mask6, void* strea
  *   done_out    uint8 [G] end_of_game after the step
  *   status_out  uint8 [G] AZB_ST_* bits of this call plus the sticky ones
  * Any n_games and any buffer alignment work; with n_games % 4 == 0 and 16-byte aligned state / mask6_out / action
- * pointers the rows of 32 games move as 16-byte asynchronous copies and whole-line stores (the fast path). */
+ * pointers the rows of 32 games move as 16-byte asynchronous copies and whole-line stores (the fast path).
+ * The kernel's warps take their rows from a small counter block owned by the handle (allocated by azb_create, reset by
+ * the kernel itself): launch azb_step on ONE stream at a time per handle; other entry points are unaffected. */
 int azb_step(azb_t* h, uint32_t* state, const uint8_t* action, const int8_t* draws20, uint32_t* mask6_out,
              int16_t* preview_out, uint8_t* done_out, uint8_t* status_out, void* stream);
 
