@@ -189,7 +189,7 @@ AZB_HD void new_round_philox_v(GameV<P, F>& g, const Philox& rng, uint32_t gid, 
     new_round_header_v(g);
     constexpr uint32_t CALLS = POOL == POOL_LID ? (2u * F + 3u) / 4u : (F + 3u) / 4u;
     BoxRegs B;
-    if (POOL == POOL_LID) B.unpack(g.box);
+    if (POOL == POOL_LID) { if (!B.unpack(g.box)) g.add_status(ST_BAD_IMPORT); }
     AZB_ROLLED
     for (uint32_t j = 0; j < CALLS; j++) {
         uint32_t w[4];
