@@ -54,7 +54,8 @@ def build(force=False, verbose=False):
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH] + objs)
+    # the link step gets the same -gencode: without it nvcc embeds an (empty) default-architecture device image
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
