@@ -263,16 +263,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = o;
             }
         }
-        // ---- critic head, partial sum over this part's units (before layer 2 reuses TMEM columns 180..191) ----
+        // ---- critic head, partial sum over this part's units.  The critic's hidden units live in TMEM columns 180 + j
+        // (unit = critic_unit(j)); layer 2 reuses columns [0,192), i.e. the first twelve of them: part 0 reads its first
+        // chunk (columns 180..195) now, every other chunk is read WHILE the layer-2 MMAs run (they write other columns) ----
         float value_p = 0.0f;
-#pragma unroll 1
-        for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {      // critic hidden units live in TMEM columns 180 + j, unit = critic_unit(j)
+        auto critic_chunk = [&](int c0) {
             float v[16], ww[16];
             tmem_ld16(tmem_row + HID + c0, v);
             ld16f(vec + V_W2C + c0, ww);
 #pragma unroll
             for (int i = 0; i < 16; i++) value_p = fmaf(fmaxf(v[i], 0.0f), ww[i], value_p);   // the w2c vector is indexed like the columns; zero where no unit lives
-        }
+        };
+        if (part == 0) critic_chunk(0);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -301,6 +303,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             const uint32_t idx = gm.steps & 3u;
             sample_word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
         }
+#pragma unroll 1
+        for (int c0 = part == 0 ? 16 : col0; c0 < col0 + PART_COLS; c0 += 16) critic_chunk(c0);
         mbar_wait(bar2, phase);
         tc_fence_after();
         phase ^= 1;
