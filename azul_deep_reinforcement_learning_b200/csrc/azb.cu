@@ -348,6 +348,9 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
 #ifdef AZB_STEP_NOCOMPUTE
             moved = valid;
 #endif
+#ifdef AZB_STEP_NODRAIN        // tuning only: no game enters the queue of finished rounds (results are wrong)
+            round_over = false;
+#endif
             if (fast) {
                 // whole lines through the tile; the lanes whose round ended write their interim state and outputs here
                 // and the final ones in the drain -- later in program order of this warp, ordered by __syncwarp.  (Parking only
@@ -399,6 +402,7 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
                 Game<P> h;
                 uint32_t gidx, st;
                 queue_get<P, QCAP>(q, waiting - count + lane, h, gidx, st);
+#ifndef AZB_STEP_DRAIN_NOCOMPUTE   // tuning only: the drain's stores without its rules work (results are wrong)
                 count_score<P, POOL>(h);                                      // azul.py:307
                 if (is_end_of_game(h)) {                                      // azul.py:308-309
                     h.misc |= 1u << 12;
@@ -408,6 +412,10 @@ __global__ void __launch_bounds__(32 * STEP_WARPS, AZB_STEP_MINBLOCKS) k_step(La
                 } else {
                     new_round_philox<P, POOL>(h, rng, L.gid0 + gidx, PURPOSE_REFILL);
                 }
+#endif
+#ifdef AZB_STEP_DRAIN_NOSTORE      // tuning only: the drain's rules work without its stores (results are wrong)
+                if (h.steps == 0xFFFFFFF3u)
+#endif
                 step_finish<P, POOL>(L, O, h, (int64_t)gidx, st, true, pol_first);
             }
             waiting -= count;

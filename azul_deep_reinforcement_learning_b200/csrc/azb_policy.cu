@@ -133,7 +133,10 @@ __device__ __forceinline__ RowPart load_part(const float* parts, int slot)
     return rp;
 }
 
-template <int POOL, int MODE>
+// FULL: the single-step entry point (azb_policy_step) with its optional diagnostics -- raw logits and the entropy term;
+// the persistent rollouts (azb_policy_rollout) never ask for either, and the sum of the legal logits that the entropy
+// needs is 2 of the 6.5 instructions per logit of the softmax pass (measured: 31 % of that pass).
+template <int POOL, int MODE, bool FULL>
 __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             float v[16];
             tmem_ld16(tmem_row + c0, v);                               // b2 is already in the accumulator (BIAS_K2)
             const uint32_t bits = (uint32_t)(mybits >> (16 * c)) & 0xFFFFu;
-            if (A.logits_out && valid) {
+            if (FULL && A.logits_out && valid) {
 #pragma unroll
                 for (int i = 0; i < 16; i++)
                     if (c0 + i < ACT) A.logits_out[g * ACT + c0 + i] = v[i];
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 const bool legal = (bits >> i) & 1u;
                 const float l = v[i];
                 v[i] = legal ? l : -INFINITY;
-                sl += legal ? l : 0.0f;
+                if (FULL) sl += legal ? l : 0.0f;
                 if (MODE == 1) { if (v[i] > cm) { cm = v[i]; ci = i; } }      // argmax mode tracks the index
                 else cm = fmaxf(cm, v[i]);
             }
@@ -344,11 +347,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             const float ms2 = ms * LOG2E;
             float sum = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 16; i++) sum += ex2f(fmaf(v[i], LOG2E, -ms2));
+            for (int i = 0; i < 16; i++) { v[i] = ex2f(fmaf(v[i], LOG2E, -ms2)); sum += v[i]; }
+            // sampling mode: the weights 2^(logit - chunk maximum) -- exactly 0 for an illegal action -- replace the logits in
+            // TMEM, so that the inverse-CDF scan below neither repeats the exponentials nor looks at the mask again
+            if (MODE == 0) tmem_st16(tmem_row + c0, v);
             se = se * ex2f(fmaf(mx, LOG2E, -ms2)) + sum;
             cs[c] = sum; cms[c] = ms;
             mx = nm;
         }
+        if (MODE == 0) tc_wait_st();
         {
             const int slot = part * TILE_M + row;
             parts[0 * THREADS + slot] = mx; parts[1 * THREADS + slot] = se; parts[2 * THREADS + slot] = sl;
@@ -399,9 +406,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             const bool mine = owner == part && n_valid > 0;
             const float gm2 = (n_valid > 0 ? gmx : 0.0f) * LOG2E;
             // chunk k: the first whose cumulative weight passes the target; `base` = weight before it (<= target)
-            float wc[3];
+            float sc[3], wc[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) wc[c] = cs[c] * ex2f(fmaf(cms[c], LOG2E, -gm2));
+            for (int c = 0; c < 3; c++) { sc[c] = ex2f(fmaf(cms[c], LOG2E, -gm2)); wc[c] = cs[c] * sc[c]; }
             int k = -1;
             float base = prefix, acc = prefix;
 #pragma unroll
@@ -416,7 +423,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 k = (mybits >> 32) ? 2 : ((mybits >> 16) & 0xFFFFull) ? 1 : 0;
                 base = prefix + (k > 0 ? wc[0] : 0.0f) + (k > 1 ? wc[1] : 0.0f);
             }
-            float vs[16];
+            const float sk = k == 0 ? sc[0] : k == 1 ? sc[1] : sc[2], mk = k == 0 ? cms[0] : k == 1 ? cms[1] : cms[2];
+            float vs[16];                                  // the chunk's weights relative to its own maximum mk (epilogue 2a)
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 float v[16];
@@ -425,20 +433,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
 #pragma unroll
                 for (int i = 0; i < 16; i++) vs[i] = take ? v[i] : vs[i];
             }
-            const uint32_t kb = (uint32_t)(mybits >> (16 * k)) & 0xFFFFu;
-            float cum = base, chosen_l = 0.0f;
+            float cum = base, chosen_e = 1.0f;
             int chosen = -1;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                const bool legal = (kb >> i) & 1u;
-                const bool upd = legal && cum <= target;   // rounding may leave cum <= target to the end: then the chunk's last legal action
+                // an action with weight 0 (illegal, or underflowed) is never chosen; rounding may leave cum <= target to the
+                // end: then the chunk's last action of positive weight
+                const bool upd = vs[i] > 0.0f && cum <= target;
                 chosen = upd ? i : chosen;
-                chosen_l = upd ? vs[i] : chosen_l;
-                // the weight of an illegal column is masked to +0.0 with integer logic: a `legal ? ... : ...` around the SFU op
-                // is compiled to a branch per column (half the lanes idle)
-                const uint32_t keep = 0u - ((kb >> i) & 1u);
-                cum += __uint_as_float(__float_as_uint(ex2f(fmaf(vs[i], LOG2E, -gm2))) & keep);
+                chosen_e = upd ? vs[i] : chosen_e;
+                cum = fmaf(vs[i], sk, cum);
             }
+            const float chosen_l = fmaf(lg2f(chosen_e), LN2, mk);        // the logit back from its weight: l = mk + ln(e)
             if (mine && chosen >= 0) result[row] = make_int2(col0 + 16 * k + chosen, __float_as_int(chosen_l));
         }
         tc_fence_before();
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
                 if (A.value_out) A.value_out[g] = value;
                 if (A.action_out) A.action_out[g] = n_valid > 0 ? (uint8_t)action : (uint8_t)AZB_ACTION_SKIP;
                 if (A.logp_out) A.logp_out[g] = logp;
-                if (A.entropy_out) A.entropy_out[g] = entropy;
+                if (FULL && A.entropy_out) A.entropy_out[g] = entropy;
             }
             if (A.runner_mode) {
                 // NNRunner.run_episode's per-decision record (nn_runner.py:27-45) in compact form: the warp's deciding games take
@@ -656,17 +662,17 @@ __global__ void k_pack_weights(const float* __restrict__ w1a, const float* __res
     }
 }
 
-template <int POOL, int MODE>
+template <int POOL, int MODE, bool FULL>
 static int launch_policy(const PolicyArgs& A, int grid, cudaStream_t stream)
 {
-    AZB_CUDA(cudaFuncSetAttribute(k_policy<POOL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AZB_CUDA(cudaFuncSetAttribute(k_policy<POOL, MODE, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see griddepcontrol in k_policy
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    AZB_CUDA(cudaLaunchKernelEx(&cfg, k_policy<POOL, MODE>, A));
+    AZB_CUDA(cudaLaunchKernelEx(&cfg, k_policy<POOL, MODE, FULL>, A));
     return 0;
 }
 
@@ -712,8 +718,8 @@ int azb_policy_step(azb_t* h, uint32_t* state, const void* packed, int mode, int
     const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     int rc = 0;
-    if (h->tile_pool == AZB_POOL_LID) rc = mode == 0 ? pol::launch_policy<1, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<1, 1>(A, grid, (cudaStream_t)stream);
-    else rc = mode == 0 ? pol::launch_policy<0, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<0, 1>(A, grid, (cudaStream_t)stream);
+    if (h->tile_pool == AZB_POOL_LID) rc = mode == 0 ? pol::launch_policy<1, 0, true>(A, grid, (cudaStream_t)stream) : pol::launch_policy<1, 1, true>(A, grid, (cudaStream_t)stream);
+    else rc = mode == 0 ? pol::launch_policy<0, 0, true>(A, grid, (cudaStream_t)stream) : pol::launch_policy<0, 1, true>(A, grid, (cudaStream_t)stream);
     if (rc) return rc;
     CHECK_LAUNCH();
     return 0;
@@ -745,8 +751,8 @@ int azb_policy_rollout(azb_t* h, uint32_t* state, const void* packed, int mode, 
     const int64_t tiles = (h->n_games + pol::TILE_M - 1) / pol::TILE_M;
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     int rc = 0;
-    if (h->tile_pool == AZB_POOL_LID) rc = mode == 0 ? pol::launch_policy<1, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<1, 1>(A, grid, (cudaStream_t)stream);
-    else rc = mode == 0 ? pol::launch_policy<0, 0>(A, grid, (cudaStream_t)stream) : pol::launch_policy<0, 1>(A, grid, (cudaStream_t)stream);
+    if (h->tile_pool == AZB_POOL_LID) rc = mode == 0 ? pol::launch_policy<1, 0, false>(A, grid, (cudaStream_t)stream) : pol::launch_policy<1, 1, false>(A, grid, (cudaStream_t)stream);
+    else rc = mode == 0 ? pol::launch_policy<0, 0, false>(A, grid, (cudaStream_t)stream) : pol::launch_policy<0, 1, false>(A, grid, (cudaStream_t)stream);
     if (rc) return rc;
     CHECK_LAUNCH();
     return 0;

@@ -135,6 +135,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers (complete when tc_wait_st() returns)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Operand format of both MMAs: IEEE half (fp16), fp32 accumulation.  kind::f16 takes fp16 or bf16 at the same rate; fp16's 11-bit
 // significand keeps the logits within 1e-3 of the fp32 network (bf16: 4e-3), and nothing here comes near its range: observations
@@ -152,6 +165,14 @@ __device__ __forceinline__ float ex2f(float x)
     return y;
 }
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+// log2(x) on the SFU
+__device__ __forceinline__ float lg2f(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // relu + round-to-nearest fp16 (saturating at the largest finite value) + pack of two floats in ONE instruction
 __device__ __forceinline__ uint32_t pack_relu_f16(float lo, float hi)
