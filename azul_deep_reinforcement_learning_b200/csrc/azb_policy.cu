@@ -121,7 +121,8 @@ constexpr int OBS_TILE_BYTES = K1_CHUNKS * M_GROUPS * 128;
 constexpr int OFF_PARTS = OBS_TILE_BYTES;                                // RowPart[PARTS][TILE_M] as 5 words each
 constexpr int PART_WORDS = 5;                                            // m, s, sl, value, amax | n << 8
 constexpr int OFF_RESULT = OFF_PARTS + PARTS * TILE_M * PART_WORDS * 4;  // int2[TILE_M]: sampled action, logit bits
-static_assert(OFF_RESULT + TILE_M * 8 <= A_BYTES, "scratch exceeds the A tile");
+constexpr int OFF_SAMPLE = OFF_RESULT + TILE_M * 8;                      // uint32[TILE_M]: the row's Philox word (computed by part 0)
+static_assert(OFF_SAMPLE + TILE_M * 4 <= A_BYTES, "scratch exceeds the A tile");
 
 __device__ __forceinline__ RowPart load_part(const float* parts, int slot)
 {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
     float* parts = reinterpret_cast<float*>(a_tile + OFF_PARTS);     // [word][part][row]: conflict-free
     int2* result = reinterpret_cast<int2*>(a_tile + OFF_RESULT);
+    uint32_t* sample = reinterpret_cast<uint32_t*>(a_tile + OFF_SAMPLE);
     __shared__ unsigned long long cnt[AZB_N_COUNTERS];
     if (tid < AZB_N_COUNTERS) cnt[tid] = 0ull;
     SmemSink sink{cnt};
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         linear_mask(m, lin);
         const uint64_t mybits = mask_window(lin, col0);
         uint32_t sample_word = 0u;
-        if (MODE == 0) {
+        if (MODE == 0 && part == 0) {                     // one Philox per game, not four: the other parts read it from the scratch
             uint32_t w[4];
             rng(A.gid0 + (uint32_t)gl, gm.steps >> 2, PURPOSE_POLICY, 0u, w);
             const uint32_t idx = gm.steps & 3u;
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             parts[0 * THREADS + slot] = mx; parts[1 * THREADS + slot] = se; parts[2 * THREADS + slot] = sl;
             parts[3 * THREADS + slot] = value_p;
             parts[4 * THREADS + slot] = __int_as_float(amax | (__popcll(mybits) << 8));
-            if (part == 0) result[row] = make_int2(-1, 0);
+            if (part == 0) { result[row] = make_int2(-1, 0); sample[row] = sample_word; }
         }
         tc_fence_before();
         __syncthreads();
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             // target, then the 16-column chunk inside it (from the chunk sums), then a branch-free scan of that chunk only.
             // tcgen05.ld is warp-collective and the chunk differs from lane to lane, so every lane loads its three chunks
             // and keeps the one it needs by selects.
-            const float target = (float)(sample_word >> 8) * (1.0f / 16777216.0f) * gse;
+            const float target = (float)(sample[row] >> 8) * (1.0f / 16777216.0f) * gse;
             int owner = -1;
             float run = 0.0f;
 #pragma unroll
