@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         __syncthreads();
 
         // ---- epilogue 2c: one thread per game publishes the decision and plays the move ----
+        bool issuer = false;                               // warp-uniform: this warp issues the next tile's layer 1 (below)
         if (part == 0) {
             uint32_t action = (uint32_t)gamax;
             float la = gmx;                             // argmax mode, and the fallback if rounding left no part a winner
@@ -534,10 +535,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             // threads of parts 1..3, which meet at a named barrier of their own.
             fence_async_smem();
             asm volatile("bar.sync 1, %0;" ::"n"(THREADS - TILE_M) : "memory");
-            if (tid == TILE_M) issue_layer1();
+            if (warp == TILE_M / 32) {
+                // the issuing warp only ARRIVES at the end-of-tile barrier: nobody waits for the ~300 uniform-datapath
+                // instructions of the issue loop (the other warps go on to the next tile's state loads and meet the MMAs at
+                // their mbarrier), and the warp itself is done with this tile's TMEM and scratch
+                asm volatile("bar.arrive 2, %0;" ::"n"(THREADS) : "memory");
+                if (tid == TILE_M) issue_layer1();
+                issuer = true;
+            }
         }
         // all TMEM reads and scratch reads of this tile are complete before the next tile overwrites them
-        __syncthreads();
+        if (!issuer) asm volatile("bar.sync 2, %0;" ::"n"(THREADS) : "memory");
     }
 
     // ---- the rare, long part of Azul.step for this CTA's own games: the ones flagged above (round over / fresh game) are
