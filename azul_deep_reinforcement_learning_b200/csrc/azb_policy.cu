@@ -225,15 +225,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         // the previous tile's last epilogue and thread 128 issued the MMAs right there (see the end of the loop body): the
         // MMAs start while part 0 still plays the previous tile's moves (+1.4 % decisions/s; building the observation even
         // earlier -- right after layer 2, by all four parts -- and issuing before epilogue 2c was measured and is no faster) ----
+        // (descriptors: the start-address field advances by a constant per k-step and never carries out of its 14 bits -- shared
+        // memory ends below 2^18 bytes -- so the loop is unrolled into one add per descriptor; the rolled loop rebuilt each
+        // descriptor from the byte address, ~35 dependent uniform-datapath instructions per k-step on the one issuing thread)
         auto issue_layer1 = [&]() {
             tc_fence_after();
-#pragma unroll 1
+            const uint64_t ad0 = smem_desc(a_addr, M_GROUPS * 128, 128);
+            const uint64_t ba0 = smem_desc(w1_addr, N1_GROUPS * 128, 128);
+            const uint64_t bc0 = smem_desc(w1_addr + (N1A / 8) * 128, N1_GROUPS * 128, 128);
+#pragma unroll
             for (int s = 0; s < K1 / 16; s++) {
-                const uint64_t ad = smem_desc(a_addr + s * 2 * (M_GROUPS * 128), M_GROUPS * 128, 128);
-                const uint64_t bd_a = smem_desc(w1_addr + s * 2 * (N1_GROUPS * 128), N1_GROUPS * 128, 128);
-                const uint64_t bd_c = smem_desc(w1_addr + (N1A / 8) * 128 + s * 2 * (N1_GROUPS * 128), N1_GROUPS * 128, 128);
-                umma(tmem_base, ad, bd_a, instr_desc(N1A), s > 0);
-                umma(tmem_base + N1A, ad, bd_c, instr_desc(N1C), s > 0);
+                const uint64_t ad = ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4));
+                const uint64_t bo = (uint64_t)(s * ((2 * N1_GROUPS * 128) >> 4));
+                umma(tmem_base, ad, ba0 + bo, instr_desc(N1A), s > 0);
+                umma(tmem_base + N1A, ad, bc0 + bo, instr_desc(N1C), s > 0);
             }
             umma_commit(bar1);
         };
@@ -285,14 +290,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         __syncthreads();
 
         // ---- layer 2 on the tensor cores ----
-        if (tid == 0) {
+        if (tid == 2 * TILE_M) {                           // a warp of part 2: part 0 has the Philox word, warp 4 the layer-1 issue
             tc_fence_after();
-#pragma unroll 1
-            for (int s = 0; s < K2 / 16; s++) {
-                const uint64_t ad = smem_desc(a_addr + s * 2 * (M_GROUPS * 128), M_GROUPS * 128, 128);
-                const uint64_t bd = smem_desc(w2_addr + s * 2 * (N2_GROUPS * 128), N2_GROUPS * 128, 128);
-                umma(tmem_base, ad, bd, instr_desc(N2), s > 0);
-            }
+            const uint64_t ad0 = smem_desc(a_addr, M_GROUPS * 128, 128), bd0 = smem_desc(w2_addr, N2_GROUPS * 128, 128);
+#pragma unroll
+            for (int s = 0; s < K2 / 16; s++)
+                umma(tmem_base, ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4)), bd0 + (uint64_t)(s * ((2 * N2_GROUPS * 128) >> 4)),
+                     instr_desc(N2), s > 0);
             umma_commit(bar2);
         }
         // while the layer-2 MMAs run: everything the epilogue needs that does not depend on the logits -- the legal
