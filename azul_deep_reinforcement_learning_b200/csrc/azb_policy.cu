@@ -106,6 +106,55 @@ __device__ __forceinline__ void finish_game(Game<2>& h, uint32_t gidx, uint32_t 
     if (status_out) status_out[gidx] |= (uint8_t)h.status();
 }
 
+// GameRunner.step's opponent loop (game_runner.py:46-52; opponent_random() in azb_rules.cuh is the one-game form) for the 32
+// games of a warp TOGETHER: every lane makes the same sequence of rule calls on its own game as the one-game form, but a game
+// whose round ended -- by the agent's move (`pending`) or by an opponent move -- waits until no lane of the warp can move any
+// more, and ONE count_score + refill pass serves all of them (the rollout kernel's light / heavy split).  Run one game at a
+// time under divergence, the ~1,300-instruction pass was walked by the warp once for the agent's move and again at every
+// loop iteration in which some lane's opponent move ended a round.  Inactive lanes take part in the votes only.
+template <int POOL>
+__device__ __forceinline__ int32_t opponent_random_warp(Game<2>& h, const Philox& rng, uint32_t gid, bool active, bool pending,
+                                                        uint32_t m[6])
+{
+    int phase = !active ? 2 : pending ? 1 : 0;            // 0 to move, 1 round over: waits for the pass, 2 handed back
+    for (;;) {
+        if (phase == 0) {
+            legal_mask(h, m);
+            if (h.ended()) {
+                phase = 2;
+            } else {
+                const int n_valid = popc(m[0]) + popc(m[1]) + popc(m[2]) + popc(m[3]) + popc(m[4]) + popc(m[5]);
+                if (h.current_player() == 1u && n_valid >= 2) {
+                    phase = 2;                                             // seat 1 decides again (game_runner.py:46)
+                } else if (n_valid == 0) {
+                    h.add_status(ST_STUCK);
+                    phase = 2;
+                } else {
+                    uint32_t w[4];
+                    rng(gid, h.steps >> 2, PURPOSE_ACTION, 0u, w);
+                    const uint32_t idx = h.steps & 3u;
+                    const uint32_t word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
+                    apply_move<2, POOL>(h, random_action(m, word));        // azul.py:304
+                    h.steps += 1u;
+                    if (is_end_of_round(h)) phase = 1;                     // azul.py:306
+                    else next_player(h);                                   // azul.py:313
+                }
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, phase == 0)) continue;
+        if (!__any_sync(0xFFFFFFFFu, phase == 1)) break;
+        if (phase == 1) {
+            count_score<2, POOL>(h);                                       // azul.py:307
+            if (is_end_of_game(h)) h.misc |= 1u << 12;                     // azul.py:308-309
+            else new_round_philox<2, POOL>(h, rng, gid, PURPOSE_REFILL);   // azul.py:311
+            phase = 0;
+        }
+    }
+    Game<2> cp = h;                                                        // game_runner.py:48-50: score preview on a copy
+    count_score<2, POOL>(cp);
+    return (int32_t)(cp.scf[0] & 0xFFFFu) - (int32_t)(cp.scf[1] & 0xFFFFu);
+}
+
 // bits [start, start + 48) of the 180-bit linear mask; start is 0, 48, 96 or 144
 __device__ __forceinline__ uint64_t mask_window(const uint32_t (&lin)[6], int start)
 {
@@ -564,22 +613,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         bool alive = false;
         // (spreading a tile's 128 games over all 16 warps, 8 lanes each, was measured slower: 1.07 vs 0.97 ms per rollout of
         // 16,384 episodes -- the state loads lose their coalescing and every warp still walks the union of its games' paths)
-        for (int64_t j = part; j < my_tiles; j += PARTS) {
+        for (int64_t j = part; j < my_tiles; j += PARTS) {                 // warp-uniform trip count: the opponent loop votes
             const int64_t g = ((int64_t)blockIdx.x + j * gridDim.x) * TILE_M + row;
-            if (g >= A.n) continue;
-            const bool decided = A.flags_rec[(int64_t)it * A.n + g] & 1;
-            if (!decided) { A.reward_rec[(int64_t)it * A.n + g] = 0; continue; }
+            const bool in_range = g < A.n;
+            const int64_t gl2 = in_range ? g : A.n - 1;
+            const bool decided = in_range && (A.flags_rec[(int64_t)it * A.n + gl2] & 1);
+            if (in_range && !decided) A.reward_rec[(int64_t)it * A.n + g] = 0;
             Game<2> h;
-            h.load(A.state, A.n, g);
-            const uint32_t gid = A.gid0 + (uint32_t)g;
-            if (h.misc & FLAG_ROUND_OVER) {
-                h.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
-                count_score<2, POOL>(h);                                  // azul.py:307
-                if (is_end_of_game(h)) h.misc |= 1u << 12;                // azul.py:308-309
-                else new_round_philox<2, POOL>(h, rng, gid, PURPOSE_REFILL);   // azul.py:311
-            }
+            h.load(A.state, A.n, gl2);
+            const uint32_t gid = A.gid0 + (uint32_t)gl2;
+            const bool pending = (h.misc & FLAG_ROUND_OVER) != 0u;
+            if (decided) h.misc &= ~(FLAG_ROUND_OVER | FLAG_FRESH_GAME);
             uint32_t m2[6];
-            const int32_t diff = opponent_random<2, POOL>(h, rng, gid, true, m2);
+            const int32_t diff = opponent_random_warp<POOL>(h, rng, gid, decided, pending, m2);
+            if (!decided) continue;
             h.store(A.state, A.n, g);
             const int32_t before = (int32_t)A.player_score[g];
             A.player_score[g] = (int16_t)diff;                            // game_runner.py:52
