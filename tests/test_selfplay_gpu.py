@@ -255,17 +255,19 @@ def test_persistent_selfplay_rollout_equals_stepwise():
         assert torch.equal(last["action"], got["action"]) and torch.equal(last["logp"], got["logp"])
 
 
-def test_persistent_runner_rollout_equals_episode_loop():
+@pytest.mark.parametrize("n", [700, 148 * 128 + 333])
+def test_persistent_runner_rollout_equals_episode_loop(n):
     """azb_policy_rollout (runner mode: agent decision + opponent loop + reward + record, whole episodes in one launch)
     reproduces run_episodes (one policy launch + one opponent launch per decision): per game the same actions, rewards,
-    decision states and final state; discounted returns equal nn_runner.py:72-75 on those rewards."""
+    decision states and final state; discounted returns equal nn_runner.py:72-75 on those rewards.  The in-kernel opponent
+    loop votes across the warp (one count_score + refill pass per warp), the step-wise launches run one game per thread:
+    a ragged batch of one tile per CTA, and one with two tiles on some CTAs (two parts in the runner phase)."""
     from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
     from azul_deep_reinforcement_learning_b200.engine import PackedPolicy
     from azul_deep_reinforcement_learning_b200.selfplay import (BatchedGameRunner, PersistentEpisodes, discounted_returns,
                                                                  run_episodes)
     torch.manual_seed(6)
     net = ActorCritic(136, 180)
-    n = 700
     a, b = BatchedGameRunner(n, seed=31), BatchedGameRunner(n, seed=31)
     pa, pb = PackedPolicy(a.engine, net), PackedPolicy(b.engine, net)
     eager = run_episodes(a, pa, max_decisions=160, record_obs=True)
