@@ -161,13 +161,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
         // ---- layer 1 ----
         if (tid == 0) {
             tc_fence_after();
-#pragma unroll 1
+            // (unrolled, one add per descriptor and k-step: the start-address field never carries out of its 14 bits; see k_policy)
+            const uint64_t ad0 = smem_desc(a_addr, M_GROUPS * 128, 128);
+            const uint64_t ba0 = smem_desc(w1_addr, N1_GROUPS * 128, 128);
+            const uint64_t bc0 = smem_desc(w1_addr + (N1A / 8) * 128, N1_GROUPS * 128, 128);
+#pragma unroll
             for (int s = 0; s < K1 / 16; s++) {
-                const uint64_t ad = smem_desc(a_addr + s * 2 * (M_GROUPS * 128), M_GROUPS * 128, 128);
-                const uint64_t bd_a = smem_desc(w1_addr + s * 2 * (N1_GROUPS * 128), N1_GROUPS * 128, 128);
-                const uint64_t bd_c = smem_desc(w1_addr + (N1A / 8) * 128 + s * 2 * (N1_GROUPS * 128), N1_GROUPS * 128, 128);
-                umma(tmem_base, ad, bd_a, instr_desc(N1A), s > 0);
-                umma(tmem_base + N1A, ad, bd_c, instr_desc(N1C), s > 0);
+                const uint64_t ad = ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4));
+                const uint64_t bo = (uint64_t)(s * ((2 * N1_GROUPS * 128) >> 4));
+                umma(tmem_base, ad, ba0 + bo, instr_desc(N1A), s > 0);
+                umma(tmem_base + N1A, ad, bc0 + bo, instr_desc(N1C), s > 0);
             }
             umma_commit(bar1);
         }
@@ -230,12 +233,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
         // ---- layer 2 ----
         if (tid == 0) {
             tc_fence_after();
-#pragma unroll 1
-            for (int s = 0; s < K2 / 16; s++) {
-                const uint64_t ad = smem_desc(a_addr + s * 2 * (M_GROUPS * 128), M_GROUPS * 128, 128);
-                const uint64_t bd = smem_desc(w2_addr + s * 2 * (N2_GROUPS * 128), N2_GROUPS * 128, 128);
-                umma(tmem_base, ad, bd, instr_desc(N2), s > 0);
-            }
+            const uint64_t ad0 = smem_desc(a_addr, M_GROUPS * 128, 128), bd0 = smem_desc(w2_addr, N2_GROUPS * 128, 128);
+#pragma unroll
+            for (int s = 0; s < K2 / 16; s++)
+                umma(tmem_base, ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4)), bd0 + (uint64_t)(s * ((2 * N2_GROUPS * 128) >> 4)),
+                     instr_desc(N2), s > 0);
             umma_commit(bar2);
         }
         mbar_wait(bar2, phase);
@@ -348,12 +350,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_update_fwd_bwd(FwdArgs A)
         // MN-major operand (N = hidden unit, contiguous in the image; K = action) -> TMEM [0,192) (the logits are consumed) ----
         if (tid == 0) {
             tc_fence_after();
-#pragma unroll 1
-            for (int s = 0; s < N2 / 16; s++) {
-                const uint64_t ad = smem_desc(a_addr + s * 2 * (M_GROUPS * 128), M_GROUPS * 128, 128);
-                const uint64_t bd = smem_desc(w2_addr + s * 2 * 128, 128, N2_GROUPS * 128);      // LBO: next 8 actions, SBO: next 8 hidden units
-                umma(tmem_base, ad, bd, instr_desc(K2) | (1u << 16), s > 0);
-            }
+            const uint64_t ad0 = smem_desc(a_addr, M_GROUPS * 128, 128);
+            const uint64_t bd0 = smem_desc(w2_addr, 128, N2_GROUPS * 128);                       // LBO: next 8 actions, SBO: next 8 hidden units
+#pragma unroll
+            for (int s = 0; s < N2 / 16; s++)
+                umma(tmem_base, ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4)), bd0 + (uint64_t)(s * ((2 * 128) >> 4)),
+                     instr_desc(K2) | (1u << 16), s > 0);
             umma_commit(bar3);
         }
         // ---- meanwhile, the critic: dHc = dv w2c (Hc > 0) -> HBM;  grad w2c += dv relu(Hc_pre);  grad b2c += dv ----
