@@ -67,6 +67,8 @@ struct PolicyArgs {
 };
 
 constexpr uint32_t PURPOSE_POLICY = 4;
+constexpr int TM_H = 384;                    // tensor-memory columns [384, 480): the fp16 hidden tile, layer 2's A operand
+static_assert(CRITIC_SHIFT + 16 * 10 + 16 <= 192 && TM_H >= N1 + 8 && TM_H + K2 / 2 <= (int)TMEM_COLS, "tensor-memory map");
 // transient MISC bits between k_policy's tile loop and its finishing phase (never visible outside azb_policy_step)
 constexpr uint32_t FLAG_ROUND_OVER = 1u << 28, FLAG_FRESH_GAME = 1u << 29;
 
@@ -199,6 +201,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     int2* result = reinterpret_cast<int2*>(a_tile + OFF_RESULT);
     uint32_t* sample = reinterpret_cast<uint32_t*>(a_tile + OFF_SAMPLE);
     __shared__ unsigned long long cnt[AZB_N_COUNTERS];
+    __shared__ uint64_t bar3_storage;                      // layer 1, critic half (bar1: actor half)
+    const uint32_t bar3 = smem_u32(&bar3_storage);
     if (tid < AZB_N_COUNTERS) cnt[tid] = 0ull;
     SmemSink sink{cnt};
 
@@ -213,6 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     if (tid == 0) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
+        mbar_init(bar3, 1);
         mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -282,14 +287,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             const uint64_t ad0 = smem_desc(a_addr, M_GROUPS * 128, 128);
             const uint64_t ba0 = smem_desc(w1_addr, N1_GROUPS * 128, 128);
             const uint64_t bc0 = smem_desc(w1_addr + (N1A / 8) * 128, N1_GROUPS * 128, 128);
+            // the actor half first, with its own commit: epilogue 1 only needs that half, and since the hidden tile goes to
+            // tensor memory (below) it no longer overwrites the observation tile that the critic half is still reading
 #pragma unroll
-            for (int s = 0; s < K1 / 16; s++) {
-                const uint64_t ad = ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4));
-                const uint64_t bo = (uint64_t)(s * ((2 * N1_GROUPS * 128) >> 4));
-                umma(tmem_base, ad, ba0 + bo, instr_desc(N1A), s > 0);
-                umma(tmem_base + N1A, ad, bc0 + bo, instr_desc(N1C), s > 0);
-            }
+            for (int s = 0; s < K1 / 16; s++)
+                umma(tmem_base, ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4)), ba0 + (uint64_t)(s * ((2 * N1_GROUPS * 128) >> 4)),
+                     instr_desc(N1A), s > 0);
             umma_commit(bar1);
+#pragma unroll
+            for (int s = 0; s < K1 / 16; s++)
+                umma(tmem_base + N1A, ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4)), bc0 + (uint64_t)(s * ((2 * N1_GROUPS * 128) >> 4)),
+                     instr_desc(N1C), s > 0);
+            umma_commit(bar3);
         };
         if (tile == (int64_t)blockIdx.x) {
             fence_async_smem();
@@ -304,48 +313,49 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         mbar_wait(bar1, phase);
         tc_fence_after();
 
-        // ---- epilogue 1: actor hidden -> relu -> fp16 -> shared memory (layer-2 A operand, aliases the obs tile) ----
+        // ---- epilogue 1: actor hidden -> relu -> fp16 -> TENSOR memory columns [TM_H, TM_H + 96): the layer-2 A operand
+        // (row = lane, two hidden units per column).  Shared memory could only hold it on top of the observation tile ----
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + PART_COLS; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_row + c0, v);                               // b1 is already in the accumulator (BIAS_K1)
+            uint32_t o[8];
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                uint4 o;
-                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int j = c0 + 8 * q + 2 * e;                  // hidden unit (even, so j and j + 1 are both < or >= 180)
-                    ow[e] = j < HID ? pack_relu_f16(v[8 * q + 2 * e], v[8 * q + 2 * e + 1])
-                                    : (j == BIAS_K2 ? 0x3C003C00u : 0u);   // the two constant-one units that carry b2
-                }
-                *reinterpret_cast<uint4*>(a_tile + (((c0 >> 3) + q) * M_GROUPS + (row >> 3)) * 128 + (row & 7) * 16) = o;
+            for (int e = 0; e < 8; e++) {
+                const int j = c0 + 2 * e;                              // hidden unit (even, so j and j + 1 are both < or >= 180)
+                o[e] = j < HID ? pack_relu_f16(v[2 * e], v[2 * e + 1])
+                               : (j == BIAS_K2 ? 0x3C003C00u : 0u);    // the two constant-one units that carry b2
             }
+            tmem_st8(tmem_row + TM_H + (c0 >> 1), o);
         }
-        // ---- critic head, partial sum over this part's units.  The critic's hidden units live in TMEM columns 180 + j
-        // (unit = critic_unit(j)); layer 2 reuses columns [0,192), i.e. the first twelve of them: part 0 reads its first
-        // chunk (columns 180..195) now, every other chunk is read WHILE the layer-2 MMAs run (they write other columns) ----
+        // ---- critic head, partial sum over this part's units.  Critic units 176..179 sit in columns 180..183 of the ACTOR
+        // half (which layer 2 overwrites): part 0 reads them now; units 0..175 are columns [192,368) of the critic half, read
+        // in eleven 16-column chunks WHILE the layer-2 MMAs run (part 0 two, parts 1..3 three each) ----
         float value_p = 0.0f;
-        auto critic_chunk = [&](int c0) {
+        auto critic_chunk = [&](int k) {                               // columns 192 + 16 k .. + 15 = units 16 k .. + 15
             float v[16], ww[16];
-            tmem_ld16(tmem_row + HID + c0, v);
-            ld16f(vec + V_W2C + c0, ww);
+            tmem_ld16(tmem_row + N1A + 16 * k, v);
+            ld16f(vec + V_W2C + CRITIC_SHIFT + 16 * k, ww);
 #pragma unroll
-            for (int i = 0; i < 16; i++) value_p = fmaf(fmaxf(v[i], 0.0f), ww[i], value_p);   // the w2c vector is indexed like the columns; zero where no unit lives
+            for (int i = 0; i < 16; i++) value_p = fmaf(fmaxf(v[i], 0.0f), ww[i], value_p);
         };
-        if (part == 0) critic_chunk(0);
-        fence_async_smem();
+        if (part == 0) {
+            float v[16];
+            tmem_ld16(tmem_row + HID - 4, v);                          // columns 176..191: [4..7] are critic units 176..179
+#pragma unroll
+            for (int i = 0; i < 4; i++) value_p = fmaf(fmaxf(v[4 + i], 0.0f), vec[V_W2C + i], value_p);
+        }
+        tc_wait_st();
         tc_fence_before();
         __syncthreads();
 
-        // ---- layer 2 on the tensor cores ----
+        // ---- layer 2 on the tensor cores: A from tensor memory ----
         if (tid == 2 * TILE_M) {                           // a warp of part 2: part 0 has the Philox word, warp 4 the layer-1 issue
             tc_fence_after();
-            const uint64_t ad0 = smem_desc(a_addr, M_GROUPS * 128, 128), bd0 = smem_desc(w2_addr, N2_GROUPS * 128, 128);
+            const uint64_t bd0 = smem_desc(w2_addr, N2_GROUPS * 128, 128);
 #pragma unroll
             for (int s = 0; s < K2 / 16; s++)
-                umma(tmem_base, ad0 + (uint64_t)(s * ((2 * M_GROUPS * 128) >> 4)), bd0 + (uint64_t)(s * ((2 * N2_GROUPS * 128) >> 4)),
-                     instr_desc(N2), s > 0);
+                umma_ts(tmem_base, tmem_base + TM_H + 8 * s, bd0 + (uint64_t)(s * ((2 * N2_GROUPS * 128) >> 4)), instr_desc(N2), s > 0);
             umma_commit(bar2);
         }
         // while the layer-2 MMAs run: everything the epilogue needs that does not depend on the logits -- the legal
@@ -361,8 +371,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             const uint32_t idx = gm.steps & 3u;
             sample_word = idx == 0u ? w[0] : idx == 1u ? w[1] : idx == 2u ? w[2] : w[3];
         }
+        mbar_wait(bar3, phase);                            // the critic half of layer 1 (long done: it ran under epilogue 1)
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = part == 0 ? 16 : col0; c0 < col0 + PART_COLS; c0 += 16) critic_chunk(c0);
+        for (int k = part == 0 ? 0 : 3 * part - 1; k < 3 * part + 2; k++) critic_chunk(k);
         mbar_wait(bar2, phase);
         tc_fence_after();
         phase ^= 1;
