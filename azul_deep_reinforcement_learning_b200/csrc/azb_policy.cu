@@ -260,18 +260,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     for (; it < A.k_decisions; it++) {
     // software pipeline over tiles: the next tile's state is loaded during this tile's epilogues and its observation
     // is built by parts 1..3 while part 0 plays this tile's moves
-    Game<2> nxt;
+    // (the next tile's state is held as the 17 RAW words: Game::load unpacks the MISC word on the spot, and that first use
+    // made every thread sit out the L2 round trip right behind the loads -- 3 % of the kernel's stall samples)
+    uint32_t nraw[Game<2>::WORDS];
+    auto load_raw = [&](int64_t g1) {
+#pragma unroll
+        for (int i = 0; i < Game<2>::WORDS; i++) nraw[i] = A.state_in[i * A.n + g1];
+    };
     if ((int64_t)blockIdx.x < tiles) {
         const int64_t g0 = (int64_t)blockIdx.x * TILE_M + row;
-        nxt.load(A.state_in, A.n, g0 < A.n ? g0 : A.n - 1);
-        build_obs_tile(nxt, a_tile, row, part);
+        load_raw(g0 < A.n ? g0 : A.n - 1);
+        Game<2> first;
+        first.load(nraw, 1, 0);
+        build_obs_tile(first, a_tile, row, part);
     }
     if (it == 0) mbar_wait(bar_w, 0);                     // weights and vectors have landed (every thread reads the vectors)
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t g = tile * TILE_M + row;
         const bool valid = g < A.n;
         const int64_t gl = valid ? g : A.n - 1;
-        Game<2> gm = nxt;
+        Game<2> gm;
+        gm.load(nraw, 1, 0);
         const bool has_next = tile + gridDim.x < tiles;
 
         // ---- layer 1 on the tensor cores.  For the first tile of a decision round the observation was built by all four
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
         }
         if (has_next) {                                    // in flight while the epilogues run
             const int64_t g2 = (tile + gridDim.x) * TILE_M + row;
-            nxt.load(A.state_in, A.n, g2 < A.n ? g2 : A.n - 1);
+            load_raw(g2 < A.n ? g2 : A.n - 1);
         }
         mbar_wait(bar1, phase);
         tc_fence_after();
@@ -593,6 +602,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             }
         }
         else if (has_next) {
+            Game<2> nxt;
+            nxt.load(nraw, 1, 0);
             build_obs_tile_3(nxt, a_tile, row, part);      // writes [0, OBS_TILE_BYTES): the scratch above it stays intact
             // Layer 1 of the NEXT tile starts now, while part 0 still publishes and plays this tile's moves: nobody reads
             // TMEM any more (every thread passed the barrier after epilogue 2b behind a tcgen05 fence; part 0 works from
