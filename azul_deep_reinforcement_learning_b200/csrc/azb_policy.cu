@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
     uint32_t phase = 0;
     const int64_t tiles = (A.n + TILE_M - 1) / TILE_M;
     const int col0 = part * PART_COLS;                 // this thread's 48 epilogue columns
+    auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + (warp & 3)), "n"(TILE_M) : "memory"); };
 
     // Persistent form: a CTA owns the tiles blockIdx.x + j * gridDim.x for the whole launch and takes k_decisions decisions for
     // each of their games; between decisions the packed state stays in global memory (L2-resident: 68 B per game), written and
@@ -440,7 +441,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             if (part == 0) { result[row] = make_int2(-1, 0); sample[row] = sample_word; }
         }
         tc_fence_before();
-        __syncthreads();
+        // the scratch is exchanged between the four threads of a ROW only: the four warps that share rows 32 q .. 32 q + 31
+        // (warps q, q + 4, q + 8, q + 12) meet at a named barrier of their own instead of waiting for all sixteen
+        quad_sync();
 
         // ---- epilogue 2b: merge the four parts of the row (every thread of the row computes the same numbers) ----
         float gmx = -INFINITY, gsl = 0.0f, value = vec[V_B2C];
@@ -524,7 +527,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_policy(PolicyArgs A)
             if (mine && chosen >= 0) result[row] = make_int2(col0 + 16 * k + chosen, __float_as_int(chosen_l));
         }
         tc_fence_before();
-        __syncthreads();
+        quad_sync();                                       // (the layer-1 issue below still follows a barrier of ALL part 1..3 warps,
+                                                           // each of which has met its part-0 warp here: every TMEM read is over)
 
         // ---- epilogue 2c: one thread per game publishes the decision and plays the move ----
         bool issuer = false;                               // warp-uniform: this warp issues the next tile's layer 1 (below)
