@@ -138,7 +138,8 @@ __device__ __forceinline__ void step_finish(const Launch& L, const StepOut& O, G
 
 // games waiting in a warp's queue that trigger a pass: fuller passes cost fewer instructions, earlier passes patch lines that
 // are still in L2 (measured 16 / 20 / 24 / 28 / 32: 201 / 191 / 183 / 186 / 196 us for 4.2 M two-player games)
-// (the AZB_STEP_* macros exist for tuning sweeps: tools/sweep_step.sh builds variants of the library with -D)
+// (the AZB_STEP_* macros exist for tuning sweeps: tools/build_variant.py builds variants of the library with -D,
+// tools/sweep_step.sh benches them through AZB_LIB)
 #ifndef AZB_STEP_DRAIN_AT
 #define AZB_STEP_DRAIN_AT 24
 #endif

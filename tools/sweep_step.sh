@@ -1,4 +1,5 @@
 #!/bin/bash
+# usage: python tools/build_variant.py NAME -D...; gpurun -- bash tools/sweep_step.sh NAME...
 # step bench (2 players unless PLAYERS is set) for every variant library named on the command line
 for v in "$@"; do
   for p in ${PLAYERS:-2}; do
