@@ -609,8 +609,11 @@ struct RoundWords {
     }
 };
 
+#ifndef AZB_ROLLOUT_BOUNDS
+#define AZB_ROLLOUT_BOUNDS
+#endif
 template <int P, int POOL>
-__global__ void k_rollout_random(Launch L, int k_steps, int defer, uint32_t* __restrict__ mask6_out,
+__global__ void AZB_ROLLOUT_BOUNDS k_rollout_random(Launch L, int k_steps, int defer, uint32_t* __restrict__ mask6_out,
                                  unsigned long long* __restrict__ counters)
 {
     extern __shared__ uint32_t round_words[];          // [ROUND_WORDS][blockDim.x]
@@ -637,6 +640,108 @@ __global__ void k_rollout_random(Launch L, int k_steps, int defer, uint32_t* __r
             store_mask(mask6_out, L.n, g, m);
         }
     }
+    __syncthreads();
+    if (counters && threadIdx.x < AZB_N_COUNTERS && cnt[threadIdx.x]) atomicAdd(&counters[threadIdx.x], cnt[threadIdx.x]);
+}
+
+// ---- k_rollout_rotate: the same rollout with the 32-game batches ROTATING through the warps of the block ----
+// A batch resident in one wave gives every SM one block; with 14 batches per block (65,536 games on 148 SMs) the four warp
+// schedulers of an SM hold 4, 4, 3 and 3 warps, every game runs the same number of steps, and the warps on the fuller
+// schedulers set the kernel's time (8.7 % of all warp samples sat at the barrier before EXIT; per warp the 14-warp block is no
+// faster than a 16-warp one).  No static placement fixes 14 on 4.  Here the block has two warps more than batches: a warp
+// plays its batch for `passes_per_turn` end-of-round passes, then -- if the next warp of the ring is idle -- parks the batch
+// (packed states, steps left) in that warp's shared-memory slot and becomes idle itself.  The two idle slots travel backwards
+// round the ring, the batches forwards: every batch spends its time on fuller and emptier schedulers alike, and so does
+// every scheduler.  Results cannot depend on it: a game's trajectory depends on its id and step counter only.
+__device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_shared_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+
+template <int P, int POOL>
+__global__ void __launch_bounds__(512) k_rollout_rotate(Launch L, int k_steps, int defer, uint32_t* __restrict__ mask6_out,
+                                                        unsigned long long* __restrict__ counters, int batches_per_block,
+                                                        int passes_per_turn)
+{
+    constexpr int W = Game<P>::WORDS;
+    extern __shared__ uint32_t rot_smem[];             // [ROUND_WORDS][blockDim.x] action words, then [warps][W + 1][32] parked batches
+    __shared__ unsigned long long cnt[AZB_N_COUNTERS];
+    __shared__ uint32_t slot_state[16];                // 0 playing, 1 idle, 3 a batch is parked in this warp's slot
+    __shared__ uint32_t slot_batch[16];
+    __shared__ uint32_t n_done;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = (int)(blockDim.x >> 5);
+    uint32_t* park = rot_smem + ROUND_WORDS * blockDim.x;
+    const int64_t block_g0 = blockIdx.x * (int64_t)(32 * batches_per_block);
+    const int64_t games_here = L.n - block_g0 < 32 * batches_per_block ? L.n - block_g0 : 32 * batches_per_block;
+    const uint32_t n_batches = (uint32_t)((games_here + 31) / 32);
+    if (threadIdx.x < AZB_N_COUNTERS) cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 16) slot_state[threadIdx.x] = (uint32_t)threadIdx.x < n_batches ? 0u : 1u;
+    if (threadIdx.x == 0) n_done = 0u;
+    __syncthreads();
+    const Philox rng{L.k0, L.k1};
+    BlockSink sink(cnt);
+    RoundWords words;
+    words.base = (uint32_t)__cvta_generic_to_shared(rot_smem + threadIdx.x);
+    words.stride = 4u * blockDim.x;
+    Game<P> gm;
+    bool have = (uint32_t)warp < n_batches;
+    uint32_t batch = (uint32_t)warp;
+    int remaining = 0;
+    int64_t g = block_g0 + 32 * (int64_t)batch + lane;
+    bool valid = have && g < L.n;
+    int64_t gl = g < L.n ? g : L.n - 1;
+    if (have) { gm.load(L.state, L.n, gl); remaining = valid ? k_steps : 0; }
+    const int succ = warp + 1 == warps ? 0 : warp + 1;
+    for (;;) {
+        if (have) {
+            remaining = rollout_steps<P, POOL, true>(gm, rng, L.gid0 + (uint32_t)gl, L.first_rule, remaining, sink, WarpLanes{}, valid, defer,
+                                                     words, passes_per_turn);
+            if (!__any_sync(0xFFFFFFFFu, remaining > 0)) {                    // the batch has run all its steps
+                if (valid) {
+                    gm.store(L.state, L.n, g);
+                    if (mask6_out) {
+                        uint32_t m[6];
+                        legal_mask(gm, m);
+                        store_mask(mask6_out, L.n, g, m);
+                    }
+                }
+                have = false;
+                __syncwarp();
+                if (lane == 0) { atomicAdd(&n_done, 1u); __threadfence_block(); st_shared_volatile(&slot_state[warp], 1u); }
+            } else if (ld_shared_volatile(&slot_state[succ]) == 1u) {         // the next warp is idle: the batch moves on
+                uint32_t* dst = park + (size_t)succ * (W + 1) * 32;
+                gm.store(dst, 32, lane);
+                dst[W * 32 + lane] = (uint32_t)remaining;
+                if (lane == 0) slot_batch[succ] = batch;
+                __threadfence_block();
+                __syncwarp();
+                have = false;
+                if (lane == 0) { st_shared_volatile(&slot_state[succ], 3u); st_shared_volatile(&slot_state[warp], 1u); }
+            }
+        } else {
+            uint32_t s = 0u;
+            if (lane == 0) {
+                for (;;) {
+                    s = ld_shared_volatile(&slot_state[warp]);
+                    if (s == 3u) break;
+                    if (ld_shared_volatile(&n_done) >= n_batches) break;      // every batch has finished: none can arrive
+                    __nanosleep(400);
+                }
+            }
+            s = __shfl_sync(0xFFFFFFFFu, s, 0);
+            if (s != 3u) break;
+            __threadfence_block();
+            const uint32_t* src = park + (size_t)warp * (W + 1) * 32;
+            gm.load(src, 32, lane);
+            remaining = (int)src[W * 32 + lane];
+            batch = slot_batch[warp];
+            g = block_g0 + 32 * (int64_t)batch + lane;
+            valid = g < L.n;
+            gl = valid ? g : L.n - 1;
+            __syncwarp();
+            if (lane == 0) st_shared_volatile(&slot_state[warp], 0u);
+            have = true;
+        }
+    }
+    sink.flush();
     __syncthreads();
     if (counters && threadIdx.x < AZB_N_COUNTERS && cnt[threadIdx.x]) atomicAdd(&counters[threadIdx.x], cnt[threadIdx.x]);
 }
@@ -1025,6 +1130,24 @@ int azb_rollout_random(azb_t* h, uint32_t* state, int k_steps, uint32_t* mask6_o
             threads = 128;
         }
     }
+#ifndef AZB_ROLLOUT_NO_ROTATE
+#ifndef AZB_ROTATE_PASSES
+#define AZB_ROTATE_PASSES 32      // 1 / 2 / 4 / 8 / 16 / 24 / 32 / 64 / 128 passes per turn: 2.96 / 4.06 / 4.54 / 4.75 / 4.82 / 4.87 / 4.85 / 4.84 / 4.88e10 env steps/s (never: 4.67)
+#endif
+    // one block per SM whose 32-game batches spread 4, 4, 3, 3 (or 3, 3, 2, 2, ...) over the warp schedulers: two warps more than
+    // batches, and the batches rotate (k_rollout_rotate)
+    if (!h->block_threads_set && h->defer >= 32 && (threads / 32) % 4 == 2 && threads + 64 <= 512 && k_steps > 0 &&
+        (h->n_games + threads - 1) / threads <= h->sm_count) {
+        const int launch_threads = threads + 64;
+        const size_t smem = ((size_t)ROUND_WORDS * launch_threads + (size_t)(launch_threads / 32) * (7 + 5 * h->players + 1) * 32) * sizeof(uint32_t);
+        const dim3 rgrid((unsigned)((h->n_games + threads - 1) / threads));
+        DISPATCH_PP(h, AZB_CUDA(cudaFuncSetAttribute(k_rollout_rotate<P, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)));
+        DISPATCH_PP(h, (k_rollout_rotate<P, POOL><<<rgrid, launch_threads, smem, (cudaStream_t)stream>>>(
+                           L, k_steps, h->defer, mask6_out, counters, threads / 32, AZB_ROTATE_PASSES)));
+        CHECK_LAUNCH();
+        return 0;
+    }
+#endif
     const size_t words_bytes = (size_t)ROUND_WORDS * threads * sizeof(uint32_t);
     if (words_bytes > 48 * 1024) return azb_fail(AZB_E_INVALID, "block threads too large for the rollout kernel's word buffer%s");
     const dim3 grid((unsigned)((h->n_games + threads - 1) / threads));

@@ -931,11 +931,16 @@ struct WarpLanes {
 //          warp only once `defer` of its games are waiting for it (or nothing else can move).
 // A game that finished its round simply waits for the next heavy pass; its trajectory, and so every
 // result, is independent of `defer` and of which games share its warp.
-template <int P, int POOL, typename Sink, typename Vote, typename Words>
-AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first_rule, int k_steps, Sink& sink,
-                          const Vote vote, bool valid, int defer, Words& words)
+// TURNS (the rotating rollout kernel, k_rollout_rotate): the group stops right after its `max_passes`-th end-of-round pass --
+// every game is then between two moves -- and the steps each game still has to take are returned; the caller continues
+// them with another call (k_steps = the returned count: a trajectory does not depend on where it is cut).  Otherwise the
+// call runs to the end and returns 0.
+template <int P, int POOL, bool TURNS = false, typename Sink, typename Vote, typename Words>
+AZB_HD int rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first_rule, int k_steps, Sink& sink,
+                         const Vote vote, bool valid, int defer, Words& words, int max_passes = 0)
 {
     uint32_t rounds = 0;
+    int n_pass = 0;
     int remaining = valid ? k_steps : 0;
     // 0 playing, 1 round over: waits for score + refill, 2 waits for a fresh game (stuck / ended on entry)
     int phase = (remaining > 0 && g.ended()) ? 2 : 0;
@@ -996,11 +1001,13 @@ AZB_HD void rollout_steps(Game<P>& g, const Philox& rng, uint32_t gid, int first
                 words.prefetch(rng, gid, g.steps);                    // the whole warp is here: words for the next round
             }
             sink.pass_done();                                         // every lane of the group is here
+            if (TURNS && ++n_pass >= max_passes) break;
         } else if (n_movable == 0) {
             break;
         }
     }
-    if (valid) { sink.add(0, (uint32_t)k_steps); sink.add(2, rounds); }
+    if (valid) { sink.add(0, (uint32_t)(k_steps - remaining)); sink.add(2, rounds); }
+    return remaining;
 }
 
 // ---- GameRunner.step's opponent loop + reward (game_runner.py:46-52), random-agent opponent ----

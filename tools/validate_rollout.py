@@ -1,5 +1,5 @@
 """Wider one-off check of the fused rollout against the C oracle than the test-suite's: every (players, pool, first-player
-rule), 20,000 games x 400 env steps, records and counters bit-exact.  python tools/validate_rollout.py"""
+rule), 20,000 games x 400 env steps, records and counters bit-exact.  python tools/validate_rollout.py [n_games]"""
 import os
 import sys
 import time
@@ -12,7 +12,7 @@ from oracle import oracle as O  # noqa: E402
 
 
 def main():
-    n, k = 20000, 400
+    n, k = (int(sys.argv[1]) if len(sys.argv) > 1 else 20000), 400     # 65536: one block of 14 game warps + 2 helper warps per SM
     t0 = time.time()
     for players in (2, 3, 4):
         for pool in (0, 1):
