@@ -459,6 +459,16 @@ class Ctx:
             self.torch.distributed.destroy_process_group()
 
 
+def rollout_kernel_name(games, players, pool, sms, tuned):
+    """Which kernel azb_rollout_random picks (csrc/azb.cu): one block per SM whose 32-game batches number 2 mod 4 (65,536 games
+    on 148 SMs: 14) -> the rotating form, two warps more than batches; otherwise one warp per batch for the whole launch."""
+    per_sm = -(-games // sms)
+    k = -(-per_sm // 512)
+    threads = min(512, max(64, -(-(-(-per_sm // k)) // 32) * 32))
+    rotate = (not tuned and per_sm <= 2048 and (threads // 32) % 4 == 2 and threads + 64 <= 512 and -(-games // threads) <= sms)
+    return ("k_rollout_rotate<%d,%d>" if rotate else "k_rollout_random<%d,%d>") % (players, pool)
+
+
 def measure_random(args, ctx, players, games, steps, warmup, e2e=True):
     """configs[1] / configs[2]: azb_rollout_random, K env steps per game per launch, L2 flushed between launches."""
     torch = ctx.torch
@@ -520,7 +530,8 @@ def measure_random(args, ctx, players, games, steps, warmup, e2e=True):
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": profiled("p%d_%s_g%d_k%d" % (players, pool_name, G, K)), "peak_source": peak_src,
             "algorithmic_bytes_per_env_step": b_alg, "env_steps_per_launch": G * K,
-            "kernel": "k_rollout_random<%d,%d>" % (players, ctx.pool),
+            "kernel": rollout_kernel_name(G, players, ctx.pool, torch.cuda.get_device_properties(ctx.dev).multi_processor_count,
+                                          bool(args.block or args.defer)),
             "kernel_ms_avg": dev_ms / steps, "kernel_ms_min": min(kernel_ms)}
     # frac follows the metric's definition (algorithmic bytes of a step-at-a-time simulator / time / measured copy peak); the fused
     # kernel keeps the state in registers for K steps, so the figure is not bounded by 1 -- `traffic` is what DRAM really moved
