@@ -526,12 +526,16 @@ def measure_random(args, ctx, players, games, steps, warmup, e2e=True):
     achieved = b_alg * G * K / ((dev_ms / steps) * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
     pool_name = "lid" if ctx.pool else "random"
-    inst = profiled("inst_per_env_step_p%d_%s" % (players, pool_name)) or profiled("inst_per_env_step_p2_lid")
+    kernel_name = rollout_kernel_name(G, players, ctx.pool, torch.cuda.get_device_properties(ctx.dev).multi_processor_count,
+                                      bool(args.block or args.defer))
+    rot = "_rotate" if "rotate" in kernel_name else ""
+    inst = (profiled("inst_per_env_step_p%d_%s%s" % (players, pool_name, rot)) or profiled("inst_per_env_step_p2_lid" + rot)
+            or profiled("inst_per_env_step_p2_lid"))
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": profiled("p%d_%s_g%d_k%d" % (players, pool_name, G, K)), "peak_source": peak_src,
+            "traffic": profiled("p%d_%s_g%d_k%d%s" % (players, pool_name, G, K, rot)) or profiled("p%d_%s_g%d_k%d" % (players, pool_name, G, K)),
+            "peak_source": peak_src,
             "algorithmic_bytes_per_env_step": b_alg, "env_steps_per_launch": G * K,
-            "kernel": rollout_kernel_name(G, players, ctx.pool, torch.cuda.get_device_properties(ctx.dev).multi_processor_count,
-                                          bool(args.block or args.defer)),
+            "kernel": kernel_name,
             "kernel_ms_avg": dev_ms / steps, "kernel_ms_min": min(kernel_ms)}
     # frac follows the metric's definition (algorithmic bytes of a step-at-a-time simulator / time / measured copy peak); the fused
     # kernel keeps the state in registers for K steps, so the figure is not bounded by 1 -- `traffic` is what DRAM really moved
