@@ -25,6 +25,15 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_every_entry_point_is_documented_for_the_binding():
+    """INTEGRATION.md names every entry point of include/azb.h (the reference function it replaces, or what it answers)."""
+    hdr = open(os.path.join(REPO, "include", "azb.h")).read()
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"^\s*(?:const char\*|int64_t|int)\s+(azb_\w+)\s*\(", hdr, flags=re.M))
+    missing = sorted(n for n in declared if n not in doc)
+    assert not missing, missing
+
+
 def test_sizes(lib):
     assert lib.azb_abi_version() == 1
     for p in (2, 3, 4):
