@@ -550,6 +550,11 @@ def measure_random(args, ctx, players, games, steps, warmup, e2e=True):
         roof.update(issue_frac=(value / world) / issue_peak, issue_peak_env_steps_per_sec=issue_peak,
                     warp_instructions_per_env_step=inst,
                     issue_note="warp instructions per env step from the committed ncu capture; peak = SMs x 4 x sampled SM clock / that")
+    alu = profiled("alu_pipe_pct_p%d_%s_g%d%s" % (players, pool_name, G, rot))
+    if alu:
+        roof.update(alu_pipe_busy_pct_ncu=alu,
+                    alu_note="integer ALU pipe utilisation of this kernel at this batch size in the committed ncu capture "
+                             "(profiles/rollout_traffic.json): the unit closest to its peak, i.e. the kernel's binding pipe")
     return {"value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": dev_ms_max / steps, "e2e": out_e2e, "gpu_launches": steps, "roofline": roof, "clocks": clocks,
             "wall_s": wall, "games_per_sec": (cnt[1] / max(cnt[0], 1)) * value,
@@ -706,7 +711,8 @@ def measure_policy(args, ctx, games, steps, warmup):
                     "d2h_bytes_per_step": host_state.numel() * 4 + 9 * G + host_cnt.numel() * 8, "steps": e2e_steps},
             "gpu_launches": steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback",
+                         "traffic": profiled("policy_p2_%s_g%d_k%d" % ("lid" if ctx.pool else "random", G, K)),
+                         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback",
                          "algorithmic_flop_per_decision": flop, "decisions_per_launch": G * K,
                          "kernel": "pol::k_policy_rollout<%d>" % ctx.pool},
             "clocks": clocks, "decisions_per_sec": value, "games_per_sec": (cnt[1] / max(cnt[0], 1)) * value,
