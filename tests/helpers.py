@@ -123,3 +123,11 @@ def net_from_golden(z, prefix, scale=1.0, device="cpu"):
     net = ActorCritic(136, 180)
     net.load_state_dict({n: torch.from_numpy(z[prefix + n] * np.float32(scale)) for n in PARAM_NAMES})
     return net.to(device)
+
+
+def free_port():
+    """A TCP port nobody listens on right now (rendezvous of the world_size-2 gloo tests on 127.0.0.1)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]

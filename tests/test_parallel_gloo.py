@@ -36,7 +36,8 @@ def test_two_rank_sharding_and_reduction(tmp_path):
     from oracle import oracle as O
     from tests import harness as H
     H.lib(); O.lib()                      # build once before forking
-    n, k, seed, port = 96, 90, 31337, 29533
+    from tests.helpers import free_port
+    n, k, seed, port = 96, 90, 31337, free_port()
     mp.spawn(_worker, args=(2, port, n, k, seed, str(tmp_path)), nprocs=2, join=True)
     whole = O.fresh_records(2 * n, 2, 1, 0, seed, 0)
     cnt = O.rollout_random(whole, 2, 1, 0, seed, 0, k)

@@ -125,7 +125,8 @@ def _worker(rank, world, port, out_dir):
 def test_two_rank_gradient_allreduce_matches_global_batch(tmp_path):
     from azul_deep_reinforcement_learning_b200.azulnet.model import ActorCritic
     from azul_deep_reinforcement_learning_b200.train import a2c_loss_terms
-    mp.spawn(_worker, args=(2, 29577, str(tmp_path)), nprocs=2, join=True)
+    from tests.helpers import free_port
+    mp.spawn(_worker, args=(2, free_port(), str(tmp_path)), nprocs=2, join=True)
     torch.manual_seed(0)
     net = ActorCritic(136, 180)
     parts = [_fake_batch(40, 10), _fake_batch(65, 11)]
@@ -150,7 +151,9 @@ def _flat_worker(rank, world, port, out):
     stats = torch.tensor([10.0 + rank, 1.5 * (rank + 1)], dtype=torch.float64)
     allreduce_flat_and_stats(flat, stats)
     if rank == 0:
-        out.put((flat.clone(), stats.clone()))
+        # by value: a torch tensor in a multiprocessing queue travels as a handle into the SENDER's shared memory, which
+        # is gone if this process exits before the parent has rebuilt it
+        out.put((flat.numpy().copy(), str(flat.dtype), stats.tolist()))
     dist.destroy_process_group()
 
 
@@ -158,17 +161,18 @@ def test_flat_gradient_and_stats_allreduce_two_ranks_gloo():
     """The trainer's collectives (one flat fp32 gradient all-reduce + one float64 statistics all-reduce) on two gloo ranks."""
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29600 + os.getpid() % 200
+    from tests.helpers import free_port
+    port = free_port()
     procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    flat, stats = out.get(timeout=120)
+    flat, flat_dtype, stats = out.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     want = sum(torch.randn(82081, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
-    assert torch.allclose(flat, want) and flat.dtype == torch.float32
-    assert stats.tolist() == [21.0, 4.5]
+    assert torch.allclose(torch.from_numpy(flat), want) and flat_dtype == "torch.float32"
+    assert stats == [21.0, 4.5]
 
 
 def test_saved_networks_load_back_through_agent(tmp_path):
